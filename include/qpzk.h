@@ -1,0 +1,169 @@
+/* qpzk — B200-native (sm_100a) backend for the Plonky2 polynomial-commitment / quotient / FRI hot
+ * path of the qp-wormhole prover, voting circuit and aggregator.
+ *
+ * This is the drop-in boundary: a flat C ABI (plain pointers and sizes) that a `cc`-built Rust
+ * `-sys` crate binds, so that a `[patch.crates-io]` copy of qp-plonky2 1.1.1 can forward the
+ * bodies of the functions below to the GPU while every signature the reference touches stays as it
+ * is. The reference contains no FFI of its own (it calls qp-plonky2 as plain Rust, pinned at
+ * /root/reference/Cargo.lock:489-490), so each entry point cites the qp-plonky2 function whose
+ * body it replaces and the reference call site that reaches it. INTEGRATION.md shows the Rust
+ * bindings.
+ *
+ * Conventions
+ *  - All field elements are u64. Inputs may be any representative (< 2^64); outputs are canonical
+ *    (< p = 2^64 - 2^32 + 1). Extension elements are two consecutive u64 (a + bX, X^2 = 7).
+ *    Hashes / digests are four consecutive u64.
+ *  - Host pointers are borrowed for the duration of the call and never retained; `_dev` entry
+ *    points take device pointers valid on the context's device.
+ *  - Handles own device memory and are released with their *_free function.
+ *  - Every function returns QPZK_OK (0) or a negative qpzk_status; nothing throws or aborts across
+ *    the ABI. `qpzk_last_error` returns a human-readable message for the calling thread.
+ *  - Re-entrant: one qpzk_ctx per calling thread (the aggregator proves chunks concurrently from
+ *    rayon workers, /root/reference/wormhole/aggregator/src/circuits/tree.rs:92-103). A context
+ *    owns one CUDA stream; calls on different contexts overlap on the device.
+ *  - There is NO CPU fallback: if no CUDA device is usable, qpzk_ctx_create fails.
+ */
+#ifndef QPZK_H
+#define QPZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum qpzk_status {
+  QPZK_OK = 0,
+  QPZK_ERR_BAD_ARG = -1,
+  QPZK_ERR_CUDA = -2,
+  QPZK_ERR_OOM = -3,
+  QPZK_ERR_NOT_DIVISIBLE = -4, /* quotient: vanishing polynomial not divisible by Z_H */
+  QPZK_ERR_UNSUPPORTED = -5
+} qpzk_status;
+
+typedef struct qpzk_ctx qpzk_ctx;
+typedef struct qpzk_batch qpzk_batch; /* PolynomialBatch: coefficients + LDE + Merkle tree, on device */
+typedef struct qpzk_tree qpzk_tree;   /* MerkleTree over caller-provided leaves, on device */
+
+#define QPZK_SALT_SIZE 4 /* plonky2 SALT_SIZE: blinding columns appended to each hiding oracle */
+
+/* Stage indices for qpzk_ctx_stage_ms (CUDA-event time of the last commit on this context). */
+enum {
+  QPZK_STAGE_H2D = 0,
+  QPZK_STAGE_IFFT = 1,
+  QPZK_STAGE_LDE = 2,
+  QPZK_STAGE_LEAF_HASH = 3,
+  QPZK_STAGE_MERKLE_LEVELS = 4,
+  QPZK_STAGE_D2H = 5,
+  QPZK_NUM_STAGES = 6
+};
+
+/* ---- context ---- */
+int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out);
+void qpzk_ctx_destroy(qpzk_ctx* ctx);
+const char* qpzk_last_error(void);
+int qpzk_ctx_sync(qpzk_ctx* ctx);
+/* CUDA stream owned by the context (a cudaStream_t), for callers that time with their own events. */
+void* qpzk_ctx_stream(qpzk_ctx* ctx);
+/* Per-stage device time in milliseconds of the most recent commit on this context. */
+int qpzk_ctx_stage_ms(qpzk_ctx* ctx, float* out_ms /* [QPZK_NUM_STAGES] */);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx);
+
+/* Pinned host memory for callers that want full-speed transfers (optional). */
+int qpzk_host_alloc(size_t bytes, void** out);
+void qpzk_host_free(void* p);
+/* Plain device memory helpers (used by the bench harness and tests for the `_dev` entry points). */
+int qpzk_dev_alloc(qpzk_ctx* ctx, size_t bytes, void** out);
+void qpzk_dev_free(qpzk_ctx* ctx, void* p);
+int qpzk_memcpy_h2d(qpzk_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int qpzk_memcpy_d2h(qpzk_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- hashing: PoseidonPermutation / PoseidonHash (qp-plonky2 hash/poseidon.rs, hashing.rs) ----
+ * Reference call sites: /root/reference/wormhole/circuit/src/nullifier.rs:64-65,
+ * /root/reference/wormhole/circuit/src/unspendable_account.rs:54-56. */
+/* n independent permutations of 12-element states, in place. */
+int qpzk_poseidon_permute(qpzk_ctx* ctx, uint64_t* states /* host [n][12] */, uint64_t n);
+/* n independent `hash_no_pad` of `len` elements each (overwrite-mode sponge, rate 8). */
+int qpzk_hash_no_pad(qpzk_ctx* ctx, const uint64_t* inputs /* host [n][len] */, uint64_t n, uint32_t len,
+                     uint64_t* out /* host [n][4] */);
+/* n independent `two_to_one(left, right)` compressions. */
+int qpzk_two_to_one(qpzk_ctx* ctx, const uint64_t* pairs /* host [n][8] */, uint64_t n,
+                    uint64_t* out /* host [n][4] */);
+
+/* ---- MerkleTree::new / prove / cap (qp-plonky2 hash/merkle_tree.rs) ----
+ * Reached from every commit under /root/reference/wormhole/prover/src/lib.rs:233-237 and the FRI
+ * commit phase. Leaves: row-major [nleaves][leaf_len]; nleaves a power of two >= 2^cap_height. */
+int qpzk_merkle_new(qpzk_ctx* ctx, const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len,
+                    uint32_t cap_height, qpzk_tree** out);
+int qpzk_tree_cap(const qpzk_tree* t, uint64_t* out /* [2^cap_height][4] */);
+/* MerkleTree::prove(leaf_index): siblings bottom-up, log2(nleaves) - cap_height of them. */
+int qpzk_tree_prove(const qpzk_tree* t, uint64_t leaf_index, uint64_t* siblings /* [.][4] */);
+/* The `digests` vector in plonky2's interleaved layout, 2*(nleaves - 2^cap_height) hashes. */
+int qpzk_tree_digests(const qpzk_tree* t, uint64_t* out);
+void qpzk_tree_free(qpzk_tree* t);
+
+/* ---- PolynomialBatch (qp-plonky2 fri/oracle.rs) ----
+ * from_values: `PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, ..)`
+ *   = per column IFFT -> LDE on the coset g*<w_N> -> (+ salt columns) -> bit-reversed row-major
+ *   leaves -> MerkleTree::new.  Reached from ProverCircuitData::prove
+ *   (/root/reference/wormhole/prover/src/lib.rs:233-237, wires and Z/partial-product batches) and
+ *   CircuitBuilder::build (/root/reference/wormhole/circuit/src/circuit.rs:98-108, constants|sigmas;
+ *   also /root/reference/wormhole/aggregator/src/circuits/tree.rs:127 and /root/reference/voting/src/lib.rs:355).
+ * from_coeffs: same from coefficient form (quotient chunks, /root/reference/wormhole/prover/src/lib.rs:233-237).
+ * values / coeffs: column-major [ncols][2^degree_bits].
+ * salts: NULL (blinding = false), or column-major [salt_cols][2^(degree_bits+rate_bits)] values in
+ *   natural LDE-domain order — the caller draws them from its RNG (the reference uses an OS RNG;
+ *   injecting them keeps proofs reproducible). */
+int qpzk_batch_from_values(qpzk_ctx* ctx, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                           uint32_t salt_cols, qpzk_batch** out);
+int qpzk_batch_from_coeffs(qpzk_ctx* ctx, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                           uint32_t salt_cols, qpzk_batch** out);
+/* Same, inputs already resident on the context's device (used by the prover pipeline, the
+ * multi-GPU shards and the HBM-resident bench leg). The input buffer is not modified. */
+int qpzk_batch_from_values_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint32_t ncols,
+                               uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                               const uint64_t* salts_dev, uint32_t salt_cols, qpzk_batch** out);
+int qpzk_batch_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t ncols,
+                               uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                               const uint64_t* salts_dev, uint32_t salt_cols, qpzk_batch** out);
+/* Shard of a commit for multi-GPU: only the cap subtrees
+ * [subtree_begin, subtree_end) of the 2^cap_height are evaluated, hashed and reduced; the cap
+ * entries of the other subtrees are left zero for the caller to all-gather. */
+int qpzk_batch_from_values_shard_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint32_t ncols,
+                                     uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                                     const uint64_t* salts_dev, uint32_t salt_cols,
+                                     uint32_t subtree_begin, uint32_t subtree_end, qpzk_batch** out);
+/* `merkle_tree.cap`: [2^cap_height][4]. */
+int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out);
+/* Device pointer to the cap (for NCCL all-gather of subtree roots); 2^cap_height * 4 u64. */
+uint64_t* qpzk_batch_cap_dev(qpzk_batch* b);
+/* `polynomials`: coefficient form, column-major [ncols][n]. */
+int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out);
+/* `get_lde_values(index, step)` for a list of indices: out[i] = leaves[rev(idx[i]*step)][..ncols]
+ * (salt columns stripped), row-major [nidx][ncols]. */
+int qpzk_batch_get_lde_rows(const qpzk_batch* b, const uint32_t* idx, uint32_t nidx, uint32_t step,
+                            uint64_t* out);
+/* `merkle_tree.leaves[leaf_index]` (salted row, ncols + salt_cols wide) and
+ * `merkle_tree.prove(leaf_index)`. Either output may be NULL. */
+int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out, uint64_t* siblings_out);
+/* Full materialisation (compatibility / debugging): `merkle_tree.leaves` row-major
+ * [N][ncols+salt_cols] and `merkle_tree.digests` in plonky2's layout. Either may be NULL. */
+int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests);
+uint32_t qpzk_batch_ncols(const qpzk_batch* b);
+uint32_t qpzk_batch_width(const qpzk_batch* b); /* ncols + salt_cols */
+uint32_t qpzk_batch_degree_bits(const qpzk_batch* b);
+void qpzk_batch_free(qpzk_batch* b);
+
+/* ---- measurement helper: dependency-free integer multiply-add throughput (the Poseidon
+ * roofline denominator). kind 0: 32-bit mad.lo.u32, kind 1: mad.wide.u32.
+ * Returns multiply-adds per second over the whole device. */
+int qpzk_measure_imad_peak(qpzk_ctx* ctx, int kind, double* out_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPZK_H */

@@ -1,0 +1,196 @@
+// Host-side generation of the Poseidon-Goldilocks constant tables uploaded to __constant__ memory.
+//
+// Replaces the constant arrays of `PoseidonGoldilocksConfig` (qp-plonky2 1.1.1, un-vendored;
+// used through `C` at /root/reference/common/src/circuit.rs:10 and directly at
+// /root/reference/wormhole/circuit/src/nullifier.rs:64-65). Nothing is copied: the 360 round
+// constants are re-drawn from ChaCha8 keyed by seed 0 and the sparse ("fast") partial-round
+// factorisation is derived from the circulant MDS matrix here, in the transposed (row-vector)
+// formulation. Runs once per context; never on the data path.
+#pragma once
+#include <cstring>
+#include <vector>
+
+#include "gl.cuh"
+
+namespace qpzk {
+
+struct PoseidonTablesHost {
+  u64 rc[360];
+  u64 fast_first[12];
+  u64 fast_rc[22];
+  u64 fast_init[121];  // [r-1][c-1], out[c] += in[r] * init
+  u64 fast_w_hat[242]; // [round][i-1]
+  u64 fast_v[242];     // [round][i-1]
+};
+
+static const u64 kMdsCirc[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const u64 kMdsDiag0 = 8;
+
+namespace detail {
+
+// Keystream of ChaCha with 8 rounds, 64-bit block counter, zero nonce.
+class ChaCha8Stream {
+ public:
+  explicit ChaCha8Stream(u64 seed) {
+    // rand_core::SeedableRng::seed_from_u64: PCG32 output function over an LCG
+    u64 s = seed;
+    for (int w = 0; w < 8; w++) {
+      s = s * 6364136223846793005ULL + 11634580027462260723ULL;
+      u32 x = (u32)(((s >> 18) ^ s) >> 27);
+      u32 r = (u32)(s >> 59);
+      key_[w] = (x >> r) | (x << ((32u - r) & 31u));
+    }
+  }
+  u64 next64() {
+    u64 lo = next32();
+    u64 hi = next32();
+    return lo | (hi << 32);
+  }
+
+ private:
+  u32 key_[8];
+  u64 block_ = 0;
+  u32 out_[16];
+  int pos_ = 16;
+  static u32 rol(u32 v, int n) { return (v << n) | (v >> (32 - n)); }
+  static void quarter(u32* x, int a, int b, int c, int d) {
+    x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 16);
+    x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 12);
+    x[a] += x[b]; x[d] = rol(x[d] ^ x[a], 8);
+    x[c] += x[d]; x[b] = rol(x[b] ^ x[c], 7);
+  }
+  u32 next32() {
+    if (pos_ == 16) {
+      u32 in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+      memcpy(in + 4, key_, sizeof key_);
+      in[12] = (u32)block_;
+      in[13] = (u32)(block_ >> 32);
+      in[14] = in[15] = 0;
+      u32 x[16];
+      memcpy(x, in, sizeof x);
+      for (int dr = 0; dr < 4; dr++) {
+        quarter(x, 0, 4, 8, 12); quarter(x, 1, 5, 9, 13); quarter(x, 2, 6, 10, 14); quarter(x, 3, 7, 11, 15);
+        quarter(x, 0, 5, 10, 15); quarter(x, 1, 6, 11, 12); quarter(x, 2, 7, 8, 13); quarter(x, 3, 4, 9, 14);
+      }
+      for (int i = 0; i < 16; i++) out_[i] = x[i] + in[i];
+      block_++;
+      pos_ = 0;
+    }
+    return out_[pos_++];
+  }
+};
+
+// Flat row-major square matrices mod p.
+typedef std::vector<u64> Mx;
+static inline Mx mx_mul(const Mx& A, const Mx& B, int n) {
+  Mx C((size_t)n * n, 0);
+  for (int i = 0; i < n; i++)
+    for (int k = 0; k < n; k++) {
+      u64 a = A[i * n + k];
+      if (!a) continue;
+      for (int j = 0; j < n; j++) C[i * n + j] = glh::add(C[i * n + j], glh::mul(a, B[k * n + j]));
+    }
+  return C;
+}
+static inline Mx mx_inv(Mx A, int n) {  // Gauss-Jordan
+  Mx R((size_t)n * n, 0);
+  for (int i = 0; i < n; i++) R[i * n + i] = 1;
+  for (int col = 0; col < n; col++) {
+    int p = col;
+    while (A[p * n + col] == 0) p++;
+    for (int j = 0; j < n; j++) {
+      std::swap(A[p * n + j], A[col * n + j]);
+      std::swap(R[p * n + j], R[col * n + j]);
+    }
+    u64 s = glh::inv(A[col * n + col]);
+    for (int j = 0; j < n; j++) {
+      A[col * n + j] = glh::mul(A[col * n + j], s);
+      R[col * n + j] = glh::mul(R[col * n + j], s);
+    }
+    for (int r = 0; r < n; r++) {
+      u64 f = A[r * n + col];
+      if (r == col || !f) continue;
+      for (int j = 0; j < n; j++) {
+        A[r * n + j] = glh::sub(A[r * n + j], glh::mul(f, A[col * n + j]));
+        R[r * n + j] = glh::sub(R[r * n + j], glh::mul(f, R[col * n + j]));
+      }
+    }
+  }
+  return R;
+}
+
+}  // namespace detail
+
+static inline void build_poseidon_tables(PoseidonTablesHost* T) {
+  using namespace detail;
+  typedef unsigned __int128 u128;
+  // 360 x gen_range(0..p) (rand 0.8 widening-multiply rejection sampling; zone = p - 1)
+  ChaCha8Stream rng(0);
+  for (int i = 0; i < 360; i++) {
+    for (;;) {
+      u128 m = (u128)rng.next64() * GL_P;
+      if ((u64)m <= GL_P - 1) {
+        T->rc[i] = (u64)(m >> 64);
+        break;
+      }
+    }
+  }
+  // Transposed MDS: row-vector convention, new_row = state_row * Mt, Mt[c][r] = circ[(c - r) mod 12].
+  const int W = 12;
+  Mx Mt(W * W);
+  for (int r = 0; r < W; r++)
+    for (int c = 0; c < W; c++)
+      Mt[c * W + r] = kMdsCirc[((c - r) % W + W) % W] + ((r == c && r == 0) ? kMdsDiag0 : 0);
+  Mx M(W * W);
+  for (int r = 0; r < W; r++)
+    for (int c = 0; c < W; c++) M[r * W + c] = Mt[c * W + r];
+  Mx Minv = mx_inv(M, W);
+
+  // Equivalent round constants for the 22 partial rounds (rounds 4..25).
+  u64 c[30][12];
+  memcpy(c, T->rc, sizeof c);
+  for (int i = 24; i >= 4; i--) {
+    u64 t[12];
+    for (int r = 0; r < W; r++) {
+      u64 s = 0;
+      for (int k = 0; k < W; k++) s = glh::add(s, glh::mul(Minv[r * W + k], c[i + 1][k]));
+      t[r] = s;
+    }
+    for (int k = 1; k < W; k++) c[i][k] = glh::add(c[i][k], t[k]);
+    memset(c[i + 1], 0, sizeof c[i + 1]);
+    c[i + 1][0] = t[0];
+  }
+  memcpy(T->fast_first, c[4], sizeof T->fast_first);
+  for (int r = 0; r < 22; r++) T->fast_rc[r] = r < 21 ? c[5 + r][0] : 0;
+
+  // Sparse factorisation, walking the rounds backwards.
+  Mx Mmul = Mt;
+  for (int i = 21; i >= 0; i--) {
+    Mx Mhat(11 * 11), w(11), v(11);
+    for (int a = 0; a < 11; a++) {
+      for (int b = 0; b < 11; b++) Mhat[a * 11 + b] = Mmul[(a + 1) * W + (b + 1)];
+      w[a] = Mmul[(a + 1) * W + 0];
+      v[a] = Mmul[0 * W + (a + 1)];
+    }
+    Mx MhatInv = mx_inv(Mhat, 11);
+    for (int a = 0; a < 11; a++) {
+      u64 s = 0;
+      for (int b = 0; b < 11; b++) s = glh::add(s, glh::mul(MhatInv[a * 11 + b], w[b]));
+      T->fast_w_hat[i * 11 + a] = s;
+      T->fast_v[i * 11 + a] = v[a];
+    }
+    Mx Mi(W * W, 0);
+    Mi[0] = 1;
+    for (int a = 0; a < 11; a++)
+      for (int b = 0; b < 11; b++) Mi[(a + 1) * W + (b + 1)] = Mhat[a * 11 + b];
+    if (i > 0) {
+      Mmul = mx_mul(Mt, Mi, W);
+    } else {
+      // state_row * Mi is applied before the first partial round
+      for (int a = 0; a < 11; a++)
+        for (int b = 0; b < 11; b++) T->fast_init[a * 11 + b] = Mhat[a * 11 + b];
+    }
+  }
+}
+
+}  // namespace qpzk

@@ -1,0 +1,738 @@
+// libqpzk: C ABI (include/qpzk.h) over the sm_100a kernels. Unity build: the kernels share the
+// Poseidon tables in __constant__ memory, so everything is one translation unit.
+//
+// Host-side orchestration that replaces the bodies of `PolynomialBatch::from_values /
+// from_coeffs`, `MerkleTree::new / prove` (qp-plonky2 1.1.1 fri/oracle.rs, hash/merkle_tree.rs),
+// reached from /root/reference/wormhole/prover/src/lib.rs:233-237 and
+// /root/reference/wormhole/circuit/src/circuit.rs:98-108. There is no CPU fallback anywhere in
+// this file: every entry point either runs the CUDA path or returns an error.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/qpzk.h"
+#include "gl.cuh"
+#include "merkle.cuh"
+#include "ntt.cuh"
+#include "poseidon.cuh"
+#include "poseidon_tables.hpp"
+
+using namespace qpzk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(x)                                                                               \
+  do {                                                                                      \
+    cudaError_t e_ = (x);                                                                   \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(e_ == cudaErrorMemoryAllocation ? QPZK_ERR_OOM : QPZK_ERR_CUDA,           \
+                  std::string(#x) + ": " + cudaGetErrorString(e_));                         \
+  } while (0)
+#define QP(x)             \
+  do {                    \
+    int r_ = (x);         \
+    if (r_ != QPZK_OK) return r_; \
+  } while (0)
+
+struct TabKey {
+  int k;
+  bool inverse;
+  bool operator<(const TabKey& o) const { return k != o.k ? k < o.k : inverse < o.inverse; }
+};
+
+struct qpzk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[QPZK_NUM_STAGES + 1];
+  float stage_ms[QPZK_NUM_STAGES] = {0};
+  uint64_t launches = 0;
+  int sm_count = 148;
+  std::map<TabKey, std::pair<u64*, u64*>> root_tabs;   // (lo, hi)
+  std::map<std::pair<int, int>, u64*> coset_pm;          // (k, r) -> pm[2^r][2^k]
+  u64* scratch_path = nullptr;                           // small device scratch for openings
+};
+
+struct qpzk_batch {
+  qpzk_ctx* ctx;
+  uint32_t ncols, salt_cols, degree_bits, rate_bits, cap_height;
+  u64* coeffs = nullptr;   // [ncols][n]
+  u64* lde = nullptr;      // [ncols+salt_cols][N], bit-reversed row order
+  u64* levels = nullptr;   // digest levels, 2N*4 u64
+  uint32_t log_N() const { return degree_bits + rate_bits; }
+  uint32_t width() const { return ncols + salt_cols; }
+};
+
+struct qpzk_tree {
+  qpzk_ctx* ctx;
+  uint32_t log_n, cap_height, leaf_len;
+  u64* levels = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------
+static int dev_alloc(qpzk_ctx* c, size_t bytes, u64** out) {
+  void* p = nullptr;
+  CU(cudaMallocAsync(&p, bytes ? bytes : 8, c->stream));
+  *out = (u64*)p;
+  return QPZK_OK;
+}
+static void dev_free(qpzk_ctx* c, void* p) {
+  if (p) cudaFreeAsync(p, c->stream);
+}
+
+static int get_root_tab(qpzk_ctx* c, int k, bool inverse, RootTab* out) {
+  TabKey key{k, inverse};
+  auto it = c->root_tabs.find(key);
+  int lk = (k + 1) / 2;
+  if (it == c->root_tabs.end()) {
+    u64 root = glh::root_of_unity(k);
+    if (inverse) root = glh::inv(root);
+    u64 *lo, *hi;
+    QP(dev_alloc(c, sizeof(u64) << lk, &lo));
+    QP(dev_alloc(c, sizeof(u64) << (k - lk), &hi));
+    u64 cnt = (u64)1 << lk;
+    k_build_root_tab<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(lo, hi, root, k, lk);
+    c->launches++;
+    CU(cudaGetLastError());
+    it = c->root_tabs.emplace(key, std::make_pair(lo, hi)).first;
+  }
+  out->lo = it->second.first;
+  out->hi = it->second.second;
+  out->k = k;
+  out->lk = lk;
+  return QPZK_OK;
+}
+
+static int get_coset_pm(qpzk_ctx* c, int k, int r, const u64** out) {
+  auto key = std::make_pair(k, r);
+  auto it = c->coset_pm.find(key);
+  if (it == c->coset_pm.end()) {
+    u64* pm;
+    u64 cnt = (u64)1 << (k + r);
+    QP(dev_alloc(c, cnt * sizeof(u64), &pm));
+    u64 wN = glh::root_of_unity(k + r);
+    k_build_coset_pm<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(pm, wN, k, r);
+    c->launches++;
+    CU(cudaGetLastError());
+    it = c->coset_pm.emplace(key, pm).first;
+  }
+  *out = it->second;
+  return QPZK_OK;
+}
+
+// Batched n-point transforms. flavour LDE: src natural -> dst DIF order per coset (ncosets = 2^r,
+// coset pre-multipliers applied). flavour IFFT: src natural values -> dst natural coefficients.
+static const int kSmallMaxLog = 12;
+static const u32 kTileElems = 4096;
+
+static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride,
+                      u32 ncols, int k, int r) {
+  if (ncols == 0) return QPZK_OK;
+  RootTab tab;
+  QP(get_root_tab(c, k, false, &tab));
+  const u64* pm;
+  QP(get_coset_pm(c, k, r, &pm));
+  u32 ncosets = 1u << r;
+  if (k <= kSmallMaxLog) {
+    size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
+    k_ntt_small<false><<<dim3(ncols, ncosets), 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride,
+                                                                       pm, tab, k, r, 1);
+    c->launches++;
+  } else {
+    if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
+    int a = (k + 1) / 2;
+    if (a > 8) a = 8;
+    int b = k - a;
+    u32 cols = 16;
+    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
+    k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
+        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols);
+    u32 rows = kTileElems >> b;
+    if (rows < 1) rows = 1;
+    if (rows > (1u << a)) rows = 1u << a;
+    size_t smem_b = ((size_t)rows * (1u << b) + (1u << b) / 2) * 8;
+    k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k,
+                                                                                         a, r, rows);
+    c->launches += 2;
+  }
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+
+static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coeffs, u64 dst_stride,
+                       u32 ncols, int k) {
+  if (ncols == 0) return QPZK_OK;
+  RootTab tab;
+  QP(get_root_tab(c, k, true, &tab));
+  u64 ninv = glh::inv(((u64)1 << k) % GL_P);
+  if (k <= kSmallMaxLog) {
+    size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
+    k_ntt_small<true><<<dim3(ncols, 1), 256, smem, c->stream>>>(values, src_stride, coeffs, dst_stride, nullptr,
+                                                                tab, k, 0, ninv);
+    c->launches++;
+  } else {
+    if (k > 18) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 18 not supported");
+    int a = (k + 1) / 2, b = k - a;
+    u32 cols = a <= 8 ? 16 : 8;
+    u32 rc = b <= 8 ? 16 : 8;
+    u64* tmp;
+    QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
+    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
+    k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
+        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols);
+    size_t smem_b = ((size_t)rc * ((1u << b) + 1) + (1u << b) / 2) * 8;
+    k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs,
+                                                                                    dst_stride, tab, k, a, rc, ninv);
+    c->launches += 2;
+    dev_free(c, tmp);
+  }
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+
+// Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
+static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u32 log_n, u32 cap_height,
+                      u64* levels, cudaEvent_t after_leaves) {
+  u64 N = (u64)1 << log_n;
+  k_leaf_hash<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(src, rs, cs, width, N, levels);
+  c->launches++;
+  CU(cudaGetLastError());
+  if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
+  u64 twoN = 2 * N;
+  for (u32 l = 0; l < log_n - cap_height; l++) {
+    u64 nout = N >> (l + 1);
+    const u64* in = levels + (twoN - (twoN >> l)) * 4;
+    u64* out = levels + (twoN - (twoN >> (l + 1))) * 4;
+    k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
+    c->launches++;
+  }
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+
+static const u64* cap_ptr(const u64* levels, u32 log_n, u32 cap_height) {
+  u64 twoN = (u64)2 << log_n;
+  return levels + (twoN - (twoN >> (log_n - cap_height))) * 4;
+}
+
+// ---- integer multiply-add peak ----
+template <int KIND>
+__global__ void k_imad_peak(u64* out, int iters, u32 seed) {
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  u64 acc[8];
+  u32 acc32[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    acc[i] = i + a;
+    acc32[i] = i + b;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (KIND == 0) {
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc32[i]) : "r"(a), "r"(b));
+      } else {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
+      }
+    }
+  }
+  u64 s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i] + acc32[i];
+  if (s == 0x123456789ULL) out[0] = s;  // keep the chains alive
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* qpzk_last_error(void) { return g_err.c_str(); }
+
+int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
+  (void)flags;
+  if (!out) return fail(QPZK_ERR_BAD_ARG, "out is NULL");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(QPZK_ERR_BAD_ARG, "no such CUDA device (there is no CPU fallback)");
+  CU(cudaSetDevice(device));
+  qpzk_ctx* c = new qpzk_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (auto& e : c->ev) CU(cudaEventCreate(&e));
+  // keep freed blocks in the pool: commits allocate and release hundreds of MB per call
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thresh = ~0ull;
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  // Poseidon tables -> __constant__ (same values for every context; the copy is idempotent)
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    static PoseidonTablesHost* T = nullptr;
+    if (!T) {
+      T = new PoseidonTablesHost();
+      build_poseidon_tables(T);
+    }
+    CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
+    CU(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
+    CU(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
+    CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
+    CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
+    CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
+  }
+  QP(dev_alloc(c, 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return QPZK_OK;
+}
+
+void qpzk_ctx_destroy(qpzk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->root_tabs) {
+    dev_free(c, kv.second.first);
+    dev_free(c, kv.second.second);
+  }
+  for (auto& kv : c->coset_pm) dev_free(c, kv.second);
+  dev_free(c, c->scratch_path);
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int qpzk_ctx_sync(qpzk_ctx* c) {
+  if (!c) return fail(QPZK_ERR_BAD_ARG, "ctx is NULL");
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+void* qpzk_ctx_stream(qpzk_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t qpzk_ctx_launch_count(const qpzk_ctx* c) { return c ? c->launches : 0; }
+int qpzk_ctx_stage_ms(qpzk_ctx* c, float* out_ms) {
+  if (!c || !out_ms) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  memcpy(out_ms, c->stage_ms, sizeof c->stage_ms);
+  return QPZK_OK;
+}
+
+void* qpzk_poseidon_tables_host(void) {  // test hook: the generated tables (PoseidonTablesHost*)
+  static PoseidonTablesHost T;
+  static bool done = false;
+  if (!done) {
+    build_poseidon_tables(&T);
+    done = true;
+  }
+  return &T;
+}
+
+int qpzk_host_alloc(size_t bytes, void** out) {
+  CU(cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault));
+  return QPZK_OK;
+}
+void qpzk_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int qpzk_dev_alloc(qpzk_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  u64* p;
+  QP(dev_alloc(c, bytes, &p));
+  *out = p;
+  return QPZK_OK;
+}
+void qpzk_dev_free(qpzk_ctx* c, void* p) {
+  if (c) dev_free(c, p);
+}
+int qpzk_memcpy_h2d(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+int qpzk_memcpy_d2h(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+// ---- hashing ----
+int qpzk_poseidon_permute(qpzk_ctx* c, uint64_t* states, uint64_t n) {
+  if (!c || (!states && n)) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (!n) return QPZK_OK;
+  CU(cudaSetDevice(c->device));
+  u64* d;
+  QP(dev_alloc(c, n * 96, &d));
+  CU(cudaMemcpyAsync(d, states, n * 96, cudaMemcpyHostToDevice, c->stream));
+  k_permute<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d, n);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(states, d, n * 96, cudaMemcpyDeviceToHost, c->stream));
+  dev_free(c, d);
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+int qpzk_hash_no_pad(qpzk_ctx* c, const uint64_t* inputs, uint64_t n, uint32_t len, uint64_t* out) {
+  if (!c || !inputs || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (!n) return QPZK_OK;
+  if (len == 0) return fail(QPZK_ERR_BAD_ARG, "len must be > 0");
+  CU(cudaSetDevice(c->device));
+  u64 *din, *dout;
+  QP(dev_alloc(c, n * len * 8, &din));
+  QP(dev_alloc(c, n * 32, &dout));
+  CU(cudaMemcpyAsync(din, inputs, n * len * 8, cudaMemcpyHostToDevice, c->stream));
+  k_hash_no_pad<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din, n, len, dout);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
+  dev_free(c, din);
+  dev_free(c, dout);
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+int qpzk_two_to_one(qpzk_ctx* c, const uint64_t* pairs, uint64_t n, uint64_t* out) {
+  if (!c || !pairs || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (!n) return QPZK_OK;
+  CU(cudaSetDevice(c->device));
+  u64 *din, *dout;
+  QP(dev_alloc(c, n * 64, &din));
+  QP(dev_alloc(c, n * 32, &dout));
+  CU(cudaMemcpyAsync(din, pairs, n * 64, cudaMemcpyHostToDevice, c->stream));
+  k_merkle_level<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din, dout, n);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
+  dev_free(c, din);
+  dev_free(c, dout);
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+// ---- MerkleTree ----
+static bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static uint32_t ilog2(uint64_t x) {
+  uint32_t k = 0;
+  while (((uint64_t)1 << k) < x) k++;
+  return k;
+}
+
+int qpzk_merkle_new(qpzk_ctx* c, const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len,
+                    uint32_t cap_height, qpzk_tree** out) {
+  if (!c || !leaves || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (!is_pow2(nleaves)) return fail(QPZK_ERR_BAD_ARG, "nleaves must be a power of two");
+  uint32_t log_n = ilog2(nleaves);
+  if (cap_height > log_n)
+    return fail(QPZK_ERR_BAD_ARG, "cap_height must be at most log2(nleaves)");  // plonky2 asserts the same
+  CU(cudaSetDevice(c->device));
+  qpzk_tree* t = new qpzk_tree();
+  t->ctx = c;
+  t->log_n = log_n;
+  t->cap_height = cap_height;
+  t->leaf_len = leaf_len;
+  u64* dl = nullptr;
+  int rc = dev_alloc(c, nleaves * (leaf_len ? leaf_len : 1) * 8, &dl);
+  if (rc == QPZK_OK) rc = dev_alloc(c, nleaves * 2 * 32, &t->levels);
+  if (rc != QPZK_OK) {
+    dev_free(c, dl);
+    delete t;
+    return rc;
+  }
+  CU(cudaMemcpyAsync(dl, leaves, nleaves * leaf_len * 8, cudaMemcpyHostToDevice, c->stream));
+  QP(build_tree(c, dl, leaf_len, 1, leaf_len, log_n, cap_height, t->levels, nullptr));
+  dev_free(c, dl);
+  CU(cudaStreamSynchronize(c->stream));
+  *out = t;
+  return QPZK_OK;
+}
+
+int qpzk_tree_cap(const qpzk_tree* t, uint64_t* out) {
+  if (!t || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(t->ctx->device));
+  CU(cudaMemcpyAsync(out, cap_ptr(t->levels, t->log_n, t->cap_height), ((size_t)32) << t->cap_height,
+                     cudaMemcpyDeviceToHost, t->ctx->stream));
+  CU(cudaStreamSynchronize(t->ctx->stream));
+  return QPZK_OK;
+}
+
+static int prove_from_levels(qpzk_ctx* c, const u64* levels, u32 log_n, u32 cap_height, u64 leaf,
+                             uint64_t* siblings) {
+  u32 L = log_n - cap_height;
+  if (L == 0) return QPZK_OK;
+  if (L > 64) return fail(QPZK_ERR_BAD_ARG, "tree too deep");
+  k_gather_path<<<1, 256, 0, c->stream>>>(levels, log_n, cap_height, leaf, c->scratch_path);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(siblings, c->scratch_path, (size_t)L * 32, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+int qpzk_tree_prove(const qpzk_tree* t, uint64_t leaf_index, uint64_t* siblings) {
+  if (!t || !siblings) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (leaf_index >> t->log_n) return fail(QPZK_ERR_BAD_ARG, "leaf_index out of range");
+  CU(cudaSetDevice(t->ctx->device));
+  return prove_from_levels(t->ctx, t->levels, t->log_n, t->cap_height, leaf_index, siblings);
+}
+
+static int export_digests(qpzk_ctx* c, const u64* levels, u32 log_n, u32 cap_height, uint64_t* out) {
+  u64 total = ((u64)2 << log_n) - ((u64)2 << cap_height);
+  if (!total) return QPZK_OK;
+  u64* d;
+  QP(dev_alloc(c, total * 32, &d));
+  k_export_digests<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(levels, log_n, cap_height, d);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, d, total * 32, cudaMemcpyDeviceToHost, c->stream));
+  dev_free(c, d);
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+
+int qpzk_tree_digests(const qpzk_tree* t, uint64_t* out) {
+  if (!t || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(t->ctx->device));
+  return export_digests(t->ctx, t->levels, t->log_n, t->cap_height, out);
+}
+
+void qpzk_tree_free(qpzk_tree* t) {
+  if (!t) return;
+  cudaSetDevice(t->ctx->device);
+  dev_free(t->ctx, t->levels);
+  delete t;
+}
+
+// ---- PolynomialBatch ----
+static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is_coeffs, uint32_t ncols,
+                       uint32_t k, uint32_t r, uint32_t cap_height, const uint64_t* salts, bool salts_host,
+                       uint32_t salt_cols, qpzk_batch** out) {
+  if (!c || !in || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (ncols == 0) return fail(QPZK_ERR_BAD_ARG, "ncols must be > 0");
+  if (!salts) salt_cols = 0;
+  if (k + r > 30) return fail(QPZK_ERR_UNSUPPORTED, "LDE domain too large");
+  if (cap_height > k + r) return fail(QPZK_ERR_BAD_ARG, "cap_height must be at most degree_bits + rate_bits");
+  CU(cudaSetDevice(c->device));
+  const u64 n = (u64)1 << k, N = n << r;
+  const u32 width = ncols + salt_cols;
+  qpzk_batch* b = new qpzk_batch();
+  b->ctx = c;
+  b->ncols = ncols;
+  b->salt_cols = salt_cols;
+  b->degree_bits = k;
+  b->rate_bits = r;
+  b->cap_height = cap_height;
+  u64 *staging = nullptr, *salt_staging = nullptr;
+  auto cleanup = [&](int rc) {
+    dev_free(c, staging);
+    dev_free(c, salt_staging);
+    dev_free(c, b->coeffs);
+    dev_free(c, b->lde);
+    dev_free(c, b->levels);
+    delete b;
+    return rc;
+  };
+  int rc;
+  if ((rc = dev_alloc(c, (size_t)ncols * n * 8, &b->coeffs)) != QPZK_OK) return cleanup(rc);
+  if ((rc = dev_alloc(c, (size_t)width * N * 8, &b->lde)) != QPZK_OK) return cleanup(rc);
+  if ((rc = dev_alloc(c, (size_t)N * 2 * 32, &b->levels)) != QPZK_OK) return cleanup(rc);
+
+  cudaEvent_t* ev = c->ev;
+  CU(cudaEventRecord(ev[0], c->stream));
+  const u64* src = in;
+  if (in_is_host) {
+    u64* dstp = is_coeffs ? b->coeffs : nullptr;
+    if (!is_coeffs) {
+      if ((rc = dev_alloc(c, (size_t)ncols * n * 8, &staging)) != QPZK_OK) return cleanup(rc);
+      dstp = staging;
+    }
+    CU(cudaMemcpyAsync(dstp, in, (size_t)ncols * n * 8, cudaMemcpyHostToDevice, c->stream));
+    src = dstp;
+  } else if (is_coeffs) {
+    CU(cudaMemcpyAsync(b->coeffs, in, (size_t)ncols * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    src = b->coeffs;
+  }
+  const u64* salt_src = salts;
+  if (salt_cols && salts_host) {
+    if ((rc = dev_alloc(c, (size_t)salt_cols * N * 8, &salt_staging)) != QPZK_OK) return cleanup(rc);
+    CU(cudaMemcpyAsync(salt_staging, salts, (size_t)salt_cols * N * 8, cudaMemcpyHostToDevice, c->stream));
+    salt_src = salt_staging;
+  }
+  CU(cudaEventRecord(ev[1], c->stream));
+  if (!is_coeffs) {
+    if ((rc = launch_ifft(c, src, n, b->coeffs, n, ncols, (int)k)) != QPZK_OK) return cleanup(rc);
+  }
+  CU(cudaEventRecord(ev[2], c->stream));
+  if ((rc = launch_lde(c, b->coeffs, n, b->lde, N, ncols, (int)k, (int)r)) != QPZK_OK) return cleanup(rc);
+  if (salt_cols) {
+    k_bitrev_rows<<<dim3((unsigned)((N + 255) / 256), salt_cols), 256, 0, c->stream>>>(
+        salt_src, b->lde + (size_t)ncols * N, (int)(k + r), salt_cols);
+    c->launches++;
+  }
+  CU(cudaEventRecord(ev[3], c->stream));
+  if ((rc = build_tree(c, b->lde, 1, N, width, k + r, cap_height, b->levels, ev[4])) != QPZK_OK) return cleanup(rc);
+  CU(cudaEventRecord(ev[5], c->stream));
+  dev_free(c, staging);
+  dev_free(c, salt_staging);
+  staging = salt_staging = nullptr;
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
+  c->stage_ms[QPZK_STAGE_D2H] = 0;
+  *out = b;
+  return QPZK_OK;
+}
+
+int qpzk_batch_from_values(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts, uint32_t salt_cols,
+                           qpzk_batch** out) {
+  return commit_impl(c, values, true, false, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out);
+}
+int qpzk_batch_from_coeffs(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts, uint32_t salt_cols,
+                           qpzk_batch** out) {
+  return commit_impl(c, coeffs, true, true, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out);
+}
+int qpzk_batch_from_values_dev(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
+                               uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                               uint32_t salt_cols, qpzk_batch** out) {
+  return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out);
+}
+int qpzk_batch_from_coeffs_dev(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
+                               uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                               uint32_t salt_cols, qpzk_batch** out) {
+  return commit_impl(c, coeffs, false, true, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out);
+}
+int qpzk_batch_from_values_shard_dev(qpzk_ctx*, const uint64_t*, uint32_t, uint32_t, uint32_t, uint32_t,
+                                     const uint64_t*, uint32_t, uint32_t, uint32_t, qpzk_batch**) {
+  return fail(QPZK_ERR_UNSUPPORTED, "sharded commit not built yet");
+}
+
+int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out) {
+  if (!b || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaMemcpyAsync(out, cap_ptr(b->levels, b->log_N(), b->cap_height), ((size_t)32) << b->cap_height,
+                     cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stage_ms[QPZK_STAGE_D2H], c->ev[0], c->ev[1]);
+  return QPZK_OK;
+}
+uint64_t* qpzk_batch_cap_dev(qpzk_batch* b) {
+  return b ? const_cast<u64*>(cap_ptr(b->levels, b->log_N(), b->cap_height)) : nullptr;
+}
+int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out) {
+  if (!b || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(b->ctx->device));
+  CU(cudaMemcpyAsync(out, b->coeffs, ((size_t)b->ncols << b->degree_bits) * 8, cudaMemcpyDeviceToHost,
+                     b->ctx->stream));
+  CU(cudaStreamSynchronize(b->ctx->stream));
+  return QPZK_OK;
+}
+int qpzk_batch_get_lde_rows(const qpzk_batch* b, const uint32_t* idx, uint32_t nidx, uint32_t step,
+                            uint64_t* out) {
+  if (!b || !idx || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (!nidx) return QPZK_OK;
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  u64 N = (u64)1 << b->log_N();
+  for (uint32_t i = 0; i < nidx; i++)
+    if ((u64)idx[i] * step >= N) return fail(QPZK_ERR_BAD_ARG, "index*step out of range");
+  u64 *didx, *dout;
+  QP(dev_alloc(c, (size_t)nidx * 4, &didx));
+  QP(dev_alloc(c, (size_t)nidx * b->ncols * 8, &dout));
+  CU(cudaMemcpyAsync(didx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream));
+  k_gather_rows<<<nidx, 128, 0, c->stream>>>(b->lde, (int)b->log_N(), (const u32*)didx, nidx, step, b->ncols, dout);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout, (size_t)nidx * b->ncols * 8, cudaMemcpyDeviceToHost, c->stream));
+  dev_free(c, didx);
+  dev_free(c, dout);
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
+}
+int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out, uint64_t* siblings_out) {
+  if (!b) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (leaf_index >> b->log_N()) return fail(QPZK_ERR_BAD_ARG, "leaf_index out of range");
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  if (leaf_out) {
+    if (b->width() > 4096) return fail(QPZK_ERR_UNSUPPORTED, "row too wide");
+    u64* row = c->scratch_path + 64 * 4;
+    k_gather_leaf<<<1, 128, 0, c->stream>>>(b->lde, (u64)1 << b->log_N(), leaf_index, b->width(), row);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(leaf_out, row, (size_t)b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (siblings_out) return prove_from_levels(c, b->levels, b->log_N(), b->cap_height, leaf_index, siblings_out);
+  return QPZK_OK;
+}
+int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests) {
+  if (!b) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  u64 N = (u64)1 << b->log_N();
+  if (leaves) {
+    u64* rows;
+    QP(dev_alloc(c, (size_t)N * b->width() * 8, &rows));
+    dim3 grid((unsigned)((N + 31) / 32), (b->width() + 31) / 32);
+    k_transpose_to_rows<<<grid, dim3(32, 8), 0, c->stream>>>(b->lde, rows, N, b->width());
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(leaves, rows, (size_t)N * b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
+    dev_free(c, rows);
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (digests) return export_digests(c, b->levels, b->log_N(), b->cap_height, digests);
+  return QPZK_OK;
+}
+uint32_t qpzk_batch_ncols(const qpzk_batch* b) { return b ? b->ncols : 0; }
+uint32_t qpzk_batch_width(const qpzk_batch* b) { return b ? b->width() : 0; }
+uint32_t qpzk_batch_degree_bits(const qpzk_batch* b) { return b ? b->degree_bits : 0; }
+void qpzk_batch_free(qpzk_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  dev_free(b->ctx, b->coeffs);
+  dev_free(b->ctx, b->lde);
+  dev_free(b->ctx, b->levels);
+  delete b;
+}
+
+int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
+  if (!c || !out_ops_per_s) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  u64* d;
+  QP(dev_alloc(c, 64, &d));
+  const int iters = 4096, threads = 256;
+  const int blocks = c->sm_count * 8;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (kind == 0)
+      k_imad_peak<0><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep);
+    else
+      k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep);
+    c->launches++;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  dev_free(c, d);
+  double ops = (double)blocks * threads * iters * 8;
+  *out_ops_per_s = ops / (best * 1e-3);
+  return QPZK_OK;
+}
+
+}  // extern "C"

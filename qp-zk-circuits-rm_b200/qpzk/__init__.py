@@ -1,0 +1,364 @@
+"""qpzk — host-side mirror of the plonky2 commitment API over the sm_100a C ABI (include/qpzk.h).
+
+The reference is Rust and there is no Rust toolchain in this image, so this Python layer plays the
+role the patched `qp-plonky2` crate plays in production: it keeps the names and
+argument meaning of the functions whose bodies move to the GPU —
+`PolynomialBatch::{from_values, from_coeffs, get_lde_values}`, `MerkleTree::{new, prove, cap}`,
+`PoseidonHash::{hash_no_pad, two_to_one}` (qp-plonky2 1.1.1, reached from
+/root/reference/wormhole/prover/src/lib.rs:233-237 and
+/root/reference/wormhole/circuit/src/circuit.rs:98-108) — and calls the same C entry points a
+`qpzk-sys` crate would bind. There is no CPU fallback: importing works anywhere, but creating a
+`Context` without `libqpzk.so` or without a CUDA device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "libqpzk.so")
+
+P = 0xFFFFFFFF00000001
+SALT_SIZE = 4
+STAGES = ("h2d", "ifft", "lde", "leaf_hash", "merkle_levels", "d2h")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_vp = ctypes.c_void_p
+_lib = None
+
+
+class QpzkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("qpzk error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """dlopen libqpzk.so and declare every symbol include/qpzk.h exports."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpzkError(-2, "%s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    u32, u64, i = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+    sig = {
+        "qpzk_ctx_create": (i, [i, u32, ctypes.POINTER(_vp)]),
+        "qpzk_ctx_destroy": (None, [_vp]),
+        "qpzk_last_error": (ctypes.c_char_p, []),
+        "qpzk_ctx_sync": (i, [_vp]),
+        "qpzk_ctx_stream": (_vp, [_vp]),
+        "qpzk_ctx_stage_ms": (i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+        "qpzk_ctx_launch_count": (u64, [_vp]),
+        "qpzk_host_alloc": (i, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+        "qpzk_host_free": (None, [_vp]),
+        "qpzk_dev_alloc": (i, [_vp, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+        "qpzk_dev_free": (None, [_vp, _vp]),
+        "qpzk_memcpy_h2d": (i, [_vp, _vp, _vp, ctypes.c_size_t]),
+        "qpzk_memcpy_d2h": (i, [_vp, _vp, _vp, ctypes.c_size_t]),
+        "qpzk_poseidon_permute": (i, [_vp, _u64p, u64]),
+        "qpzk_hash_no_pad": (i, [_vp, _u64p, u64, u32, _u64p]),
+        "qpzk_two_to_one": (i, [_vp, _u64p, u64, _u64p]),
+        "qpzk_merkle_new": (i, [_vp, _u64p, u64, u32, u32, ctypes.POINTER(_vp)]),
+        "qpzk_tree_cap": (i, [_vp, _u64p]),
+        "qpzk_tree_prove": (i, [_vp, u64, _u64p]),
+        "qpzk_tree_digests": (i, [_vp, _u64p]),
+        "qpzk_tree_free": (None, [_vp]),
+        "qpzk_batch_from_values": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, ctypes.POINTER(_vp)]),
+        "qpzk_batch_from_coeffs": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, ctypes.POINTER(_vp)]),
+        "qpzk_batch_from_values_dev": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, ctypes.POINTER(_vp)]),
+        "qpzk_batch_from_coeffs_dev": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, ctypes.POINTER(_vp)]),
+        "qpzk_batch_from_values_shard_dev": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, u32, u32,
+                                                 ctypes.POINTER(_vp)]),
+        "qpzk_batch_cap": (i, [_vp, _u64p]),
+        "qpzk_batch_cap_dev": (_vp, [_vp]),
+        "qpzk_batch_coeffs": (i, [_vp, _u64p]),
+        "qpzk_batch_get_lde_rows": (i, [_vp, _u32p, u32, u32, _u64p]),
+        "qpzk_batch_open": (i, [_vp, u64, _u64p, _u64p]),
+        "qpzk_batch_export": (i, [_vp, _u64p, _u64p]),
+        "qpzk_batch_ncols": (u32, [_vp]),
+        "qpzk_batch_width": (u32, [_vp]),
+        "qpzk_batch_degree_bits": (u32, [_vp]),
+        "qpzk_batch_free": (None, [_vp]),
+        "qpzk_measure_imad_peak": (i, [_vp, i, ctypes.POINTER(ctypes.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise QpzkError(rc, load_library().qpzk_last_error().decode(errors="replace"))
+
+
+def _arr(x):
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_u64p)
+
+
+class Context:
+    """One CUDA stream + caches (twiddle tables, coset pre-multipliers) on one device."""
+
+    def __init__(self, device=0):
+        L = load_library()
+        h = _vp()
+        _check(L.qpzk_ctx_create(device, 0, ctypes.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().qpzk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(load_library().qpzk_ctx_sync(self._h))
+
+    @property
+    def stream(self):
+        return load_library().qpzk_ctx_stream(self._h)
+
+    def stage_ms(self):
+        out = (ctypes.c_float * len(STAGES))()
+        _check(load_library().qpzk_ctx_stage_ms(self._h, out))
+        return dict(zip(STAGES, [float(x) for x in out]))
+
+    def launch_count(self):
+        return int(load_library().qpzk_ctx_launch_count(self._h))
+
+    def measure_imad_peak(self, kind=1):
+        out = ctypes.c_double()
+        _check(load_library().qpzk_measure_imad_peak(self._h, kind, ctypes.byref(out)))
+        return out.value
+
+    # -- raw device memory (bench / multi-GPU plumbing) --
+    def dev_alloc(self, nbytes):
+        p = _vp()
+        _check(load_library().qpzk_dev_alloc(self._h, nbytes, ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        load_library().qpzk_dev_free(self._h, _vp(p))
+
+    def h2d(self, dev_ptr, host_array):
+        a = np.ascontiguousarray(host_array)
+        _check(load_library().qpzk_memcpy_h2d(self._h, _vp(dev_ptr), a.ctypes.data_as(_vp), a.nbytes))
+
+    def d2h(self, host_array, dev_ptr):
+        _check(load_library().qpzk_memcpy_d2h(self._h, host_array.ctypes.data_as(_vp), _vp(dev_ptr),
+                                              host_array.nbytes))
+
+    # -- PoseidonHash --
+    def poseidon_permute(self, states):
+        s = _arr(states).copy().reshape(-1, 12)
+        _check(load_library().qpzk_poseidon_permute(self._h, _ptr(s), s.shape[0]))
+        return s
+
+    def hash_no_pad(self, inputs):
+        x = _arr(inputs)
+        x2 = x.reshape(1, -1) if x.ndim == 1 else x
+        out = np.zeros((x2.shape[0], 4), np.uint64)
+        _check(load_library().qpzk_hash_no_pad(self._h, _ptr(x2), x2.shape[0], x2.shape[1], _ptr(out)))
+        return out[0] if x.ndim == 1 else out
+
+    def two_to_one(self, left, right):
+        l, r = _arr(left).reshape(-1, 4), _arr(right).reshape(-1, 4)
+        pairs = np.ascontiguousarray(np.concatenate([l, r], axis=1))
+        out = np.zeros((pairs.shape[0], 4), np.uint64)
+        _check(load_library().qpzk_two_to_one(self._h, _ptr(pairs), pairs.shape[0], _ptr(out)))
+        return out[0] if np.ndim(left) == 1 else out
+
+
+class PinnedBuffer:
+    """Page-locked host array (optional fast path for callers that own their trace buffers)."""
+
+    def __init__(self, shape, dtype=np.uint64):
+        L = load_library()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _vp()
+        _check(L.qpzk_host_alloc(n, ctypes.byref(p)))
+        self._p = p
+        buf = (ctypes.c_uint8 * n).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            load_library().qpzk_host_free(self._p)
+            self._p = None
+
+
+class MerkleTree:
+    """`MerkleTree::new(leaves, cap_height)` on the device; `cap`, `prove`, `digests` read back."""
+
+    def __init__(self, ctx, leaves, cap_height):
+        lv = _arr(leaves)
+        if lv.ndim != 2:
+            raise ValueError("leaves must be [nleaves][leaf_len]")
+        self.ctx, self.nleaves, self.leaf_len, self.cap_height = ctx, lv.shape[0], lv.shape[1], cap_height
+        h = _vp()
+        _check(load_library().qpzk_merkle_new(ctx._h, _ptr(lv), lv.shape[0], lv.shape[1], cap_height,
+                                              ctypes.byref(h)))
+        self._h = h
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), np.uint64)
+        _check(load_library().qpzk_tree_cap(self._h, _ptr(out)))
+        return out
+
+    def prove(self, leaf_index):
+        nl = (self.nleaves.bit_length() - 1) - self.cap_height
+        out = np.zeros((max(nl, 1), 4), np.uint64)
+        _check(load_library().qpzk_tree_prove(self._h, leaf_index, _ptr(out)))
+        return out[:nl]
+
+    @property
+    def digests(self):
+        out = np.zeros((max(2 * (self.nleaves - (1 << self.cap_height)), 1), 4), np.uint64)
+        _check(load_library().qpzk_tree_digests(self._h, _ptr(out)))
+        return out[:2 * (self.nleaves - (1 << self.cap_height))]
+
+    def free(self):
+        if getattr(self, "_h", None):
+            load_library().qpzk_tree_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PolynomialBatch:
+    """Device-resident `PolynomialBatch` (coefficients, LDE leaves, Merkle tree)."""
+
+    def __init__(self, ctx, handle, ncols, degree_bits, rate_bits, cap_height, salt_cols):
+        self.ctx, self._h = ctx, handle
+        self.ncols, self.degree_bits, self.rate_bits = ncols, degree_bits, rate_bits
+        self.cap_height, self.salt_cols = cap_height, salt_cols
+
+    @staticmethod
+    def _make(ctx, fn, data, rate_bits, cap_height, salts, dev=False, shape=None):
+        L = load_library()
+        if dev:
+            ncols, n = shape
+            dptr = _vp(data)
+            sptr = _vp(salts[0]) if salts is not None else None
+            salt_cols = salts[1] if salts is not None else 0
+            keep = None
+        else:
+            a = _arr(data)
+            if a.ndim != 2:
+                raise ValueError("expected column-major [ncols][n]")
+            ncols, n = a.shape
+            dptr = a.ctypes.data_as(_vp)
+            keep = a
+            sptr, salt_cols = None, 0
+            if salts is not None:
+                s = _arr(salts)
+                if s.shape != (s.shape[0], n << rate_bits):
+                    raise ValueError("salts must be [salt_cols][n << rate_bits]")
+                sptr, salt_cols, keep = s.ctypes.data_as(_vp), s.shape[0], (a, s)
+        if n & (n - 1) or n == 0:
+            raise ValueError("polynomial length must be a power of two")
+        k = n.bit_length() - 1
+        h = _vp()
+        _check(getattr(L, fn)(ctx._h, dptr, ncols, k, rate_bits, cap_height, sptr, salt_cols, ctypes.byref(h)))
+        del keep
+        return PolynomialBatch(ctx, h, ncols, k, rate_bits, cap_height, salt_cols)
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, cap_height, salts=None):
+        """values: [ncols][n] evaluations on the subgroup. `blinding` = salts is not None."""
+        return cls._make(ctx, "qpzk_batch_from_values", values, rate_bits, cap_height, salts)
+
+    @classmethod
+    def from_coeffs(cls, ctx, coeffs, rate_bits, cap_height, salts=None):
+        return cls._make(ctx, "qpzk_batch_from_coeffs", coeffs, rate_bits, cap_height, salts)
+
+    @classmethod
+    def from_values_dev(cls, ctx, dev_ptr, ncols, n, rate_bits, cap_height, salts=None):
+        return cls._make(ctx, "qpzk_batch_from_values_dev", dev_ptr, rate_bits, cap_height, salts, dev=True,
+                         shape=(ncols, n))
+
+    @classmethod
+    def from_coeffs_dev(cls, ctx, dev_ptr, ncols, n, rate_bits, cap_height, salts=None):
+        return cls._make(ctx, "qpzk_batch_from_coeffs_dev", dev_ptr, rate_bits, cap_height, salts, dev=True,
+                         shape=(ncols, n))
+
+    @property
+    def width(self):
+        return self.ncols + self.salt_cols
+
+    @property
+    def lde_size(self):
+        return 1 << (self.degree_bits + self.rate_bits)
+
+    @property
+    def cap(self):
+        out = np.zeros((1 << self.cap_height, 4), np.uint64)
+        _check(load_library().qpzk_batch_cap(self._h, _ptr(out)))
+        return out
+
+    @property
+    def cap_dev(self):
+        return load_library().qpzk_batch_cap_dev(self._h)
+
+    @property
+    def polynomials(self):
+        out = np.zeros((self.ncols, 1 << self.degree_bits), np.uint64)
+        _check(load_library().qpzk_batch_coeffs(self._h, _ptr(out)))
+        return out
+
+    def get_lde_values(self, index, step=1):
+        idx = np.ascontiguousarray(np.atleast_1d(index), dtype=np.uint32)
+        out = np.zeros((idx.size, self.ncols), np.uint64)
+        _check(load_library().qpzk_batch_get_lde_rows(self._h, idx.ctypes.data_as(_u32p), idx.size, step,
+                                                      _ptr(out)))
+        return out[0] if np.ndim(index) == 0 else out
+
+    def open(self, leaf_index):
+        """(merkle_tree.leaves[leaf_index], merkle_tree.prove(leaf_index).siblings)"""
+        nl = self.degree_bits + self.rate_bits - self.cap_height
+        leaf = np.zeros(self.width, np.uint64)
+        sib = np.zeros((max(nl, 1), 4), np.uint64)
+        _check(load_library().qpzk_batch_open(self._h, leaf_index, _ptr(leaf), _ptr(sib)))
+        return leaf, sib[:nl]
+
+    def export(self, leaves=True, digests=True):
+        N = self.lde_size
+        lv = np.zeros((N, self.width), np.uint64) if leaves else None
+        nd = 2 * (N - (1 << self.cap_height))
+        dg = np.zeros((max(nd, 1), 4), np.uint64) if digests else None
+        _check(load_library().qpzk_batch_export(self._h, _ptr(lv) if leaves else None,
+                                                _ptr(dg) if digests else None))
+        return lv, (dg[:nd] if digests else None)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            load_library().qpzk_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
