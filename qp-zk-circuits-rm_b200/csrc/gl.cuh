@@ -24,51 +24,129 @@ typedef uint32_t u32;
 
 GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 
-// x = lo + 2^64*hi  ->  lo - hi_hi + hi_lo*(2^32-1)   (result is any-u64 representative)
+// x = r0 + 2^32 r1 + 2^64 r2 + 2^96 r3  ->  (r1:r0) - r3 + r2*(2^32-1)   (any-u64 representative)
+// Carry-chain PTX, no compares or selects. NOTE on flags: CC.CF is the hardware carry, i.e. after a
+// sub chain it is NOT-borrow. `subc m,0,0` after a SUB chain therefore yields the borrow mask
+// (0 / 0xffffffff), but after an ADD chain it would yield the INVERTED carry mask - so add chains
+// read the carry with `addc c,0,0` (0/1), negate it into a mask and add that.
+GL_DEV u64 gl_reduce4(u32 r0, u32 r1, u32 r2, u32 r3) {
+  asm("{\n\t"
+      ".reg .u32 m, tl, th;\n\t"
+      ".reg .u64 t;\n\t"
+      "sub.cc.u32 %0, %0, %3;\n\t"     // (r1:r0) -= r3
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"          // borrow mask: -2^64 == -EPS
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "mul.wide.u32 t, %2, 0xffffffff;\n\t"  // r2 * EPS
+      "mov.b64 {tl, th}, t;\n\t"
+      "add.cc.u32 %0, %0, tl;\n\t"
+      "addc.cc.u32 %1, %1, th;\n\t"
+      "addc.u32 m, 0, 0;\n\t"          // carry (0/1): +2^64 == +EPS (cannot carry again)
+      "sub.u32 m, 0, m;\n\t"           // 0 / 0xffffffff == c*EPS (low word)
+      "add.cc.u32 %0, %0, m;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "+r"(r0), "+r"(r1)
+      : "r"(r2), "r"(r3));
+  return ((u64)r1 << 32) | r0;
+}
 GL_DEV u64 gl_reduce128(u64 lo, u64 hi) {
-  u32 hi_hi = (u32)(hi >> 32), hi_lo = (u32)hi;
-  u64 t0 = lo - (u64)hi_hi;
-  if (lo < (u64)hi_hi) t0 -= GL_EPS;          // borrow: -2^64 == -EPS
-  u64 t1 = (u64)hi_lo * (u64)0xFFFFFFFFu;     // mul.wide.u32
-  u64 r = t0 + t1;
-  if (r < t1) r += GL_EPS;                    // carry: +2^64 == +EPS (cannot overflow again)
-  return r;
+  return gl_reduce4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
 }
 
-GL_DEV u64 gl_mul(u64 a, u64 b) { return gl_reduce128(a * b, __umul64hi(a, b)); }
+// 64x64 -> 128 schoolbook product as four 32-bit limbs (mad.lo.cc / madc.hi.cc chains map to
+// IMAD.WIDE.U32 with carry-out on sm_100a).
+GL_DEV void gl_mul_wide(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  asm("{\n\t"
+      "mul.lo.u32 %0, %4, %6;\n\t"
+      "mul.hi.u32 %1, %4, %6;\n\t"
+      "mul.lo.u32 %2, %5, %7;\n\t"
+      "mul.hi.u32 %3, %5, %7;\n\t"
+      "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+      "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+      "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "}"
+      : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+
+GL_DEV u64 gl_mul(u64 a, u64 b) {
+  u32 r0, r1, r2, r3;
+  gl_mul_wide(a, b, r0, r1, r2, r3);
+  return gl_reduce4(r0, r1, r2, r3);
+}
 GL_DEV u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 
 // a*b + c, one reduction. a*b + c < 2^128 always.
 GL_DEV u64 gl_mad(u64 a, u64 b, u64 c) {
-  u64 lo = a * b, hi = __umul64hi(a, b);
-  lo += c;
-  hi += (lo < c);
-  return gl_reduce128(lo, hi);
+  u32 r0, r1, r2, r3;
+  gl_mul_wide(a, b, r0, r1, r2, r3);
+  u32 c0 = (u32)c, c1 = (u32)(c >> 32);
+  asm("add.cc.u32 %0, %0, %4;\n\t"
+      "addc.cc.u32 %1, %1, %5;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.u32 %3, %3, 0;"
+      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)
+      : "r"(c0), "r"(c1));
+  return gl_reduce4(r0, r1, r2, r3);
 }
 
-// General add: both operands may be non-canonical.
+// General add: both operands may be non-canonical. a + b = s + c*2^64, 2^64 == EPS; the first
+// correction can wrap once more (only when s >= p), hence two corrections.
 GL_DEV u64 gl_add(u64 a, u64 b) {
-  u64 s = a + b;
-  if (s < a) {            // wrapped: +EPS, which itself can wrap once more only if s >= p
-    u64 t = s + GL_EPS;
-    s = (t < s) ? t + GL_EPS : t;
-  }
-  return s;
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  asm("{\n\t.reg .u32 c, m;\n\t.reg .u64 t;\n\t"
+      "add.cc.u32 %0, %0, %2;\n\t"
+      "addc.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"           // 0 / 0xffffffff == low word of c*EPS
+      "add.cc.u32 %0, %0, m;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.u32 c, 0, c;\n\t"
+      "add.cc.u32 %0, %0, c;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(b0), "r"(b1));
+  return ((u64)a1 << 32) | a0;
 }
 // Add where b is canonical (< p): a single correction suffices.
 GL_DEV u64 gl_add_c(u64 a, u64 b_canon) {
-  u64 s = a + b_canon;
-  if (s < a) s += GL_EPS;
-  return s;
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b_canon, b1 = (u32)(b_canon >> 32);
+  asm("{\n\t.reg .u32 c;\n\t.reg .u64 t;\n\t"
+      "add.cc.u32 %0, %0, %2;\n\t"
+      "addc.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.u32 c, 0, c;\n\t"
+      "add.cc.u32 %0, %0, c;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(b0), "r"(b1));
+  return ((u64)a1 << 32) | a0;
 }
-// General subtract.
+// General subtract: a - b = d - c*2^64; the correction -EPS can wrap once more (only if d < EPS).
 GL_DEV u64 gl_sub(u64 a, u64 b) {
-  u64 d = a - b;
-  if (a < b) {            // wrapped: -EPS, can wrap again only if d < EPS
-    u64 t = d - GL_EPS;
-    d = (d < GL_EPS) ? t - GL_EPS : t;
-  }
-  return d;
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  asm("{\n\t.reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %0, %2;\n\t"
+      "subc.cc.u32 %1, %1, %3;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.cc.u32 %1, %1, 0;\n\t"
+      "subc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(b0), "r"(b1));
+  return ((u64)a1 << 32) | a0;
 }
 GL_DEV u64 gl_neg(u64 a) {
   u64 c = gl_canon(a);

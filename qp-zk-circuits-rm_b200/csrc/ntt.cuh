@@ -60,7 +60,8 @@ __global__ void k_build_coset_pm(u64* pm, u64 wN, int k, int r) {
 //   false : each transform is contiguous (estride == 1), adjacent threads take adjacent elements
 // After the call position p holds X[rev_lg(p)].
 template <bool C_FASTEST>
-GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt, u32 estride, u32 cstride) {
+GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 estride, u32 cstride) {
+  const u32 cnt = 1u << cnt_log;
   if (lg == 0) return;
   const u32 hcount = 1u << (lg - 1);
   const u32 half_total = hcount * cnt;
@@ -69,8 +70,8 @@ GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt, u32 estride, u32 c
     for (u32 b = threadIdx.x; b < half_total; b += blockDim.x) {
       u32 c, bb;
       if (C_FASTEST) {
-        c = b % cnt;
-        bb = b / cnt;
+        c = b & (cnt - 1);
+        bb = b >> cnt_log;
       } else {
         c = b >> (lg - 1);
         bb = b & (hcount - 1);
@@ -111,7 +112,7 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
   }
   for (u32 e = threadIdx.x; e < n / 2; e += blockDim.x) tw[e] = root_pow(tab, e);
   __syncthreads();
-  smem_dif<false>(x, tw, k, 1, 1, 0);
+  smem_dif<false>(x, tw, k, 0, 1, 0);
   u64* d = dst + (u64)col * dst_stride + ((u64)brev(t, r) << k);
   for (u32 q = threadIdx.x; q < n; q += blockDim.x) {
     u64 v = NATURAL_OUT ? x[brev(q, k)] : x[q];
@@ -127,7 +128,8 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
 template <bool ROW_BITREV>
 __global__ void __launch_bounds__(256)
 k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
-             const u64* __restrict__ pm, RootTab tab, int k, int a, int r, u32 cols) {
+             const u64* __restrict__ pm, RootTab tab, int k, int a, int r, u32 cols_log) {
+  const u32 cols = 1u << cols_log;
   extern __shared__ u64 smem[];
   const int b = k - a;
   const u32 n1 = 1u << a;
@@ -138,7 +140,7 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   const u64* s = src + (u64)col * src_stride;
   const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
   for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
-    u32 j1 = idx / cols, c = idx % cols;
+    u32 j1 = idx >> cols_log, c = idx & (cols - 1);
     u64 j = ((u64)j1 << b) + j2_base + c;
     u64 v = s[j];
     if (pmt) v = gl_mul(v, pmt[j]);
@@ -146,10 +148,10 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   }
   for (u32 e = threadIdx.x; e < n1 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << b);
   __syncthreads();
-  smem_dif<true>(x, tw, a, cols, cols, 1);
+  smem_dif<true>(x, tw, a, cols_log, cols, 1);
   u64* d = dst + (u64)col * dst_stride + ((u64)brev(t, r) << k);
   for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
-    u32 p = idx / cols, c = idx % cols;
+    u32 p = idx >> cols_log, c = idx & (cols - 1);
     u32 k1 = brev(p, a);
     u32 j2 = j2_base + c;
     u64 v = gl_mul(x[idx], root_pow(tab, (u64)j2 * k1));
@@ -162,8 +164,9 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
 // grid (n1/rows_per_cta, ncols, ncosets)
 __global__ void __launch_bounds__(256)
 k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a, int r,
-                  u32 rows_per_cta) {
+                  u32 rows_log) {
   extern __shared__ u64 smem[];
+  const u32 rows_per_cta = 1u << rows_log;
   const int b = k - a;
   const u32 n2 = 1u << b;
   u64* x = smem;                      // [rows][n2]
@@ -174,7 +177,7 @@ k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a,
   for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) x[idx] = d[idx];
   for (u32 e = threadIdx.x; e < n2 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
   __syncthreads();
-  smem_dif<false>(x, tw, b, rows_per_cta, 1, n2);
+  smem_dif<false>(x, tw, b, rows_log, 1, n2);
   for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) d[idx] = gl_canon(x[idx]);
 }
 
@@ -182,8 +185,9 @@ k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a,
 // grid (n1/rc, ncols). Tile = rc consecutive rows, padded by one element per row.
 __global__ void __launch_bounds__(256)
 k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restrict__ dst,
-                       u64 dst_stride, RootTab tab, int k, int a, u32 rc, u64 scale) {
+                       u64 dst_stride, RootTab tab, int k, int a, u32 rc_log, u64 scale) {
   extern __shared__ u64 smem[];
+  const u32 rc = 1u << rc_log;
   const int b = k - a;
   const u32 n2 = 1u << b, pitch = n2 + 1;
   u64* x = smem;               // [rc][pitch]
@@ -197,10 +201,10 @@ k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restr
   }
   for (u32 e = threadIdx.x; e < n2 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
   __syncthreads();
-  smem_dif<false>(x, tw, b, rc, 1, pitch);
+  smem_dif<false>(x, tw, b, rc_log, 1, pitch);
   u64* d = dst + (u64)col * dst_stride;
   for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x) {
-    u32 k2 = idx / rc, rr = idx % rc;
+    u32 k2 = idx >> rc_log, rr = idx & (rc - 1);
     u64 v = gl_mul(x[rr * pitch + brev(k2, b)], scale);
     d[((u64)k2 << a) + k1_base + rr] = gl_canon(v);
   }

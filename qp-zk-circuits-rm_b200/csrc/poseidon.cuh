@@ -24,6 +24,11 @@ __constant__ u64 c_fast_rc[22];
 __constant__ u64 c_fast_init[121];
 __constant__ u64 c_fast_w_hat[242];
 __constant__ u64 c_fast_v[242];
+// Kept in constant memory (not literals) on purpose: with literal multipliers nvcc strength-reduces
+// every c*x into shift/add chains on the already saturated ALU pipe; as constant-bank operands they
+// stay single IMAD.WIDE instructions.
+__constant__ u32 c_mds_circ[12];
+__constant__ u32 c_mds_diag0;
 
 GL_DEV u64 sbox7(u64 x) {
   u64 x2 = gl_sqr(x);
@@ -32,36 +37,59 @@ GL_DEV u64 sbox7(u64 x) {
   return gl_mul(x3, x4);
 }
 
-// lo + 2^64*hi with hi < 2^32 (a 96-bit value): lo + hi*EPS, single correction.
-GL_DEV u64 gl_reduce96(u64 lo, u32 hi) {
-  u64 t1 = (u64)hi * (u64)0xFFFFFFFFu;
-  u64 r = lo + t1;
-  if (r < t1) r += GL_EPS;
-  return r;
+// MDS lane recombination: al + ah*2^32 with al, ah < 2^42, folded to 64 bits.
+//   value = al0 + (al1 + ah0)*2^32 + (ah1 + carry)*2^64,  2^64 == EPS
+GL_DEV u64 mds_combine(u32 l0, u32 l1, u32 h0, u32 h1) {
+  asm("{\n\t.reg .u32 m, tl, th;\n\t.reg .u64 t;\n\t"
+      "add.cc.u32 %1, %1, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "mul.wide.u32 t, %3, 0xffffffff;\n\t"
+      "mov.b64 {tl, th}, t;\n\t"
+      "add.cc.u32 %0, %0, tl;\n\t"
+      "addc.cc.u32 %1, %1, th;\n\t"
+      "addc.u32 m, 0, 0;\n\t"          // carry as 0/1 (see gl.cuh note on flags)
+      "sub.u32 m, 0, m;\n\t"
+      "add.cc.u32 %0, %0, m;\n\t"
+      "addc.u32 %1, %1, 0;\n\t"
+      "}"
+      : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1));
+  return ((u64)l1 << 32) | l0;
 }
 
-// 160-bit accumulator for sums of up to 2^32 128-bit products.
+// 160-bit accumulator (five 32-bit limbs) for sums of up to 2^32 128-bit products.
 struct Acc160 {
-  u64 lo, hi;
-  u32 top;
+  u32 l0, l1, l2, l3, l4;
 };
-GL_DEV void acc_init(Acc160& a) { a.lo = 0; a.hi = 0; a.top = 0; }
+GL_DEV void acc_init(Acc160& a) { a.l0 = a.l1 = a.l2 = a.l3 = a.l4 = 0; }
 GL_DEV void acc_mac(Acc160& a, u64 x, u64 y) {
-  u64 plo = x * y, phi = __umul64hi(x, y);
-  asm("add.cc.u64 %0, %0, %3;\n\t"
-      "addc.cc.u64 %1, %1, %4;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "+l"(a.lo), "+l"(a.hi), "+r"(a.top)
-      : "l"(plo), "l"(phi));
+  u32 r0, r1, r2, r3;
+  gl_mul_wide(x, y, r0, r1, r2, r3);
+  asm("add.cc.u32 %0, %0, %5;\n\t"
+      "addc.cc.u32 %1, %1, %6;\n\t"
+      "addc.cc.u32 %2, %2, %7;\n\t"
+      "addc.cc.u32 %3, %3, %8;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+r"(a.l0), "+r"(a.l1), "+r"(a.l2), "+r"(a.l3), "+r"(a.l4)
+      : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
 }
-// value = lo + 2^64*hi + 2^128*top, and 2^128 == -2^32 (mod p)
+// value = l0..l3 + 2^128*l4, and 2^128 == -2^32 (mod p)
 GL_DEV u64 acc_reduce(const Acc160& a) {
-  u64 r = gl_reduce128(a.lo, a.hi);
-  return gl_sub(r, (u64)a.top << 32);
+  u64 r = gl_reduce4(a.l0, a.l1, a.l2, a.l3);
+  return gl_sub(r, (u64)a.l4 << 32);
+}
+
+// (hi:lo) += a*b as ONE IMAD.WIDE.U32 with accumulate. Written as a mad.lo.cc / madc.hi pair on
+// purpose: from `acc += (u64)a * b` nvcc added a zero high word per term, and from a single
+// `mad.wide.u32` ptxas split every term into a product plus 3-input IADD3 trees - both double the
+// load on the ALU pipe, which is the saturated one.
+GL_DEV void mad_wide(u32& lo, u32& hi, u32 a, u32 b) {
+  asm("mad.lo.cc.u32 %0, %2, %3, %0;\n\t"
+      "madc.hi.u32 %1, %2, %3, %1;"
+      : "+r"(lo), "+r"(hi)
+      : "r"(a), "r"(b));
 }
 
 GL_DEV void mds_layer(u64 (&s)[12]) {
-  const u32 circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
   u32 lo[12], hi[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
@@ -70,46 +98,60 @@ GL_DEV void mds_layer(u64 (&s)[12]) {
   }
 #pragma unroll
   for (int r = 0; r < 12; r++) {
-    u64 al = 0, ah = 0;
+    u32 al0 = 0, al1 = 0, ah0 = 0, ah1 = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-      al += (u64)lo[(i + r) % 12] * circ[i];
-      ah += (u64)hi[(i + r) % 12] * circ[i];
+      mad_wide(al0, al1, lo[(i + r) % 12], c_mds_circ[i]);
+      mad_wide(ah0, ah1, hi[(i + r) % 12], c_mds_circ[i]);
     }
     if (r == 0) {
-      al += (u64)lo[0] * 8u;
-      ah += (u64)hi[0] * 8u;
+      mad_wide(al0, al1, lo[0], c_mds_diag0);
+      mad_wide(ah0, ah1, hi[0], c_mds_diag0);
     }
-    // al, ah < 2^41.  value = al + ah*2^32
-    u64 l = al + (ah << 32);
-    u32 h = (u32)(ah >> 32) + (u32)(l < al);
-    s[r] = gl_reduce96(l, h);
+    s[r] = mds_combine(al0, al1, ah0, ah1);
   }
 }
 
 // Full round: add constants, x^7 on every lane, MDS.
+// Code size matters more than the last instruction here: ncu showed the fully unrolled permutation
+// (90 KB of SASS) stalled ~50% on instruction fetch, the 32 KB L1.5 I-cache thrashing with 24 warps
+// per SM spread over the kernel. The 12 s-boxes are therefore issued as 3 trips over 4 lanes with
+// the state ROTATED by 4 registers per trip (indices stay compile-time, 24 MOVs per trip).
 GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc) {
+#pragma unroll 1
+  for (int g = 0; g < 3; g++) {
+    u64 t0 = sbox7(gl_add_c(s[0], rc[4 * g + 0]));
+    u64 t1 = sbox7(gl_add_c(s[1], rc[4 * g + 1]));
+    u64 t2 = sbox7(gl_add_c(s[2], rc[4 * g + 2]));
+    u64 t3 = sbox7(gl_add_c(s[3], rc[4 * g + 3]));
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add_c(s[i], rc[i]));
+    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+    s[8] = t0;
+    s[9] = t1;
+    s[10] = t2;
+    s[11] = t3;
+  }
   mds_layer(s);
 }
 
 GL_DEV void partial_rounds(u64 (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
-  {  // mds_partial_layer_init: out[c] = sum_r in[r] * init[r-1][c-1]
-    u64 o[12];
-    o[0] = s[0];
-#pragma unroll
-    for (int c = 1; c < 12; c++) {
+  {  // mds_partial_layer_init: out[c] = sum_r in[r] * init[r-1][c-1], c = 1..11.
+     // One trip per output lane; results are shifted through o[] so every index is static.
+    u64 o[11];
+#pragma unroll 1
+    for (int c = 0; c < 11; c++) {
       Acc160 a;
       acc_init(a);
 #pragma unroll
-      for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + (c - 1)]);
-      o[c] = acc_reduce(a);
+      for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
+#pragma unroll
+      for (int i = 0; i < 10; i++) o[i] = o[i + 1];
+      o[10] = acc_reduce(a);
     }
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = o[i];
+    for (int i = 1; i < 12; i++) s[i] = o[i - 1];
   }
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
@@ -127,12 +169,14 @@ GL_DEV void partial_rounds(u64 (&s)[12]) {
 }
 
 // In-place permutation; inputs may be any u64 representatives, outputs likewise (not canonical).
+// Both halves of full rounds share one copy of the round body (see the I-cache note above).
 GL_DEV void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * r);
-  partial_rounds(s);
+  for (int half = 0; half < 2; half++) {
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * (26 + r));
+    for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * (26 * half + r));
+    if (half == 0) partial_rounds(s);
+  }
 }
 
 }  // namespace qpzk

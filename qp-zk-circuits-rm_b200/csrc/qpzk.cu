@@ -151,16 +151,17 @@ static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, 
     int a = (k + 1) / 2;
     if (a > 8) a = 8;
     int b = k - a;
-    u32 cols = 16;
+    u32 cols_log = 4, cols = 16;
     size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
     k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
-        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols);
-    u32 rows = kTileElems >> b;
-    if (rows < 1) rows = 1;
-    if (rows > (1u << a)) rows = 1u << a;
+        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols_log);
+    int rows_log = 12 - b;  // kTileElems / n2
+    if (rows_log < 0) rows_log = 0;
+    if (rows_log > a) rows_log = a;
+    u32 rows = 1u << rows_log;
     size_t smem_b = ((size_t)rows * (1u << b) + (1u << b) / 2) * 8;
     k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k,
-                                                                                         a, r, rows);
+                                                                                         a, r, (u32)rows_log);
     c->launches += 2;
   }
   CU(cudaGetLastError());
@@ -181,16 +182,16 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   } else {
     if (k > 18) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 18 not supported");
     int a = (k + 1) / 2, b = k - a;
-    u32 cols = a <= 8 ? 16 : 8;
-    u32 rc = b <= 8 ? 16 : 8;
+    u32 cols_log = a <= 8 ? 4 : 3, cols = 1u << cols_log;
+    u32 rc_log = b <= 8 ? 4 : 3, rc = 1u << rc_log;
     u64* tmp;
     QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
     size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
     k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
-        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols);
+        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols_log);
     size_t smem_b = ((size_t)rc * ((1u << b) + 1) + (1u << b) / 2) * 8;
     k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs,
-                                                                                    dst_stride, tab, k, a, rc, ninv);
+                                                                                    dst_stride, tab, k, a, rc_log, ninv);
     c->launches += 2;
     dev_free(c, tmp);
   }
@@ -289,6 +290,19 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
     CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
     CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
     CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
+    u32 circ[12];
+    for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
+    u32 diag0 = (u32)kMdsDiag0;
+    CU(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
+    CU(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
+    // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
+    const int kMaxSmem = 72 * 1024;
+    CU(cudaFuncSetAttribute(k_ntt_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_ntt_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   }
   QP(dev_alloc(c, 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
   CU(cudaStreamSynchronize(c->stream));
