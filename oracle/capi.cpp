@@ -10,6 +10,7 @@
 #include "ntt.hpp"
 #include "plonk.hpp"
 #include "poseidon.hpp"
+#include "prover.hpp"
 #include "verifier.hpp"
 
 using namespace orc;
@@ -224,6 +225,103 @@ int orc_check_proof_paths(const uint8_t* common, u64 common_len, const uint8_t* 
   } catch (std::exception& e) {
     g_err = e.what();
     return -1;
+  }
+}
+
+// ---- prover (restated prove()) ----
+struct OrcCircuit {
+  CircuitProverData d;
+  ProveTrace trace;
+};
+
+// constants_sigmas: column-major [num_constants + num_routed][n] values on the subgroup.
+void* orc_circuit_new(const uint8_t* common, u64 common_len, const u64* digest4,
+                      const u64* constants_sigmas, unsigned threads) {
+  try {
+    CommonData c = parse_common(common, common_len);
+    size_t n = (size_t)1 << c.degree_bits, cols = c.num_constants + c.num_routed_wires;
+    std::vector<std::vector<u64>> cs(cols);
+    for (size_t j = 0; j < cols; j++) cs[j].assign(constants_sigmas + j * n, constants_sigmas + (j + 1) * n);
+    Hash dg;
+    memcpy(dg.e, digest4, 32);
+    OrcCircuit* oc = new OrcCircuit();
+    oc->d = make_circuit(c, dg, std::move(cs), threads);
+    return oc;
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void orc_circuit_free(void* h) { delete (OrcCircuit*)h; }
+// VerifierOnlyCircuitData bytes: cap_height, cap, circuit_digest. Returns length.
+u64 orc_circuit_verifier_only(void* h, uint8_t* out, u64 cap) {
+  OrcCircuit* oc = (OrcCircuit*)h;
+  Writer w;
+  w.usize(oc->d.common.cap_height);
+  for (auto& hh : oc->d.cs_batch.tree.cap) w.hash(hh);
+  w.hash(oc->d.circuit_digest);
+  if (out && w.b.size() <= cap) memcpy(out, w.b.data(), w.b.size());
+  return w.b.size();
+}
+void orc_circuit_cs_coeffs(void* h, u64* out) {
+  OrcCircuit* oc = (OrcCircuit*)h;
+  size_t n = (size_t)1 << oc->d.common.degree_bits;
+  for (size_t j = 0; j < oc->d.cs_batch.ncols; j++) memcpy(out + j * n, oc->d.cs_batch.coeffs[j].data(), n * 8);
+}
+
+// wires: column-major [num_wires][n]. salts_*: NULL or [4][N] natural order. Writes the serialised
+// ProofWithPublicInputs; returns its length, or -1 (error text in orc_last_error).
+int64_t orc_prove(void* h, const u64* wires, const u64* public_inputs, u64 npi, const u64* salts_w,
+                  const u64* salts_z, const u64* salts_q, unsigned threads, uint8_t* out, u64 out_cap) {
+  try {
+    OrcCircuit* oc = (OrcCircuit*)h;
+    const CommonData& c = oc->d.common;
+    size_t n = (size_t)1 << c.degree_bits;
+    std::vector<std::vector<u64>> w(c.num_wires);
+    for (size_t j = 0; j < c.num_wires; j++) {
+      w[j].assign(wires + j * n, wires + (j + 1) * n);
+      for (auto& v : w[j]) v = canon(v);
+    }
+    std::vector<u64> pi(public_inputs, public_inputs + npi);
+    ProverSalts sl;
+    sl.wires = salts_w; sl.zs_pp = salts_z; sl.quotient = salts_q;
+    Proof pf = prove(oc->d, w, pi, sl, threads, &oc->trace);
+    std::vector<uint8_t> b = proof_to_bytes(pf);
+    if (b.size() > out_cap) throw std::runtime_error("output buffer too small");
+    memcpy(out, b.data(), b.size());
+    return (int64_t)b.size();
+  } catch (std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+// Intermediate values of the last orc_prove on this circuit, for stage-by-stage parity tests.
+// challenges: betas[nch] gammas[nch] alphas[nch] zeta[2] fri_alpha[2] fri_betas[2*rounds]
+void orc_trace_challenges(void* h, u64* out) {
+  OrcCircuit* oc = (OrcCircuit*)h;
+  u64* o = out;
+  for (u64 v : oc->trace.betas) *o++ = v;
+  for (u64 v : oc->trace.gammas) *o++ = v;
+  for (u64 v : oc->trace.alphas) *o++ = v;
+  *o++ = oc->trace.zeta.a; *o++ = oc->trace.zeta.b;
+  *o++ = oc->trace.fri_alpha.a; *o++ = oc->trace.fri_alpha.b;
+  for (E2 e : oc->trace.fri_betas) { *o++ = e.a; *o++ = e.b; }
+}
+void orc_trace_zs_pp(void* h, u64* out) {  // [nch*(1+npp)][n]
+  OrcCircuit* oc = (OrcCircuit*)h;
+  size_t n = (size_t)1 << oc->d.common.degree_bits;
+  for (size_t j = 0; j < oc->trace.zs_pp_values.size(); j++) memcpy(out + j * n, oc->trace.zs_pp_values[j].data(), n * 8);
+}
+void orc_trace_quotient_chunks(void* h, u64* out) {  // [nch*qdf][n]
+  OrcCircuit* oc = (OrcCircuit*)h;
+  size_t n = (size_t)1 << oc->d.common.degree_bits;
+  for (size_t j = 0; j < oc->trace.quotient_chunks.size(); j++) memcpy(out + j * n, oc->trace.quotient_chunks[j].data(), n * 8);
+}
+void orc_trace_final_poly(void* h, u64* out) {  // [n][2]
+  OrcCircuit* oc = (OrcCircuit*)h;
+  for (size_t m = 0; m < oc->trace.final_poly_coeffs_initial.size(); m++) {
+    out[2 * m] = oc->trace.final_poly_coeffs_initial[m].a;
+    out[2 * m + 1] = oc->trace.final_poly_coeffs_initial[m].b;
   }
 }
 

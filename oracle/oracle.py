@@ -235,3 +235,71 @@ def check_proof_paths(common, proof, x_indices):
     xi = _a(x_indices)
     return lib().orc_check_proof_paths(common, ctypes.c_uint64(len(common)), proof,
                                        ctypes.c_uint64(len(proof)), _p(xi))
+
+
+class Circuit:
+    """Prover-side circuit data for the restated `prove()` (oracle/prover.hpp)."""
+
+    def __init__(self, common, digest, constants_sigmas, threads=1):
+        L = lib()
+        L.orc_circuit_new.restype = ctypes.c_void_p
+        self.common = bytes(common)
+        cs = _a(constants_sigmas)
+        dg = _a(digest)
+        self._h = L.orc_circuit_new(self.common, ctypes.c_uint64(len(self.common)), _p(dg), _p(cs),
+                                    ctypes.c_uint(threads))
+        if not self._h:
+            raise RuntimeError(L.orc_last_error().decode())
+        self.ncs, self.n = cs.shape
+        self.threads = threads
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_circuit_free(ctypes.c_void_p(self._h))
+            self._h = None
+
+    def verifier_only_bytes(self):
+        L = lib()
+        L.orc_circuit_verifier_only.restype = ctypes.c_uint64
+        buf = ctypes.create_string_buffer(4096)
+        k = L.orc_circuit_verifier_only(ctypes.c_void_p(self._h), buf, ctypes.c_uint64(4096))
+        return buf.raw[:k]
+
+    def cs_coeffs(self):
+        out = np.zeros((self.ncs, self.n), np.uint64)
+        lib().orc_circuit_cs_coeffs(ctypes.c_void_p(self._h), _p(out))
+        return out
+
+    def prove(self, wires, public_inputs, salts=None):
+        L = lib()
+        L.orc_prove.restype = ctypes.c_int64
+        w, pi = _a(wires), _a(public_inputs)
+        sp = [None, None, None]
+        keep = []
+        if salts is not None:
+            for i in range(3):
+                a = _a(salts[i])
+                keep.append(a)
+                sp[i] = _p(a)
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        k = L.orc_prove(ctypes.c_void_p(self._h), _p(w), _p(pi), ctypes.c_uint64(pi.size), sp[0], sp[1], sp[2],
+                        ctypes.c_uint(self.threads), buf, ctypes.c_uint64(cap))
+        if k < 0:
+            raise RuntimeError(L.orc_last_error().decode())
+        return buf.raw[:k]
+
+    def trace(self, nch=2, npp=9, qdf=8, rounds=3):
+        L = lib()
+        h = ctypes.c_void_p(self._h)
+        ch = np.zeros(3 * nch + 4 + 2 * rounds, np.uint64)
+        L.orc_trace_challenges(h, _p(ch))
+        zs = np.zeros((nch * (1 + npp), self.n), np.uint64)
+        L.orc_trace_zs_pp(h, _p(zs))
+        q = np.zeros((nch * qdf, self.n), np.uint64)
+        L.orc_trace_quotient_chunks(h, _p(q))
+        fp = np.zeros((self.n, 2), np.uint64)
+        L.orc_trace_final_poly(h, _p(fp))
+        return dict(betas=ch[0:nch], gammas=ch[nch:2 * nch], alphas=ch[2 * nch:3 * nch],
+                    zeta=ch[3 * nch:3 * nch + 2], fri_alpha=ch[3 * nch + 2:3 * nch + 4],
+                    fri_betas=ch[3 * nch + 4:].reshape(-1, 2), zs_pp=zs, quotient_chunks=q, final_poly=fp)
