@@ -158,6 +158,45 @@ uint32_t qpzk_batch_width(const qpzk_batch* b); /* ncols + salt_cols */
 uint32_t qpzk_batch_degree_bits(const qpzk_batch* b);
 void qpzk_batch_free(qpzk_batch* b);
 
+/* ---- circuit + prove() (qp-plonky2 plonk/prover.rs `prove`, plonk/circuit_builder.rs `build`) ----
+ * qpzk_circuit_create is the prover-side residue of `CircuitBuilder::build()`
+ * (/root/reference/wormhole/circuit/src/circuit.rs:98-108): it takes the CommonCircuitData bytes
+ * (`common.to_bytes()`, the layout of /root/reference/wormhole/bench-data/common.bin), the circuit
+ * digest and the constants|sigmas value columns ([num_constants + num_routed_wires][n], values on
+ * the subgroup), performs the constants|sigmas commit ONCE and keeps everything device-resident for
+ * every later proof of the same circuit. Supported gate set: Noop, Constant, PublicInput,
+ * BaseSum<2>, Arithmetic, Poseidon (the wormhole and voting circuits); anything else returns
+ * QPZK_ERR_UNSUPPORTED at creation. */
+typedef struct qpzk_circuit qpzk_circuit;
+int qpzk_circuit_create(qpzk_ctx* ctx, const uint8_t* common_bytes, size_t common_len,
+                        const uint64_t* circuit_digest /* [4] */, const uint64_t* constants_sigmas,
+                        qpzk_circuit** out);
+/* `verifier_only.constants_sigmas_cap`: [2^cap_height][4]. */
+int qpzk_circuit_cap(const qpzk_circuit* c, uint64_t* out);
+/* `VerifierOnlyCircuitData::to_bytes()`; returns the length (writes only if it fits in cap). */
+size_t qpzk_circuit_verifier_only(const qpzk_circuit* c, uint8_t* out, size_t cap);
+void qpzk_circuit_free(qpzk_circuit* c);
+/* `ProverCircuitData::prove` after witness generation
+ * (/root/reference/wormhole/prover/src/lib.rs:233-237, /root/reference/wormhole/aggregator/src/circuits/tree.rs:136,
+ * /root/reference/voting/src/lib.rs:356): wires = the full witness matrix, column-major
+ * [num_wires][n]. Runs: commit wires -> Z / partial products -> commit -> quotient -> commit ->
+ * openings -> FRI (combine, fold + commit, proof of work, queries) and writes
+ * `ProofWithPublicInputs::to_bytes()`. salts_*: NULL for non-hiding circuits, else host
+ * [4][n << rate_bits] per blinded oracle. The proof-of-work witness is the
+ * smallest valid one (the reference returns whichever a rayon worker finds first; any valid witness
+ * verifies). flags bit 0: keep intermediates for qpzk_prove_trace. */
+int qpzk_prove(qpzk_circuit* c, const uint64_t* wires, const uint64_t* public_inputs,
+               uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+               const uint64_t* salts_quotient, uint32_t flags, uint8_t* proof_out, size_t proof_cap,
+               size_t* proof_len);
+/* Parity hook (flags bit 0): which = 0 challenges, 1 zs|partial-product values [.][n],
+ * 2 quotient chunk coefficients [.][n], 3 FRI input polynomial [n][2]. Returns u64 count. */
+size_t qpzk_prove_trace(const qpzk_circuit* c, int which, uint64_t* out);
+/* Device time of the stages of the last proof, ms: [0] wires commit, [1] Z/partial products +
+ * commit, [2] quotient + commit, [3] openings, [4] FRI combine, [5] FRI commit phase,
+ * [6] proof of work, [7] queries. */
+int qpzk_prove_stage_ms(const qpzk_circuit* c, float* out16);
+
 /* ---- measurement helper: dependency-free integer multiply-add throughput (the Poseidon
  * roofline denominator). kind 0: 32-bit mad.lo.u32, kind 1: mad.wide.u32.
  * Returns multiply-adds per second over the whole device. */

@@ -43,13 +43,14 @@ __global__ void k_build_root_tab(u64* lo, u64* hi, u64 root, int k, int lk) {
   if (i < ((u64)1 << lk)) lo[i] = gl_canon(gl_pow(root, i));
   if (i < ((u64)1 << (k - lk))) hi[i] = gl_canon(gl_pow(root, i << lk));
 }
-// pm[t][m] = (g * w_N^t)^m for t < 2^r, m < n   (coset pre-multipliers)
-__global__ void k_build_coset_pm(u64* pm, u64 wN, int k, int r) {
+// pm[t][m] = (shift * w_N^t)^m for t < 2^r, m < n   (coset pre-multipliers; shift = g for commits,
+// g^(arity^i) for the i-th FRI round)
+__global__ void k_build_coset_pm(u64* pm, u64 shift0, u64 wN, int k, int r) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   u64 n = (u64)1 << k;
   if (i >= (n << r)) return;
   u64 t = i >> k, m = i & (n - 1);
-  u64 shift = gl_mul(GL_GEN, gl_pow(wN, t));
+  u64 shift = gl_mul(shift0, gl_pow(wN, t));
   pm[i] = gl_canon(gl_pow(shift, m));
 }
 

@@ -1,0 +1,587 @@
+// Prover-stage kernels for sm_100a: Z / partial products (H8), quotient evaluation over the LDE
+// coset (H9), openings (H10), FRI batch-combine / divide-by-linear (H11), fold (H12), proof-of-work
+// grinding (H13) and query gathers (H14) - SURVEY.md §8(a).
+//
+// Replaces the bodies of `all_wires_permutation_partial_products`, `compute_quotient_polys` +
+// `eval_vanishing_poly_base_batch` + `Gate::eval_unfiltered_base_batch`, `OpeningSet::new`,
+// `PolynomialBatch::prove_openings`, `fri_committed_trees`, `fri_proof_of_work` and
+// `fri_prover_query_rounds` of qp-plonky2 1.1.1 (plonk/prover.rs, plonk/vanishing_poly.rs,
+// gates/*.rs, fri/oracle.rs, fri/prover.rs; un-vendored), reached from
+// /root/reference/wormhole/prover/src/lib.rs:233-237,
+// /root/reference/wormhole/aggregator/src/circuits/tree.rs:136 and /root/reference/voting/src/lib.rs:356.
+//
+// Data layout: every oracle's LDE is column-major [width][N] in bit-reversed row order (see
+// merkle.cuh), so a thread that owns leaf position L reads column c at lde[c*N + L]: all loads in
+// the quotient kernel are unit-stride across the warp. Natural LDE index i = bitrev(L).
+#pragma once
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+namespace qpzk {
+
+enum : u32 {
+  G_ARITHMETIC = 0,
+  G_BASE_SUM_2 = 2,
+  G_CONSTANT = 3,
+  G_NOOP = 9,
+  G_POSEIDON = 11,
+  G_PUBLIC_INPUT = 12,
+};
+
+#define QPZK_MAX_GATES 16
+#define QPZK_MAX_CHALLENGES 4
+
+// Everything the quotient / Z kernels need to know about the circuit (passed by value).
+struct CircuitDesc {
+  u32 degree_bits, rate_bits, quotient_degree_bits;
+  u32 num_wires, num_routed, num_constants, num_challenges, num_partial_products, qdf;
+  u32 num_selectors, num_gates, num_gate_constraints;
+  u32 gate_id[QPZK_MAX_GATES], gate_param[QPZK_MAX_GATES], gate_selector[QPZK_MAX_GATES];
+  u32 group_lo[QPZK_MAX_GATES], group_hi[QPZK_MAX_GATES];  // indexed by selector index
+};
+
+struct Challenges {
+  u64 beta[QPZK_MAX_CHALLENGES], gamma[QPZK_MAX_CHALLENGES], alpha[QPZK_MAX_CHALLENGES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// H8  Z and partial products
+// ---------------------------------------------------------------------------------------------
+// One thread per (row, challenge): the nchunks chunk quotients prod(num)/prod(den) and their product.
+// wires / cs are value columns on the subgroup, [.][n]. k_is in constant-like global memory.
+__global__ void __launch_bounds__(128)
+k_zs_chunk_quotients(const u64* __restrict__ wires, const u64* __restrict__ cs, const u64* __restrict__ k_is,
+                     CircuitDesc d, Challenges ch, RootTab tab, u64* __restrict__ chunk_q /*[nch][nchunks][n]*/,
+                     u64* __restrict__ row_prod /*[nch][n]*/) {
+  const u64 n = (u64)1 << d.degree_bits;
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 c = blockIdx.y;
+  const u32 nchunks = d.num_partial_products + 1;
+  const u64 x = root_pow(tab, i);
+  const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+  const u64 bx = gl_mul(beta, x);
+  u64 nums[12], dens[12];  // nchunks <= 12
+  u64 dprod = 1;
+  for (u32 k = 0; k < nchunks; k++) {
+    u64 num = 1, den = 1;
+    for (u32 j = k * d.qdf; j < (k + 1) * d.qdf && j < d.num_routed; j++) {
+      u64 w = wires[(u64)j * n + i];
+      u64 sg = cs[(u64)(d.num_constants + j) * n + i];
+      u64 nu = gl_add(gl_mad(bx, k_is[j], w), gamma);
+      u64 de = gl_add(gl_mad(beta, sg, w), gamma);
+      num = gl_mul(num, nu);
+      den = gl_mul(den, de);
+    }
+    nums[k] = num;
+    dens[k] = den;
+    dprod = gl_mul(dprod, den);
+  }
+  // Montgomery batch inversion of the nchunks denominators: one field inversion per row
+  u64 pre[12];
+  {
+    u64 acc = 1;
+    for (u32 k = 0; k < nchunks; k++) {
+      pre[k] = acc;
+      acc = gl_mul(acc, dens[k]);
+    }
+  }
+  u64 inv_all = gl_inv(dprod);
+  u64 total = 1;
+  for (int k = (int)nchunks - 1; k >= 0; k--) {
+    u64 dinv = gl_mul(inv_all, pre[k]);    // 1 / dens[k]
+    inv_all = gl_mul(inv_all, dens[k]);    // 1 / prod(dens[0..k))
+    nums[k] = gl_mul(nums[k], dinv);
+  }
+  for (u32 k = 0; k < nchunks; k++) {
+    chunk_q[((u64)c * nchunks + k) * n + i] = nums[k];
+    total = gl_mul(total, nums[k]);
+  }
+  row_prod[(u64)c * n + i] = total;
+}
+
+// Exclusive prefix product along rows: z[0] = 1, z[i+1] = z[i] * row_prod[i]. One CTA per challenge.
+__global__ void __launch_bounds__(1024) k_prefix_product(const u64* __restrict__ row_prod, u64* __restrict__ z, u64 n) {
+  __shared__ u64 part[1024];
+  const u64* in = row_prod + (u64)blockIdx.x * n;
+  u64* out = z + (u64)blockIdx.x * n;
+  const u32 t = threadIdx.x, T = blockDim.x;
+  const u64 per = (n + T - 1) / T;
+  const u64 lo = (u64)t * per, hi = lo + per < n ? lo + per : n;
+  u64 p = 1;
+  for (u64 i = lo; i < hi; i++) p = gl_mul(p, in[i]);
+  part[t] = p;
+  __syncthreads();
+  for (u32 off = 1; off < T; off <<= 1) {  // inclusive Hillis-Steele scan
+    u64 v = t >= off ? part[t - off] : 1;
+    __syncthreads();
+    part[t] = gl_mul(part[t], v);
+    __syncthreads();
+  }
+  u64 acc = t ? part[t - 1] : 1;
+  for (u64 i = lo; i < hi; i++) {
+    out[i] = gl_canon(acc);
+    acc = gl_mul(acc, in[i]);
+  }
+}
+
+// zs_pp[ch] (Z) is already in place; fill pp[ch][k][i] = Z[i] * prod_{j<=k} chunk_q[ch][j][i].
+__global__ void k_partial_products(const u64* __restrict__ chunk_q, const u64* __restrict__ z, u32 nch, u32 npp,
+                                   u64 n, u64* __restrict__ pp /*[nch][npp][n]*/) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 c = blockIdx.y;
+  u64 acc = z[(u64)c * n + i];
+  for (u32 k = 0; k < npp; k++) {
+    acc = gl_mul(acc, chunk_q[((u64)c * (npp + 1) + k) * n + i]);
+    pp[((u64)c * npp + k) * n + i] = gl_canon(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// H9  quotient evaluation
+// ---------------------------------------------------------------------------------------------
+// Running sum_t alpha^t * term_t for every challenge, 160-bit lazily reduced accumulators.
+struct AlphaAcc {
+  Acc160 acc[2];
+  u64 pw[2];  // alpha^t (times the current gate's filter while inside a gate)
+  u64 alpha[2];
+  u32 nch;
+};
+GL_DEV void aa_emit(AlphaAcc& a, u64 term) {
+#pragma unroll
+  for (int c = 0; c < 2; c++)
+    if (c < (int)a.nch) {
+      acc_mac(a.acc[c], a.pw[c], term);
+      a.pw[c] = gl_mul(a.pw[c], a.alpha[c]);
+    }
+}
+
+struct WireRow {  // column-major LDE accessor for one leaf position
+  const u64* base;
+  u64 N;
+  GL_DEV u64 operator[](u32 c) const { return __ldg(base + (u64)c * N); }
+};
+
+// PoseidonGate::eval_unfiltered (123 constraints) with the fast partial rounds; emits in order.
+GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
+  u64 swap = w[24];
+  aa_emit(a, gl_mul(swap, gl_sub(swap, 1)));
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u64 lhs = w[i], rhs = w[i + 4], delta = w[25 + i];
+    aa_emit(a, gl_sub(gl_mul(swap, gl_sub(rhs, lhs)), delta));
+    s[i] = gl_add(lhs, delta);
+    s[i + 4] = gl_sub(rhs, delta);
+  }
+#pragma unroll
+  for (int i = 8; i < 12; i++) s[i] = w[i];
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll 1
+    for (int g = 0; g < 3; g++) {  // rotate-by-4 so indices stay static (see poseidon.cuh)
+      u64 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        u64 v = gl_add_c(s[q], c_rc[12 * r + 4 * g + q]);
+        if (r != 0) {
+          u64 in = w[29 + 12 * (r - 1) + 4 * g + q];
+          aa_emit(a, gl_sub(v, in));
+          v = in;
+        }
+        t[q] = sbox7(v);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+      s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
+    }
+    mds_layer(s);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
+  {
+    u64 o[11];
+#pragma unroll 1
+    for (int c = 0; c < 11; c++) {
+      Acc160 acc;
+      acc_init(acc);
+#pragma unroll
+      for (int r = 1; r < 12; r++) acc_mac(acc, s[r], c_fast_init[(r - 1) * 11 + c]);
+#pragma unroll
+      for (int i = 0; i < 10; i++) o[i] = o[i + 1];
+      o[10] = acc_reduce(acc);
+    }
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = o[i - 1];
+  }
+#pragma unroll 1
+  for (int r = 0; r < 22; r++) {
+    u64 in = w[65 + r];
+    aa_emit(a, gl_sub(s[0], in));
+    u64 s0 = gl_add_c(sbox7(in), c_fast_rc[r]);
+    Acc160 acc;
+    acc_init(acc);
+    acc_mac(acc, s0, 25);
+#pragma unroll
+    for (int i = 1; i < 12; i++) acc_mac(acc, s[i], c_fast_w_hat[r * 11 + i - 1]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = gl_mad(s0, c_fast_v[r * 11 + i - 1], s[i]);
+    s[0] = acc_reduce(acc);
+  }
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll 1
+    for (int g = 0; g < 3; g++) {
+      u64 t[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        u64 v = gl_add_c(s[q], c_rc[12 * (26 + r) + 4 * g + q]);
+        u64 in = w[87 + 12 * r + 4 * g + q];
+        aa_emit(a, gl_sub(v, in));
+        t[q] = sbox7(in);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+      s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
+    }
+    mds_layer(s);
+  }
+#pragma unroll 1
+  for (int g = 0; g < 3; g++) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) aa_emit(a, gl_sub(s[q], w[12 + 4 * g + q]));
+    u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+    s[8] = t0; s[9] = t1; s[10] = t2; s[11] = t3;
+  }
+}
+
+// One thread per LDE leaf position. out[ch][i] (natural index i) = vanishing(x_i) / Z_H(x_i).
+__global__ void __launch_bounds__(128)
+k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, const u64* __restrict__ zs_lde,
+           u64 cs_stride, u64 wires_stride, u64 zs_stride, u32 step_bits, const u64* __restrict__ k_is,
+           CircuitDesc d, Challenges ch, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
+           const u64* __restrict__ zh_inv, RootTab tab /* size degree_bits + qdb */, u64* __restrict__ out) {
+  const u32 lb = d.degree_bits + d.quotient_degree_bits;  // quotient domain bits
+  const u64 lde = (u64)1 << lb;
+  u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;     // position in the bit-reversed quotient domain
+  if (q >= lde) return;
+  const u64 i = __brevll(q) >> (64 - lb);                  // natural index on g*<w_lde>
+  // position inside the committed LDE (rate_bits >= qdb): natural index i*step -> leaf rev(i*step)
+  const u32 full_bits = d.degree_bits + d.rate_bits;
+  const u64 leaf = __brevll(i << step_bits) >> (64 - full_bits);
+  const u64 inext = (i + ((u64)1 << d.quotient_degree_bits)) & (lde - 1);
+  const u64 leaf_next = __brevll(inext << step_bits) >> (64 - full_bits);
+  const u64 x = gl_mul(GL_GEN, root_pow(tab, i));
+  const u32 nch = d.num_challenges, npp = d.num_partial_products;
+  WireRow cs{cs_lde + leaf, cs_stride}, w{wires_lde + leaf, wires_stride}, zs{zs_lde + leaf, zs_stride};
+  WireRow zsn{zs_lde + leaf_next, zs_stride};
+  const u64 zhx = zh[i & (((u64)1 << d.quotient_degree_bits) - 1)];
+
+  AlphaAcc a;
+  a.nch = nch;
+  for (int c = 0; c < 2; c++) {
+    acc_init(a.acc[c]);
+    a.pw[c] = 1;
+    a.alpha[c] = c < (int)nch ? ch.alpha[c] : 0;
+  }
+  // L_0(x) (Z_i(x) - 1),  L_0(x) = Z_H(x) / (n (x - 1))
+  {
+    u64 nn = ((u64)1 << d.degree_bits) % GL_P;
+    u64 l0 = gl_mul(zhx, gl_inv(gl_mul(nn, gl_sub(x, 1))));
+    for (u32 c = 0; c < nch; c++) aa_emit(a, gl_mul(l0, gl_sub(zs[c], 1)));
+  }
+  // partial-product checks
+  const u32 nchunks = npp + 1;
+  for (u32 c = 0; c < nch; c++) {
+    const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+    const u64 bx = gl_mul(beta, x);
+    u64 prev = zs[c];
+    for (u32 k = 0; k < nchunks; k++) {
+      u64 num = 1, den = 1;
+      for (u32 j = k * d.qdf; j < (k + 1) * d.qdf && j < d.num_routed; j++) {
+        u64 wv = w[j];
+        num = gl_mul(num, gl_add(gl_mad(bx, k_is[j], wv), gamma));
+        den = gl_mul(den, gl_add(gl_mad(beta, cs[d.num_constants + j], wv), gamma));
+      }
+      u64 next = k + 1 < nchunks ? zs[nch + c * npp + k] : zsn[c];
+      aa_emit(a, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
+      prev = next;
+    }
+  }
+  // gate constraints: slot j gets sum_g filter_g * c_{g,j}; each gate restarts at alpha^base
+  u64 base_pw[2];
+  for (int c = 0; c < 2; c++) base_pw[c] = a.pw[c];
+  const u64* gc_dummy = nullptr;
+  (void)gc_dummy;
+  for (u32 g = 0; g < d.num_gates; g++) {
+    const u32 si = d.gate_selector[g];
+    const u64 s = cs[si];
+    u64 filter = 1;
+    for (u32 j = d.group_lo[si]; j < d.group_hi[si]; j++)
+      if (j != g) filter = gl_mul(filter, gl_sub((u64)j, s));
+    if (d.num_selectors > 1) filter = gl_mul(filter, gl_sub((u64)0xFFFFFFFFu, s));
+    for (int c = 0; c < 2; c++) a.pw[c] = gl_mul(base_pw[c], filter);
+    switch (d.gate_id[g]) {
+      case G_NOOP:
+        break;
+      case G_CONSTANT:
+        for (u32 t = 0; t < d.gate_param[g]; t++) aa_emit(a, gl_sub(cs[d.num_selectors + t], w[t]));
+        break;
+      case G_PUBLIC_INPUT:
+        for (u32 t = 0; t < 4; t++) aa_emit(a, gl_sub(w[t], pi_hash[t]));
+        break;
+      case G_BASE_SUM_2: {
+        const u32 nl = d.gate_param[g];
+        u64 sum = 0;
+        for (int t = (int)nl - 1; t >= 0; t--) sum = gl_add(gl_add(sum, sum), w[1 + t]);
+        aa_emit(a, gl_sub(sum, w[0]));
+        for (u32 t = 0; t < nl; t++) {
+          u64 l = w[1 + t];
+          aa_emit(a, gl_mul(l, gl_sub(l, 1)));
+        }
+        break;
+      }
+      case G_ARITHMETIC: {
+        const u64 c0 = cs[d.num_selectors], c1 = cs[d.num_selectors + 1];
+        for (u32 t = 0; t < d.gate_param[g]; t++) {
+          u64 m0 = w[4 * t], m1 = w[4 * t + 1], ad = w[4 * t + 2], o = w[4 * t + 3];
+          u64 comp = gl_mad(gl_mul(m0, m1), c0, gl_mul(ad, c1));
+          aa_emit(a, gl_sub(o, comp));
+        }
+        break;
+      }
+      case G_POSEIDON:
+        poseidon_gate_eval(w, a);
+        break;
+      default:
+        break;
+    }
+  }
+  const u64 zi = zh_inv[i & (((u64)1 << d.quotient_degree_bits) - 1)];
+  for (u32 c = 0; c < nch; c++) out[(u64)c * lde + i] = gl_canon(gl_mul(acc_reduce(a.acc[c]), zi));
+}
+
+// data[c][m] *= base^m via a two-level power table (coset (i)fft shift removal).
+__global__ void k_scale_by_powers(u64* __restrict__ data, u64 n, RootTab tab) {
+  u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  u64* p = data + (u64)blockIdx.y * n + m;
+  *p = gl_canon(gl_mul(*p, root_pow(tab, m)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// H10  openings: evaluate base-field coefficient columns at an extension point
+// ---------------------------------------------------------------------------------------------
+// pw[m] = z^m (ext), m < n.
+__global__ void k_ext_powers(gl2 z, u64 n, u64* __restrict__ pw /*[n][2]*/) {
+  u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  gl2 r = gl2_make(1, 0), b = z;
+  for (u64 e = m; e; e >>= 1) {
+    if (e & 1) r = gl2_mul(r, b);
+    b = gl2_mul(b, b);
+  }
+  pw[2 * m] = gl_canon(r.a);
+  pw[2 * m + 1] = gl_canon(r.b);
+}
+// One CTA per polynomial: out[p] = sum_m coeffs[p][m] * pw[m].
+__global__ void __launch_bounds__(256)
+k_eval_at_ext(const u64* __restrict__ coeffs, u64 n, const u64* __restrict__ pw, u64* __restrict__ out /*[.][2]*/) {
+  __shared__ u64 sa[256], sb[256];
+  const u64* c = coeffs + (u64)blockIdx.x * n;
+  Acc160 a, b;
+  acc_init(a);
+  acc_init(b);
+  for (u64 m = threadIdx.x; m < n; m += blockDim.x) {
+    u64 v = c[m];
+    acc_mac(a, v, pw[2 * m]);
+    acc_mac(b, v, pw[2 * m + 1]);
+  }
+  sa[threadIdx.x] = acc_reduce(a);
+  sb[threadIdx.x] = acc_reduce(b);
+  __syncthreads();
+  for (u32 off = blockDim.x / 2; off; off >>= 1) {
+    if (threadIdx.x < off) {
+      sa[threadIdx.x] = gl_add(sa[threadIdx.x], sa[threadIdx.x + off]);
+      sb[threadIdx.x] = gl_add(sb[threadIdx.x], sb[threadIdx.x + off]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = gl_canon(sa[0]);
+    out[2 * blockIdx.x + 1] = gl_canon(sb[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// H11  FRI batch combine: comp[m] = sum_j alpha^j f_j[m] over a list of coefficient columns
+// ---------------------------------------------------------------------------------------------
+struct PolyList {  // up to 4 oracles' coefficient arrays, concatenated in order
+  const u64* base[4];
+  u32 count[4];
+  u32 noracles;
+};
+// apow[j] = alpha^j (ext) for j < total (device array [total][2]). comp: SoA [2][n].
+__global__ void __launch_bounds__(128)
+k_fri_compose(PolyList pl, u64 n, const u64* __restrict__ apow, u64* __restrict__ comp) {
+  u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  Acc160 a, b;
+  acc_init(a);
+  acc_init(b);
+  u32 j = 0;
+  for (u32 o = 0; o < pl.noracles; o++)
+    for (u32 p = 0; p < pl.count[o]; p++, j++) {
+      u64 v = pl.base[o][(u64)p * n + m];
+      acc_mac(a, v, apow[2 * j]);
+      acc_mac(b, v, apow[2 * j + 1]);
+    }
+  comp[m] = acc_reduce(a);
+  comp[n + m] = acc_reduce(b);
+}
+
+// divide_by_linear: q[m-1] = p[m] + z*q[m] (descending), q[n-1] = 0. One CTA per polynomial.
+// p, q: SoA [2][n] ext coefficient vectors (may alias: each thread finishes reading before writing).
+__global__ void __launch_bounds__(1024)
+k_divide_by_linear(const u64* __restrict__ p, u64* __restrict__ q, u64 n, gl2 z) {
+  __shared__ u64 ca[1024], cb[1024];  // carry entering each segment from above
+  const u32 t = threadIdx.x, T = blockDim.x;
+  const u64 per = (n + T - 1) / T;
+  const u64 lo = (u64)t * per, hi = lo + per < n ? lo + per : n;  // segment [lo, hi)
+  // local recurrence with zero carry-in: acc after processing m = hi-1 .. lo
+  gl2 acc = gl2_make(0, 0);
+  for (u64 m = hi; m-- > lo;) {
+    if (lo >= hi) break;
+    acc = gl2_add(gl2_make(p[m], p[n + m]), gl2_mul(z, acc));
+  }
+  // z^len for this segment
+  gl2 zl = gl2_make(1, 0);
+  {
+    gl2 b = z;
+    for (u64 e = (hi > lo ? hi - lo : 0); e; e >>= 1) {
+      if (e & 1) zl = gl2_mul(zl, b);
+      b = gl2_mul(b, b);
+    }
+  }
+  ca[t] = acc.a;
+  cb[t] = acc.b;
+  __syncthreads();
+  // sequential combine (T steps of one ext mul-add; negligible): carry_in[t] = value of the
+  // recurrence just above segment t
+  __shared__ u64 za[1024], zb[1024];
+  za[t] = zl.a;
+  zb[t] = zl.b;
+  __syncthreads();
+  if (t == 0) {
+    gl2 carry = gl2_make(0, 0);
+    for (int s = (int)T - 1; s >= 0; s--) {
+      gl2 local = gl2_make(ca[s], cb[s]);
+      gl2 zs = gl2_make(za[s], zb[s]);
+      ca[s] = carry.a;
+      cb[s] = carry.b;
+      carry = gl2_add(local, gl2_mul(zs, carry));
+    }
+  }
+  __syncthreads();
+  // replay with the true carry-in and write q[m-1]
+  acc = gl2_make(ca[t], cb[t]);
+  if (t == T - 1 || hi == n) {
+    // the topmost non-empty segment also owns q[n-1] = 0
+  }
+  for (u64 m = hi; m-- > lo;) {
+    if (lo >= hi) break;
+    acc = gl2_add(gl2_make(p[m], p[n + m]), gl2_mul(z, acc));
+    if (m > 0) {
+      q[m - 1] = gl_canon(acc.a);
+      q[n + m - 1] = gl_canon(acc.b);
+    }
+  }
+  if (hi == n && lo < hi) {
+    q[n - 1] = 0;
+    q[2 * n - 1] = 0;
+  }
+}
+
+// final = q0 * s + q1  (ext scalar s), SoA [2][n]
+__global__ void k_ext_axpy(const u64* __restrict__ q0, const u64* __restrict__ q1, gl2 s, u64 n,
+                           u64* __restrict__ out) {
+  u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  gl2 v = gl2_add(gl2_mul(gl2_make(q0[m], q0[n + m]), s), gl2_make(q1[m], q1[n + m]));
+  out[m] = gl_canon(v.a);
+  out[n + m] = gl_canon(v.b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// H12  FRI fold and leaf packing
+// ---------------------------------------------------------------------------------------------
+// out[m] = sum_{j<arity} in[m*arity + j] * beta^j  (ext Horner). in: SoA [2][n_in], out: SoA [2][n_in/arity]
+__global__ void k_fri_fold(const u64* __restrict__ in, u64 n_in, u32 arity_bits, gl2 beta, u64* __restrict__ out) {
+  u64 n_out = n_in >> arity_bits;
+  u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_out) return;
+  u32 arity = 1u << arity_bits;
+  gl2 acc = gl2_make(0, 0);
+  for (int j = (int)arity - 1; j >= 0; j--) {
+    u64 idx = (m << arity_bits) + j;
+    acc = gl2_add(gl2_mul(acc, beta), gl2_make(in[idx], in[n_in + idx]));
+  }
+  out[m] = gl_canon(acc.a);
+  out[n_out + m] = gl_canon(acc.b);
+}
+// SoA [2][N] ext values -> AoS [N][2] (leaf = `arity` consecutive ext values = 2*arity felts)
+__global__ void k_ext_interleave(const u64* __restrict__ soa, u64 N, u64* __restrict__ aos) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  ulonglong2 v = make_ulonglong2(soa[i], soa[N + i]);
+  reinterpret_cast<ulonglong2*>(aos)[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// H13  proof of work: smallest w with leading_zeros(perm(state with w at pos)[7]) >= min_lz
+// ---------------------------------------------------------------------------------------------
+struct PowState {
+  u64 s[12];
+};
+__global__ void __launch_bounds__(128)
+k_pow_grind(PowState st, u32 pos, u32 min_lz, u64 start, u64 count, unsigned long long* __restrict__ best) {
+  u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  u64 cand = start + t;
+  if (cand >= *best) return;  // a smaller witness was already found
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = st.s[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++)
+    if (i == (int)pos) s[i] = cand;
+  poseidon_permute(s);
+  u64 resp = gl_canon(s[7]);
+  u32 lz = resp ? (u32)__clzll((long long)resp) : 64;
+  if (lz >= min_lz) atomicMin(best, (unsigned long long)cand);
+}
+
+// ---------------------------------------------------------------------------------------------
+// H14  batched openings: for each query q: salted row (column-major source) + Merkle path
+// ---------------------------------------------------------------------------------------------
+// grid = nq blocks. out[q] = [width felts][L*4 felts]
+__global__ void k_gather_openings(const u64* __restrict__ lde, u64 row_stride, u64 col_stride, u32 width,
+                                  const u64* __restrict__ levels, u32 log_n, u32 cap_height,
+                                  const u64* __restrict__ leaf_idx, u32 shift_bits, u64* __restrict__ out) {
+  const u32 q = blockIdx.x;
+  const u64 leaf = leaf_idx[q] >> shift_bits;
+  const u32 L = log_n - cap_height;
+  u64* o = out + (u64)q * (width + 4 * L);
+  for (u32 c = threadIdx.x; c < width; c += blockDim.x) o[c] = lde[leaf * row_stride + (u64)c * col_stride];
+  const u64 twoN = (u64)2 << log_n;
+  for (u32 e = threadIdx.x; e < 4 * L; e += blockDim.x) {
+    u32 l = e >> 2;
+    u64 off = twoN - (twoN >> l);
+    o[width + e] = levels[(off + ((leaf >> l) ^ 1)) * 4 + (e & 3)];
+  }
+}
+
+}  // namespace qpzk

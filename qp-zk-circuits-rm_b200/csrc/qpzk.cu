@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -22,6 +24,7 @@
 #include "ntt.cuh"
 #include "poseidon.cuh"
 #include "poseidon_tables.hpp"
+#include "prover.cuh"
 
 using namespace qpzk;
 
@@ -57,7 +60,8 @@ struct qpzk_ctx {
   uint64_t launches = 0;
   int sm_count = 148;
   std::map<TabKey, std::pair<u64*, u64*>> root_tabs;   // (lo, hi)
-  std::map<std::pair<int, int>, u64*> coset_pm;          // (k, r) -> pm[2^r][2^k]
+  std::map<std::tuple<int, int, u64>, u64*> coset_pm;    // (k, r, shift) -> pm[2^r][2^k]
+  std::map<std::pair<u64, int>, std::pair<u64*, u64*>> pow_tabs;  // (base, k) -> two-level base^e table
   u64* scratch_path = nullptr;                           // small device scratch for openings
 };
 
@@ -111,15 +115,37 @@ static int get_root_tab(qpzk_ctx* c, int k, bool inverse, RootTab* out) {
   return QPZK_OK;
 }
 
-static int get_coset_pm(qpzk_ctx* c, int k, int r, const u64** out) {
-  auto key = std::make_pair(k, r);
+// Two-level table of base^e, e < 2^k, for an arbitrary base (coset shift removal).
+static int get_pow_tab(qpzk_ctx* c, u64 base, int k, RootTab* out) {
+  auto key = std::make_pair(base, k);
+  auto it = c->pow_tabs.find(key);
+  int lk = (k + 1) / 2;
+  if (it == c->pow_tabs.end()) {
+    u64 *lo, *hi;
+    QP(dev_alloc(c, sizeof(u64) << lk, &lo));
+    QP(dev_alloc(c, sizeof(u64) << (k - lk), &hi));
+    u64 cnt = (u64)1 << lk;
+    k_build_root_tab<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(lo, hi, base, k, lk);
+    c->launches++;
+    CU(cudaGetLastError());
+    it = c->pow_tabs.emplace(key, std::make_pair(lo, hi)).first;
+  }
+  out->lo = it->second.first;
+  out->hi = it->second.second;
+  out->k = k;
+  out->lk = lk;
+  return QPZK_OK;
+}
+
+static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
+  auto key = std::make_tuple(k, r, shift);
   auto it = c->coset_pm.find(key);
   if (it == c->coset_pm.end()) {
     u64* pm;
     u64 cnt = (u64)1 << (k + r);
     QP(dev_alloc(c, cnt * sizeof(u64), &pm));
     u64 wN = glh::root_of_unity(k + r);
-    k_build_coset_pm<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(pm, wN, k, r);
+    k_build_coset_pm<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(pm, shift, wN, k, r);
     c->launches++;
     CU(cudaGetLastError());
     it = c->coset_pm.emplace(key, pm).first;
@@ -133,13 +159,13 @@ static int get_coset_pm(qpzk_ctx* c, int k, int r, const u64** out) {
 static const int kSmallMaxLog = 12;
 static const u32 kTileElems = 4096;
 
-static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride,
-                      u32 ncols, int k, int r) {
+static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride,
+                            u32 ncols, int k, int r, u64 shift) {
   if (ncols == 0) return QPZK_OK;
   RootTab tab;
   QP(get_root_tab(c, k, false, &tab));
   const u64* pm;
-  QP(get_coset_pm(c, k, r, &pm));
+  QP(get_coset_pm(c, k, r, shift, &pm));
   u32 ncosets = 1u << r;
   if (k <= kSmallMaxLog) {
     size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
@@ -166,6 +192,11 @@ static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, 
   }
   CU(cudaGetLastError());
   return QPZK_OK;
+}
+
+static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride, u32 ncols,
+                      int k, int r) {
+  return launch_lde_shift(c, coeffs, src_stride, lde, dst_stride, ncols, k, r, GL_GEN);
 }
 
 static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coeffs, u64 dst_stride,
@@ -319,6 +350,10 @@ void qpzk_ctx_destroy(qpzk_ctx* c) {
     dev_free(c, kv.second.second);
   }
   for (auto& kv : c->coset_pm) dev_free(c, kv.second);
+  for (auto& kv : c->pow_tabs) {
+    dev_free(c, kv.second.first);
+    dev_free(c, kv.second.second);
+  }
   dev_free(c, c->scratch_path);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->ev) cudaEventDestroy(e);
@@ -750,3 +785,5 @@ int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
 }
 
 }  // extern "C"
+
+#include "prover_host.inl"

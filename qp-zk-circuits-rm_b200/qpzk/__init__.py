@@ -83,6 +83,14 @@ def load_library():
         "qpzk_batch_degree_bits": (u32, [_vp]),
         "qpzk_batch_free": (None, [_vp]),
         "qpzk_measure_imad_peak": (i, [_vp, i, ctypes.POINTER(ctypes.c_double)]),
+        "qpzk_circuit_create": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, _vp, ctypes.POINTER(_vp)]),
+        "qpzk_circuit_cap": (i, [_vp, _u64p]),
+        "qpzk_circuit_verifier_only": (ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
+        "qpzk_circuit_free": (None, [_vp]),
+        "qpzk_prove": (i, [_vp, _vp, _u64p, u32, _vp, _vp, _vp, u32, ctypes.c_char_p, ctypes.c_size_t,
+                           ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_prove_trace": (ctypes.c_size_t, [_vp, i, _u64p]),
+        "qpzk_prove_stage_ms": (i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree
@@ -355,6 +363,82 @@ class PolynomialBatch:
     def free(self):
         if getattr(self, "_h", None):
             load_library().qpzk_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+PROVE_STAGES = ("commit_wires", "zs_partial_products_commit", "quotient_commit", "openings", "fri_combine",
+                "fri_commit_phase", "proof_of_work", "queries")
+
+
+class Circuit:
+    """Prover-side circuit data (`ProverCircuitData` after `build()`): the constants|sigmas batch is
+    committed once here and stays on the device; `prove(wires, public_inputs)` then mirrors
+    `ProverCircuitData::prove` after witness generation and returns `ProofWithPublicInputs` bytes."""
+
+    def __init__(self, ctx, common_bytes, circuit_digest, constants_sigmas):
+        L = load_library()
+        cs = _arr(constants_sigmas)
+        dg = _arr(circuit_digest)
+        h = _vp()
+        cb = bytes(common_bytes)
+        _check(L.qpzk_circuit_create(ctx._h, cb, len(cb), _ptr(dg), cs.ctypes.data_as(_vp), ctypes.byref(h)))
+        self.ctx, self._h, self.common = ctx, h, cb
+        self.n = cs.shape[1]
+
+    @property
+    def constants_sigmas_cap(self):
+        out = np.zeros((16, 4), np.uint64)
+        buf = np.zeros(4096, np.uint64)
+        _check(load_library().qpzk_circuit_cap(self._h, _ptr(buf)))
+        vo = self.verifier_only_bytes()
+        ncap = (len(vo) - 8 - 32) // 32
+        return buf[:4 * ncap].reshape(ncap, 4).copy()
+
+    def verifier_only_bytes(self):
+        L = load_library()
+        buf = ctypes.create_string_buffer(1 << 16)
+        k = L.qpzk_circuit_verifier_only(self._h, buf, 1 << 16)
+        return buf.raw[:k]
+
+    def prove(self, wires, public_inputs, salts=None, trace=False):
+        L = load_library()
+        w = _arr(wires)
+        pi = _arr(public_inputs)
+        sp = [None, None, None]
+        keep = []
+        if salts is not None:
+            for j in range(3):
+                a = _arr(salts[j])
+                keep.append(a)
+                sp[j] = a.ctypes.data_as(_vp)
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        ln = ctypes.c_size_t(0)
+        _check(L.qpzk_prove(self._h, w.ctypes.data_as(_vp), _ptr(pi), pi.size, sp[0], sp[1], sp[2],
+                            1 if trace else 0, buf, cap, ctypes.byref(ln)))
+        return buf.raw[:ln.value]
+
+    def trace(self, which):
+        L = load_library()
+        k = L.qpzk_prove_trace(self._h, which, None)
+        out = np.zeros(max(k, 1), np.uint64)
+        L.qpzk_prove_trace(self._h, which, _ptr(out))
+        return out[:k]
+
+    def stage_ms(self):
+        out = (ctypes.c_float * 16)()
+        _check(load_library().qpzk_prove_stage_ms(self._h, out))
+        return dict(zip(PROVE_STAGES, [float(x) for x in out][:len(PROVE_STAGES)]))
+
+    def free(self):
+        if getattr(self, "_h", None):
+            load_library().qpzk_circuit_free(self._h)
             self._h = None
 
     def __del__(self):

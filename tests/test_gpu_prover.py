@@ -1,0 +1,86 @@
+"""GPU prover parity: `qpzk_prove` (the device path behind `ProverCircuitData::prove`) against the
+oracle's restated prover on the same synthetic wormhole-shaped circuits and the same injected salts:
+every stage's intermediate values, then the final ProofWithPublicInputs bytes, must be identical,
+and the bytes must be accepted by the restated verifier."""
+import numpy as np
+import pytest
+
+import minibuilder
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import qpzk
+    c = qpzk.Context(0)
+    yield c
+    c.close()
+
+
+def _both(ctx, circ, threads=16):
+    import qpzk
+    oc = orc.Circuit(circ["common"], circ["digest"], circ["constants_sigmas"], threads=threads)
+    want = oc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    got = gc.prove(circ["wires"], circ["public_inputs"], circ["salts"], trace=True)
+    return oc, want, gc, got
+
+
+@pytest.mark.parametrize("k,zk", [(6, False), (7, True), (9, False), (13, False), (14, True)])
+def test_prove_matches_oracle_stage_by_stage(ctx, k, zk):
+    circ = minibuilder.build(k, zk=zk, seed=20 + k)
+    oc, want, gc, got = _both(ctx, circ)
+    assert gc.verifier_only_bytes() == oc.verifier_only_bytes()           # constants|sigmas cap (build())
+    tr = oc.trace(rounds=len(circ["arities"]))
+    n = 1 << k
+    ch = gc.trace(0)
+    want_ch = np.concatenate([tr["betas"], tr["gammas"], tr["alphas"], tr["zeta"], tr["fri_alpha"],
+                              tr["fri_betas"].ravel()])
+    assert np.array_equal(gc.trace(1).reshape(-1, n), tr["zs_pp"])       # H8 Z / partial products
+    assert np.array_equal(ch[:6], want_ch[:6])                            # betas, gammas, alphas
+    assert np.array_equal(gc.trace(2).reshape(-1, n), tr["quotient_chunks"])   # H9 quotient chunks
+    assert np.array_equal(ch[6:8], want_ch[6:8])                          # zeta
+    assert np.array_equal(ch[8:10], want_ch[8:10])                        # FRI alpha (after openings, H10)
+    assert np.array_equal(gc.trace(3).reshape(n, 2), tr["final_poly"])   # H11 polynomial entering FRI
+    assert np.array_equal(ch, want_ch)                                    # H12 betas
+    assert got == want                                                    # H13/H14/H16: identical proof bytes
+    rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), got)
+    assert rc == 0
+    gc.free()
+
+
+def test_wormhole_shape_sizes(ctx):
+    import qpzk
+    for k, zk, size in ((13, False, 132712), (14, True, 148932)):
+        circ = minibuilder.build(k, zk=zk, seed=7)
+        gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+        proof = gc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
+        assert len(proof) == size
+        rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), proof)
+        assert rc == 0
+        # second proof on the same circuit object (device-resident constants|sigmas batch is reused)
+        assert gc.prove(circ["wires"], circ["public_inputs"], circ["salts"]) == proof
+        gc.free()
+
+
+def test_invalid_witness_is_rejected_by_verifier(ctx):
+    import qpzk
+    circ = minibuilder.build(8, zk=False, seed=9)
+    w = circ["wires"].copy()
+    row = int(np.where(circ["gate"] == minibuilder.POSEIDON)[0][0])
+    w[70, row] ^= np.uint64(1)      # corrupt one partial-round s-box wire
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    proof = gc.prove(w, circ["public_inputs"])
+    rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), proof)
+    assert rc != 0
+    gc.free()
+
+
+def test_unsupported_gate_set_is_refused(ctx):
+    import qpzk
+    from helpers import common_bytes
+    bad = common_bytes(6, False, [4], gates=[(9, None), (3, 2), (12, None), (2, 63), (0, 20), (27, None)])
+    with pytest.raises(qpzk.QpzkError):
+        qpzk.Circuit(ctx, bad, np.zeros(4, np.uint64), np.zeros((84, 64), np.uint64))
