@@ -184,7 +184,8 @@ void qpzk_circuit_free(qpzk_circuit* c);
  * `ProofWithPublicInputs::to_bytes()`. salts_*: NULL for non-hiding circuits, else host
  * [4][n << rate_bits] per blinded oracle. The proof-of-work witness is the
  * smallest valid one (the reference returns whichever a rayon worker finds first; any valid witness
- * verifies). flags bit 0: keep intermediates for qpzk_prove_trace. */
+ * verifies). flags bit 0: keep intermediates for qpzk_prove_trace; bit 1: `wires` and the salt
+ * pointers are DEVICE pointers on the context's device (HBM-resident witness). */
 int qpzk_prove(qpzk_circuit* c, const uint64_t* wires, const uint64_t* public_inputs,
                uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
                const uint64_t* salts_quotient, uint32_t flags, uint8_t* proof_out, size_t proof_cap,

@@ -336,6 +336,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   if (cm.hiding && !(salt_w && salt_z && salt_q)) return fail(QPZK_ERR_BAD_ARG, "hiding circuit needs salts");
   if (npi != cm.num_public_inputs) return fail(QPZK_ERR_BAD_ARG, "public input count mismatch");
   const bool want_trace = flags & 1;
+  const bool on_device = flags & 2;  // wires / salts are device pointers (HBM-resident witness)
   cudaEvent_t evs[2];
   CU(cudaEventCreate(&evs[0]));
   CU(cudaEventCreate(&evs[1]));
@@ -358,11 +359,15 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 
   // ---- (2) commit wires ----
   tic();
-  DevBuf wires_vals(c);
-  QP(wires_vals.alloc((size_t)nw * n * 8));
-  CU(cudaMemcpyAsync(wires_vals.p, wires_host, (size_t)nw * n * 8, cudaMemcpyHostToDevice, c->stream));
+  DevBuf wires_up(c);
+  const u64* wires_dev = wires_host;
+  if (!on_device) {
+    QP(wires_up.alloc((size_t)nw * n * 8));
+    CU(cudaMemcpyAsync(wires_up.p, wires_host, (size_t)nw * n * 8, cudaMemcpyHostToDevice, c->stream));
+    wires_dev = wires_up.p;
+  }
   qpzk_batch* wires_b = nullptr;
-  QP(commit_impl(c, wires_vals.p, false, false, nw, k, r, h, cm.hiding ? salt_w : nullptr, true, salt_cols, &wires_b));
+  QP(commit_impl(c, wires_dev, false, false, nw, k, r, h, cm.hiding ? salt_w : nullptr, !on_device, salt_cols, &wires_b));
   std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> wires_guard(wires_b, qpzk_batch_free);
   std::vector<u64> cap(4ull << h);
   QP(qpzk_batch_cap(wires_b, cap.data()));
@@ -384,14 +389,14 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   QP(row_prod.alloc((size_t)nch * n * 8));
   QP(zs_vals.alloc((size_t)nzs * n * 8));
   k_zs_chunk_quotients<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(
-      wires_vals.p, q->cs_values, q->k_is_dev, d, chal, tab_n, chunk_q.p, row_prod.p);
+      wires_dev, q->cs_values, q->k_is_dev, d, chal, tab_n, chunk_q.p, row_prod.p);
   k_prefix_product<<<nch, 1024, 0, c->stream>>>(row_prod.p, zs_vals.p, n);
   k_partial_products<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(chunk_q.p, zs_vals.p, nch, npp, n,
                                                                                    zs_vals.p + (size_t)nch * n);
   c->launches += 3;
   CU(cudaGetLastError());
   qpzk_batch* zs_b = nullptr;
-  QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, true, salt_cols, &zs_b));
+  QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, !on_device, salt_cols, &zs_b));
   std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> zs_guard(zs_b, qpzk_batch_free);
   QP(qpzk_batch_cap(zs_b, cap.data()));
   std::vector<u64> zs_cap = cap;
@@ -438,7 +443,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   c->launches++;
   CU(cudaGetLastError());
   qpzk_batch* q_b = nullptr;
-  QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, true, salt_cols, &q_b));
+  QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, !on_device, salt_cols, &q_b));
   std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> q_guard(q_b, qpzk_batch_free);
   QP(qpzk_batch_cap(q_b, cap.data()));
   std::vector<u64> q_cap = cap;

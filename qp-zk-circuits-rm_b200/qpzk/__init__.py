@@ -424,6 +424,18 @@ class Circuit:
                             1 if trace else 0, buf, cap, ctypes.byref(ln)))
         return buf.raw[:ln.value]
 
+    def prove_dev(self, wires_dev, public_inputs, salts_dev=None):
+        """Same as prove() with the witness matrix (and salts) already resident on the device."""
+        L = load_library()
+        pi = _arr(public_inputs)
+        sp = [None, None, None] if salts_dev is None else [_vp(x) for x in salts_dev]
+        cap = 1 << 20
+        buf = ctypes.create_string_buffer(cap)
+        ln = ctypes.c_size_t(0)
+        _check(L.qpzk_prove(self._h, _vp(wires_dev), _ptr(pi), pi.size, sp[0], sp[1], sp[2], 2, buf, cap,
+                            ctypes.byref(ln)))
+        return buf.raw[:ln.value]
+
     def trace(self, which):
         L = load_library()
         k = L.qpzk_prove_trace(self._h, which, None)
