@@ -84,7 +84,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons. The sampler runs from before the warm-up (nvidia-smi needs a
+    few hundred ms to print its first row); only rows stamped inside [mark_begin, mark_end] - the timed
+    region - are summarised."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -92,11 +94,12 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -105,29 +108,45 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def wait_first(self, timeout=5.0):
+        t = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.t0 is not None and not (self.t0 <= ts <= (self.t1 or ts) + 0.06):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for nm, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_total": len(self.rows),
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -299,16 +318,20 @@ def run_gpu(args, rank, local_rank, world):
         return ms
 
     steps_total = args.steps
-    run_round(max(args.warmup, S), True)
-    run_round(S, False)
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    run_round(max(args.warmup, S), True)
+    run_round(S, False)
+    if rank == 0:
+        sampler.wait_first()
+        sampler.mark_begin()
     l0 = sum(c.launch_count() for c in ctxs)
     ms_res = timed(steps_total, True)
     launches = sum(c.launch_count() for c in ctxs) - l0
     ms_e2e = timed(steps_total, False)
+    if rank == 0:
+        sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     proof = results[0]
 
@@ -401,7 +424,7 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--streams", type=int, default=4, help="proofs in flight per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

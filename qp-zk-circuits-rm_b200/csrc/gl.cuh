@@ -20,6 +20,9 @@ typedef uint32_t u32;
 #define GL_ROOT_2_32 7277203076849721926ULL  // POWER_OF_TWO_GENERATOR
 
 #define GL_DEV __device__ __forceinline__
+#ifndef GL_FOLD_ALU
+#define GL_FOLD_ALU 1
+#endif
 #define GL_HD __host__ __device__ __forceinline__
 
 GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
@@ -29,27 +32,43 @@ GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 // sub chain it is NOT-borrow. `subc m,0,0` after a SUB chain therefore yields the borrow mask
 // (0 / 0xffffffff), but after an ADD chain it would yield the INVERTED carry mask - so add chains
 // read the carry with `addc c,0,0` (0/1), negate it into a mask and add that.
-GL_DEV u64 gl_reduce4(u32 r0, u32 r1, u32 r2, u32 r3) {
-  asm("{\n\t"
-      ".reg .u32 m, tl, th;\n\t"
-      ".reg .u64 t;\n\t"
-      "sub.cc.u32 %0, %0, %3;\n\t"     // (r1:r0) -= r3
-      "subc.cc.u32 %1, %1, 0;\n\t"
-      "subc.u32 m, 0, 0;\n\t"          // borrow mask: -2^64 == -EPS
-      "sub.cc.u32 %0, %0, m;\n\t"
-      "subc.u32 %1, %1, 0;\n\t"
-      "mul.wide.u32 t, %2, 0xffffffff;\n\t"  // r2 * EPS
-      "mov.b64 {tl, th}, t;\n\t"
-      "add.cc.u32 %0, %0, tl;\n\t"
-      "addc.cc.u32 %1, %1, th;\n\t"
-      "addc.u32 m, 0, 0;\n\t"          // carry (0/1): +2^64 == +EPS (cannot carry again)
-      "sub.u32 m, 0, m;\n\t"           // 0 / 0xffffffff == c*EPS (low word)
-      "add.cc.u32 %0, %0, m;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
-      "}"
-      : "+r"(r0), "+r"(r1)
-      : "r"(r2), "r"(r3));
-  return ((u64)r1 << 32) | r0;
+// The fold  lo + r2*EPS - h  (mod p)  for lo any u64, r2 < 2^32, h <= 2^63: the Goldilocks reduction
+// 2^64 == EPS, 2^96 == -1 applied to x = lo + 2^64*r2 + 2^96*h. Returns some u64 representative.
+//
+// Written with a signed 128-bit intermediate ON PURPOSE: ptxas turns it into
+//   IMAD.WIDE.U32 m, P = r2 * 0xffffffff - h     (multiply-add with negated addend and carry-out)
+//   IADD3 / IADD3.X     t = lo + m               (second carry-out)
+//   IADD3.X k = 0 - 1 + P + P'                   (BOTH carries in one 3-input add: k in {-1, 0, 1})
+//   IMAD.WIDE.U32 r = k * 0xffffffff + t ; LEA.HI hi += k >> 31    (one correction by k*EPS)
+// i.e. 6 instructions, against 12 for the same fold written as PTX add.cc/subc chains (PTX only has
+// two-input adds with a single carry flag; SASS IADD3 has three inputs and two carries).
+// The single correction never wraps again: if k = 1 then t mod 2^64 <= 2^64 - 2^33, and if k = -1
+// then t mod 2^64 >= 2^64 - h.
+GL_DEV u64 gl_fold(u64 lo, u32 r2, u64 h) {
+#if GL_FOLD_ALU
+  // same fold with r2*EPS = (r2 << 32) - r2 and k*EPS = (k << 32) - k spelled as adds: no multiplier use
+  __int128 t = (__int128)(unsigned __int128)lo - (__int128)(unsigned __int128)((u64)r2 + h) +
+               (__int128)(unsigned __int128)((u64)r2 << 32);
+  u64 tl = (u64)t;
+  u32 k = (u32)(u64)(t >> 64);
+  u32 tl0 = (u32)tl, tl1 = (u32)(tl >> 32);
+  u32 sx = (u32)((int32_t)k >> 31);
+  asm("sub.cc.u32 %0, %0, %2; subc.u32 %1, %1, %3; add.u32 %1, %1, %2;" : "+r"(tl0), "+r"(tl1) : "r"(k), "r"(sx));
+  return ((u64)tl1 << 32) | tl0;
+#else
+  __int128 t = (__int128)(unsigned __int128)lo + (__int128)((u64)r2 * GL_EPS) - (__int128)(unsigned __int128)h;
+  u64 tl = (u64)t;
+  u32 k = (u32)(u64)(t >> 64);  // 0, 1 or 0xffffffff
+  u64 r = (u64)k * GL_EPS + tl;  // k = -1: adds 2^64 - 2^33 + 1, i.e. -EPS - 2^32 (mod 2^64) ...
+  u32 rl = (u32)r, rh = (u32)(r >> 32);
+  asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(rh) : "r"(k));  // ... so give the 2^32 back: hi += k >> 31
+  return ((u64)rh << 32) | rl;
+#endif
+}
+// x = r0 + 2^32 r1 + 2^64 r2 + 2^96 r3 (+ 2^128 r4, r4 < 2^31)  ->  (r1:r0) + r2*EPS - (r4:r3)
+GL_DEV u64 gl_reduce4(u32 r0, u32 r1, u32 r2, u32 r3) { return gl_fold(((u64)r1 << 32) | r0, r2, r3); }
+GL_DEV u64 gl_reduce5(u32 r0, u32 r1, u32 r2, u32 r3, u32 r4) {
+  return gl_fold(((u64)r1 << 32) | r0, r2, ((u64)r4 << 32) | r3);
 }
 GL_DEV u64 gl_reduce128(u64 lo, u64 hi) {
   return gl_reduce4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
@@ -82,35 +101,43 @@ GL_DEV u64 gl_mul(u64 a, u64 b) {
 }
 GL_DEV u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 
-// a*b + c, one reduction. a*b + c < 2^128 always.
+// a*b + c, one reduction (a*b + c < 2^128 always). The addend rides on the first partial product:
+// (r1:r0) = a0*b0 + c is one IMAD.WIDE with carry-out, (r3:r2) = a1*b1 + carry one IMAD.WIDE.X.
 GL_DEV u64 gl_mad(u64 a, u64 b, u64 c) {
-  u32 r0, r1, r2, r3;
-  gl_mul_wide(a, b, r0, r1, r2, r3);
-  u32 c0 = (u32)c, c1 = (u32)(c >> 32);
-  asm("add.cc.u32 %0, %0, %4;\n\t"
-      "addc.cc.u32 %1, %1, %5;\n\t"
-      "addc.cc.u32 %2, %2, 0;\n\t"
-      "addc.u32 %3, %3, 0;"
-      : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)
-      : "r"(c0), "r"(c1));
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  u32 r0 = (u32)c, r1 = (u32)(c >> 32), r2, r3;
+  asm("{\n\t"
+      "mad.lo.cc.u32 %0, %4, %6, %0;\n\t"
+      "madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+      "madc.lo.cc.u32 %2, %5, %7, 0;\n\t"
+      "madc.hi.u32 %3, %5, %7, 0;\n\t"
+      "mad.lo.cc.u32 %1, %4, %7, %1;\n\t"
+      "madc.hi.cc.u32 %2, %4, %7, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "mad.lo.cc.u32 %1, %5, %6, %1;\n\t"
+      "madc.hi.cc.u32 %2, %5, %6, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "}"
+      : "+r"(r0), "+r"(r1), "=&r"(r2), "=&r"(r3)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
   return gl_reduce4(r0, r1, r2, r3);
 }
 
-// General add: both operands may be non-canonical. a + b = s + c*2^64, 2^64 == EPS; the first
-// correction can wrap once more (only when s >= p), hence two corrections.
+// a + b = s + c*2^64 with 2^64 == EPS. The corrections are multiply-adds by the carry (one IMAD.WIDE
+// with carry-out each) instead of mask-and-add chains.
+// General add: both operands may be non-canonical; the first correction can wrap once more (only
+// when s >= p), hence two corrections.
 GL_DEV u64 gl_add(u64 a, u64 b) {
   u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-  asm("{\n\t.reg .u32 c, m;\n\t.reg .u64 t;\n\t"
+  asm("{\n\t.reg .u32 c;\n\t"
       "add.cc.u32 %0, %0, %2;\n\t"
       "addc.cc.u32 %1, %1, %3;\n\t"
       "addc.u32 c, 0, 0;\n\t"
-      "sub.u32 m, 0, c;\n\t"           // 0 / 0xffffffff == low word of c*EPS
-      "add.cc.u32 %0, %0, m;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.cc.u32 %1, c, 0xffffffff, %1;\n\t"
       "addc.u32 c, 0, 0;\n\t"
-      "sub.u32 c, 0, c;\n\t"
-      "add.cc.u32 %0, %0, c;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
       "}"
       : "+r"(a0), "+r"(a1)
       : "r"(b0), "r"(b1));
@@ -119,13 +146,12 @@ GL_DEV u64 gl_add(u64 a, u64 b) {
 // Add where b is canonical (< p): a single correction suffices.
 GL_DEV u64 gl_add_c(u64 a, u64 b_canon) {
   u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b_canon, b1 = (u32)(b_canon >> 32);
-  asm("{\n\t.reg .u32 c;\n\t.reg .u64 t;\n\t"
+  asm("{\n\t.reg .u32 c;\n\t"
       "add.cc.u32 %0, %0, %2;\n\t"
       "addc.cc.u32 %1, %1, %3;\n\t"
       "addc.u32 c, 0, 0;\n\t"
-      "sub.u32 c, 0, c;\n\t"
-      "add.cc.u32 %0, %0, c;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
       "}"
       : "+r"(a0), "+r"(a1)
       : "r"(b0), "r"(b1));

@@ -16,7 +16,7 @@
 namespace qpzk {
 
 // hash_or_noop of one row per thread. Element (row, c) lives at src[row*row_stride + c*col_stride].
-__global__ void __launch_bounds__(128, 7)
+__global__ void __launch_bounds__(128, 6)
 k_leaf_hash(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 width, u64 nrows,
             u64* __restrict__ digests) {
   u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;

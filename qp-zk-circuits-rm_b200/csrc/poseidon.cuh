@@ -38,44 +38,57 @@ GL_DEV u64 sbox7(u64 x) {
 }
 
 // MDS lane recombination: al + ah*2^32 with al, ah < 2^42, folded to 64 bits.
-//   value = al0 + (al1 + ah0)*2^32 + (ah1 + carry)*2^64,  2^64 == EPS
+//   value = l0 + (l1 + h0)*2^32 + (h1 + carry)*2^64,  2^64 == EPS; the multiply-add by EPS can carry once.
 GL_DEV u64 mds_combine(u32 l0, u32 l1, u32 h0, u32 h1) {
-  asm("{\n\t.reg .u32 m, tl, th;\n\t.reg .u64 t;\n\t"
+  asm("{\n\t.reg .u32 c;\n\t"
       "add.cc.u32 %1, %1, %2;\n\t"
       "addc.u32 %3, %3, 0;\n\t"
-      "mul.wide.u32 t, %3, 0xffffffff;\n\t"
-      "mov.b64 {tl, th}, t;\n\t"
-      "add.cc.u32 %0, %0, tl;\n\t"
-      "addc.cc.u32 %1, %1, th;\n\t"
-      "addc.u32 m, 0, 0;\n\t"          // carry as 0/1 (see gl.cuh note on flags)
-      "sub.u32 m, 0, m;\n\t"
-      "add.cc.u32 %0, %0, m;\n\t"
-      "addc.u32 %1, %1, 0;\n\t"
+      "mad.lo.cc.u32 %0, %3, 0xffffffff, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, 0xffffffff, %1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
+      "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
       "}"
       : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1));
   return ((u64)l1 << 32) | l0;
 }
 
-// 160-bit accumulator (five 32-bit limbs) for sums of up to 2^32 128-bit products.
+// Dot-product accumulator: three 96-bit column sums A + B*2^32 + C*2^64 of the 32x32 partial
+// products (a0b0 | a0b1 + a1b0 | a1b1). Every partial product is ONE IMAD.WIDE with carry-out plus one
+// carry add into the column's top limb; carries never ripple across columns, so only one carry
+// predicate is live at a time (the previous 160-bit ripple accumulator made ptxas spill predicates
+// through LOP3, 135 of them per partial round). Good for up to 2^31 terms.
 struct Acc160 {
-  u32 l0, l1, l2, l3, l4;
+  u32 a0, a1, a2, b0, b1, b2, c0, c1, c2;
 };
-GL_DEV void acc_init(Acc160& a) { a.l0 = a.l1 = a.l2 = a.l3 = a.l4 = 0; }
+GL_DEV void acc_init(Acc160& a) { a.a0 = a.a1 = a.a2 = a.b0 = a.b1 = a.b2 = a.c0 = a.c1 = a.c2 = 0; }
 GL_DEV void acc_mac(Acc160& a, u64 x, u64 y) {
-  u32 r0, r1, r2, r3;
-  gl_mul_wide(x, y, r0, r1, r2, r3);
-  asm("add.cc.u32 %0, %0, %5;\n\t"
-      "addc.cc.u32 %1, %1, %6;\n\t"
-      "addc.cc.u32 %2, %2, %7;\n\t"
-      "addc.cc.u32 %3, %3, %8;\n\t"
-      "addc.u32 %4, %4, 0;"
-      : "+r"(a.l0), "+r"(a.l1), "+r"(a.l2), "+r"(a.l3), "+r"(a.l4)
-      : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+  u32 x0 = (u32)x, x1 = (u32)(x >> 32), y0 = (u32)y, y1 = (u32)(y >> 32);
+  asm("mad.lo.cc.u32 %0, %9, %11, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %11, %1;\n\t"
+      "addc.u32 %2, %2, 0;\n\t"
+      "mad.lo.cc.u32 %3, %9, %12, %3;\n\t"
+      "madc.hi.cc.u32 %4, %9, %12, %4;\n\t"
+      "addc.u32 %5, %5, 0;\n\t"
+      "mad.lo.cc.u32 %3, %10, %11, %3;\n\t"
+      "madc.hi.cc.u32 %4, %10, %11, %4;\n\t"
+      "addc.u32 %5, %5, 0;\n\t"
+      "mad.lo.cc.u32 %6, %10, %12, %6;\n\t"
+      "madc.hi.cc.u32 %7, %10, %12, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(a.a0), "+r"(a.a1), "+r"(a.a2), "+r"(a.b0), "+r"(a.b1), "+r"(a.b2), "+r"(a.c0), "+r"(a.c1),
+        "+r"(a.c2)
+      : "r"(x0), "r"(x1), "r"(y0), "r"(y1));
 }
-// value = l0..l3 + 2^128*l4, and 2^128 == -2^32 (mod p)
+// Column sums -> A + B*2^32 + C*2^64 = lo + 2^64*r2 + 2^96*h, then one fold.
 GL_DEV u64 acc_reduce(const Acc160& a) {
-  u64 r = gl_reduce4(a.l0, a.l1, a.l2, a.l3);
-  return gl_sub(r, (u64)a.l4 << 32);
+  typedef unsigned __int128 u128;
+  u128 A = ((u128)a.a2 << 64) | ((u64)a.a1 << 32) | a.a0;
+  u128 B = ((u128)a.b2 << 64) | ((u64)a.b1 << 32) | a.b0;
+  u128 C = ((u128)a.c2 << 64) | ((u64)a.c1 << 32) | a.c0;
+  u128 lowsum = A + (B << 32);          // < 2^129 never happens: A < 2^96, B << 32 < 2^128 - top limbs are tiny
+  u128 hi = (lowsum >> 64) + C;         // 2^64 units
+  return gl_fold((u64)lowsum, (u32)(u64)hi, (u64)(hi >> 32));
 }
 
 // (hi:lo) += a*b as ONE IMAD.WIDE.U32 with accumulate. Written as a mad.lo.cc / madc.hi pair on
