@@ -234,6 +234,47 @@ def commit_microbench(ctx, qpzk, steps, warmup, rank):
     return {k2: float(np.mean([s[k2] for s in stages])) for k2 in stages[0]}
 
 
+def sharded_commit_bench(ctx, qpzk, torch, dist, rank, world, steps, warmup):
+    """BASELINE configs[2] at N GPUs: ONE 2^16 x 135 commit sharded over the ranks by cap subtrees (whole
+    LDE cosets), every rank holding the trace; the only exchange is the NCCL all-gather of the 16 subtree
+    roots. Device time, max over ranks. The gathered cap must equal the unsharded cap."""
+    from qpzk import dist as qdist
+    n = 1 << DEGREE_BITS
+    tr = splitmix_trace(0x5EED0001, NCOLS, n)          # same trace on every rank
+    d = ctx.dev_alloc(tr.nbytes)
+    ctx.h2d(d, tr)
+    b0, e0 = qdist.shard_subtrees(rank, world, CAP_HEIGHT, RATE_BITS)
+    times = []
+    cap = None
+    for i in range(warmup + steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        sh = qpzk.PolynomialBatch.from_values_shard_dev(ctx, d, NCOLS, n, RATE_BITS, CAP_HEIGHT, b0, e0)
+        t = qdist.allgather_cap_nccl(sh)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if i >= warmup:
+            times.append(float(ms.item()))
+        cap = sh.cap
+        sh.free()
+    ok = None
+    if rank == 0:
+        full = qpzk.PolynomialBatch.from_values_dev(ctx, d, NCOLS, n, RATE_BITS, CAP_HEIGHT)
+        ok = bool(np.array_equal(full.cap, cap))
+        full.free()
+        if not ok:
+            raise SystemExit("bench: sharded commit cap != unsharded cap")
+    ctx.dev_free(d)
+    return {"n_gpus": world, "ms": float(np.mean(times)), "subtrees_per_gpu": e0 - b0,
+            "exchange": "NCCL all_gather_into_tensor of %d x 32 B subtree roots, in place on the device cap"
+                        % (1 << CAP_HEIGHT),
+            "cap_equals_unsharded": ok}
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import qpzk
@@ -341,6 +382,9 @@ def run_gpu(args, rank, local_rank, world):
     latency_ms = (time.perf_counter() - t0) * 1e3
     proof_stages = circuits[0].stage_ms()
 
+    sharded = None
+    if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
+        sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
     micro = commit_microbench(ctx0, qpzk, 5, 3, rank) if rank == 0 else None
     imad_wide = ctx0.measure_imad_peak(1)
     imad_lo = ctx0.measure_imad_peak(0)
@@ -405,6 +449,8 @@ def run_gpu(args, rank, local_rank, world):
                              "perms_per_s": alg["perms"] / (hash_ms * 1e-3), "stage_ms": hash_ms},
             "clocks": clocks,
         }
+        if sharded is not None:
+            line["commit_microbench"]["sharded"] = sharded
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -130,9 +130,14 @@ int qpzk_batch_from_values_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint32
 int qpzk_batch_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t ncols,
                                uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                const uint64_t* salts_dev, uint32_t salt_cols, qpzk_batch** out);
-/* Shard of a commit for multi-GPU: only the cap subtrees
- * [subtree_begin, subtree_end) of the 2^cap_height are evaluated, hashed and reduced; the cap
- * entries of the other subtrees are left zero for the caller to all-gather. */
+/* Shard of a commit for multi-GPU: every rank holds the value columns and computes
+ * the coefficients, but only the cap subtrees [subtree_begin, subtree_end) of the 2^cap_height -
+ * i.e. a contiguous range of bit-reversed leaves = whole cosets of the LDE domain - are evaluated,
+ * hashed and reduced. Cap entries (and digests) of the other subtrees are zero; the caller
+ * all-gathers the 2^cap_height x 32-byte subtree roots (NCCL on `qpzk_batch_cap_dev`, or on the host
+ * followed by `qpzk_batch_set_cap`). The range must be a multiple of 2^(cap_height - rate_bits)
+ * subtrees when cap_height > rate_bits (QPZK_ERR_UNSUPPORTED otherwise). Rows, Merkle paths and
+ * `get_lde_values` are served for the owned leaves. */
 int qpzk_batch_from_values_shard_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint32_t ncols,
                                      uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                      const uint64_t* salts_dev, uint32_t salt_cols,
@@ -141,6 +146,8 @@ int qpzk_batch_from_values_shard_dev(qpzk_ctx* ctx, const uint64_t* values_dev, 
 int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out);
 /* Device pointer to the cap (for NCCL all-gather of subtree roots); 2^cap_height * 4 u64. */
 uint64_t* qpzk_batch_cap_dev(qpzk_batch* b);
+/* Overwrite the cap with the gathered one (host pointer, [2^cap_height][4]). */
+int qpzk_batch_set_cap(qpzk_batch* b, const uint64_t* cap);
 /* `polynomials`: coefficient form, column-major [ncols][n]. */
 int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out);
 /* `get_lde_values(index, step)` for a list of indices: out[i] = leaves[rev(idx[i]*step)][..ncols]

@@ -98,12 +98,13 @@ GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 estride, u
 template <bool NATURAL_OUT>
 __global__ void __launch_bounds__(256)
 k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
-            const u64* __restrict__ pm, RootTab tab, int k, int r, u64 scale) {
+            const u64* __restrict__ pm, RootTab tab, int k, int r, u64 scale, u32 blk0) {
   extern __shared__ u64 smem[];
   const u32 n = 1u << k;
   u64* x = smem;
   u64* tw = smem + n;
-  const u32 col = blockIdx.x, t = blockIdx.y;
+  // leaf block blk (n consecutive bit-reversed leaves) holds coset t = rev_r(blk)
+  const u32 col = blockIdx.x, blk = blk0 + blockIdx.y, t = brev(blk, r);
   const u64* s = src + (u64)col * src_stride;
   const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
   for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
@@ -114,7 +115,7 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
   for (u32 e = threadIdx.x; e < n / 2; e += blockDim.x) tw[e] = root_pow(tab, e);
   __syncthreads();
   smem_dif<false>(x, tw, k, 0, 1, 0);
-  u64* d = dst + (u64)col * dst_stride + ((u64)brev(t, r) << k);
+  u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 q = threadIdx.x; q < n; q += blockDim.x) {
     u64 v = NATURAL_OUT ? x[brev(q, k)] : x[q];
     if (scale != 1) v = gl_mul(v, scale);
@@ -129,14 +130,14 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
 template <bool ROW_BITREV>
 __global__ void __launch_bounds__(256)
 k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
-             const u64* __restrict__ pm, RootTab tab, int k, int a, int r, u32 cols_log) {
+             const u64* __restrict__ pm, RootTab tab, int k, int a, int r, u32 cols_log, u32 blk0) {
   const u32 cols = 1u << cols_log;
   extern __shared__ u64 smem[];
   const int b = k - a;
   const u32 n1 = 1u << a;
   u64* x = smem;               // [n1][cols]
   u64* tw = smem + n1 * cols;  // [n1/2]
-  const u32 col = blockIdx.y, t = blockIdx.z;
+  const u32 col = blockIdx.y, blk = blk0 + blockIdx.z, t = brev(blk, r);
   const u32 j2_base = blockIdx.x * cols;
   const u64* s = src + (u64)col * src_stride;
   const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
@@ -150,7 +151,7 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   for (u32 e = threadIdx.x; e < n1 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << b);
   __syncthreads();
   smem_dif<true>(x, tw, a, cols_log, cols, 1);
-  u64* d = dst + (u64)col * dst_stride + ((u64)brev(t, r) << k);
+  u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
     u32 p = idx >> cols_log, c = idx & (cols - 1);
     u32 k1 = brev(p, a);
@@ -165,15 +166,15 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
 // grid (n1/rows_per_cta, ncols, ncosets)
 __global__ void __launch_bounds__(256)
 k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a, int r,
-                  u32 rows_log) {
+                  u32 rows_log, u32 blk0) {
   extern __shared__ u64 smem[];
   const u32 rows_per_cta = 1u << rows_log;
   const int b = k - a;
   const u32 n2 = 1u << b;
   u64* x = smem;                      // [rows][n2]
   u64* tw = smem + rows_per_cta * n2; // [n2/2]
-  const u32 col = blockIdx.y, t = blockIdx.z;
-  u64* d = data + (u64)col * stride + ((u64)brev(t, r) << k) + (u64)blockIdx.x * rows_per_cta * n2;
+  const u32 col = blockIdx.y, blk = blk0 + blockIdx.z;
+  u64* d = data + (u64)col * stride + ((u64)blk << k) + (u64)blockIdx.x * rows_per_cta * n2;
   const u32 total = rows_per_cta * n2;
   for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) x[idx] = d[idx];
   for (u32 e = threadIdx.x; e < n2 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);

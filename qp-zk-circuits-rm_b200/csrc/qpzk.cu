@@ -159,18 +159,21 @@ static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
 static const int kSmallMaxLog = 12;
 static const u32 kTileElems = 4096;
 
+// blk0 / nblk: which of the 2^r leaf blocks (n bit-reversed leaves each, block b = coset rev_r(b)) to
+// evaluate; the full commit passes (0, 2^r), a multi-GPU shard its own range.
 static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride,
-                            u32 ncols, int k, int r, u64 shift) {
+                            u32 ncols, int k, int r, u64 shift, u32 blk0 = 0, u32 nblk = 0) {
   if (ncols == 0) return QPZK_OK;
+  if (nblk == 0) nblk = (1u << r) - blk0;
   RootTab tab;
   QP(get_root_tab(c, k, false, &tab));
   const u64* pm;
   QP(get_coset_pm(c, k, r, shift, &pm));
-  u32 ncosets = 1u << r;
+  u32 ncosets = nblk;
   if (k <= kSmallMaxLog) {
     size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
     k_ntt_small<false><<<dim3(ncols, ncosets), 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride,
-                                                                       pm, tab, k, r, 1);
+                                                                       pm, tab, k, r, 1, blk0);
     c->launches++;
   } else {
     if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
@@ -180,14 +183,14 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
     u32 cols_log = 4, cols = 16;
     size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
     k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
-        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols_log);
+        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols_log, blk0);
     int rows_log = 12 - b;  // kTileElems / n2
     if (rows_log < 0) rows_log = 0;
     if (rows_log > a) rows_log = a;
     u32 rows = 1u << rows_log;
     size_t smem_b = ((size_t)rows * (1u << b) + (1u << b) / 2) * 8;
     k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k,
-                                                                                         a, r, (u32)rows_log);
+                                                                                         a, r, (u32)rows_log, blk0);
     c->launches += 2;
   }
   CU(cudaGetLastError());
@@ -195,8 +198,8 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
 }
 
 static int launch_lde(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64* lde, u64 dst_stride, u32 ncols,
-                      int k, int r) {
-  return launch_lde_shift(c, coeffs, src_stride, lde, dst_stride, ncols, k, r, GL_GEN);
+                      int k, int r, u32 blk0 = 0, u32 nblk = 0) {
+  return launch_lde_shift(c, coeffs, src_stride, lde, dst_stride, ncols, k, r, GL_GEN, blk0, nblk);
 }
 
 static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coeffs, u64 dst_stride,
@@ -208,7 +211,7 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   if (k <= kSmallMaxLog) {
     size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
     k_ntt_small<true><<<dim3(ncols, 1), 256, smem, c->stream>>>(values, src_stride, coeffs, dst_stride, nullptr,
-                                                                tab, k, 0, ninv);
+                                                                tab, k, 0, ninv, 0);
     c->launches++;
   } else {
     if (k > 18) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 18 not supported");
@@ -219,7 +222,7 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
     QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
     size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
     k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
-        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols_log);
+        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols_log, 0);
     size_t smem_b = ((size_t)rc * ((1u << b) + 1) + (1u << b) / 2) * 8;
     k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs,
                                                                                     dst_stride, tab, k, a, rc_log, ninv);
@@ -231,18 +234,22 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
 }
 
 // Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
+// [leaf0, leaf0 + nleaves) restricts the work to a range of whole cap subtrees (multi-GPU shard); the
+// default is the whole tree.
 static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u32 log_n, u32 cap_height,
-                      u64* levels, cudaEvent_t after_leaves) {
+                      u64* levels, cudaEvent_t after_leaves, u64 leaf0 = 0, u64 nleaves = 0) {
   u64 N = (u64)1 << log_n;
-  k_leaf_hash<<<(unsigned)((N + 127) / 128), 128, 0, c->stream>>>(src, rs, cs, width, N, levels);
+  if (nleaves == 0) nleaves = N - leaf0;
+  k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
+                                                                       levels + leaf0 * 4);
   c->launches++;
   CU(cudaGetLastError());
   if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
   u64 twoN = 2 * N;
   for (u32 l = 0; l < log_n - cap_height; l++) {
-    u64 nout = N >> (l + 1);
-    const u64* in = levels + (twoN - (twoN >> l)) * 4;
-    u64* out = levels + (twoN - (twoN >> (l + 1))) * 4;
+    u64 nout = nleaves >> (l + 1), first = leaf0 >> (l + 1);
+    const u64* in = levels + (twoN - (twoN >> l) + 2 * first) * 4;
+    u64* out = levels + (twoN - (twoN >> (l + 1)) + first) * 4;
     k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
     c->launches++;
   }
@@ -563,7 +570,7 @@ void qpzk_tree_free(qpzk_tree* t) {
 // ---- PolynomialBatch ----
 static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is_coeffs, uint32_t ncols,
                        uint32_t k, uint32_t r, uint32_t cap_height, const uint64_t* salts, bool salts_host,
-                       uint32_t salt_cols, qpzk_batch** out) {
+                       uint32_t salt_cols, qpzk_batch** out, uint32_t sub_begin = 0, uint32_t sub_end = 0) {
   if (!c || !in || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   if (ncols == 0) return fail(QPZK_ERR_BAD_ARG, "ncols must be > 0");
   if (!salts) salt_cols = 0;
@@ -572,6 +579,14 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
   CU(cudaSetDevice(c->device));
   const u64 n = (u64)1 << k, N = n << r;
   const u32 width = ncols + salt_cols;
+  // shard = a range of cap subtrees = a range of leaves; it must consist of whole leaf blocks (cosets)
+  if (sub_end == 0) sub_end = 1u << cap_height;
+  if (sub_begin >= sub_end || sub_end > (1u << cap_height)) return fail(QPZK_ERR_BAD_ARG, "bad subtree range");
+  const bool sharded = sub_begin != 0 || sub_end != (1u << cap_height);
+  const u64 leaf0 = ((u64)sub_begin << (k + r)) >> cap_height, leaf1 = ((u64)sub_end << (k + r)) >> cap_height;
+  if (sharded && ((leaf0 & (n - 1)) || (leaf1 & (n - 1))))
+    return fail(QPZK_ERR_UNSUPPORTED, "shard must cover whole cosets: subtree range must be a multiple of 2^(cap_height - rate_bits)");
+  const u32 blk0 = (u32)(leaf0 >> k), nblk = (u32)((leaf1 - leaf0) >> k);
   qpzk_batch* b = new qpzk_batch();
   b->ctx = c;
   b->ncols = ncols;
@@ -620,14 +635,16 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
     if ((rc = launch_ifft(c, src, n, b->coeffs, n, ncols, (int)k)) != QPZK_OK) return cleanup(rc);
   }
   CU(cudaEventRecord(ev[2], c->stream));
-  if ((rc = launch_lde(c, b->coeffs, n, b->lde, N, ncols, (int)k, (int)r)) != QPZK_OK) return cleanup(rc);
+  if (sharded) CU(cudaMemsetAsync(b->levels, 0, (size_t)N * 2 * 32, c->stream));  // foreign digests / cap read as zero
+  if ((rc = launch_lde(c, b->coeffs, n, b->lde, N, ncols, (int)k, (int)r, blk0, nblk)) != QPZK_OK) return cleanup(rc);
   if (salt_cols) {
     k_bitrev_rows<<<dim3((unsigned)((N + 255) / 256), salt_cols), 256, 0, c->stream>>>(
         salt_src, b->lde + (size_t)ncols * N, (int)(k + r), salt_cols);
     c->launches++;
   }
   CU(cudaEventRecord(ev[3], c->stream));
-  if ((rc = build_tree(c, b->lde, 1, N, width, k + r, cap_height, b->levels, ev[4])) != QPZK_OK) return cleanup(rc);
+  if ((rc = build_tree(c, b->lde, 1, N, width, k + r, cap_height, b->levels, ev[4], leaf0, leaf1 - leaf0)) != QPZK_OK)
+    return cleanup(rc);
   CU(cudaEventRecord(ev[5], c->stream));
   dev_free(c, staging);
   dev_free(c, salt_staging);
@@ -659,9 +676,22 @@ int qpzk_batch_from_coeffs_dev(qpzk_ctx* c, const uint64_t* coeffs, uint32_t nco
                                uint32_t salt_cols, qpzk_batch** out) {
   return commit_impl(c, coeffs, false, true, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out);
 }
-int qpzk_batch_from_values_shard_dev(qpzk_ctx*, const uint64_t*, uint32_t, uint32_t, uint32_t, uint32_t,
-                                     const uint64_t*, uint32_t, uint32_t, uint32_t, qpzk_batch**) {
-  return fail(QPZK_ERR_UNSUPPORTED, "sharded commit not built yet");
+int qpzk_batch_from_values_shard_dev(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
+                                     uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                                     uint32_t salt_cols, uint32_t subtree_begin, uint32_t subtree_end,
+                                     qpzk_batch** out) {
+  if (subtree_end == 0) return fail(QPZK_ERR_BAD_ARG, "empty subtree range");
+  return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out,
+                     subtree_begin, subtree_end);
+}
+int qpzk_batch_set_cap(qpzk_batch* b, const uint64_t* cap) {
+  if (!b || !cap) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(const_cast<u64*>(cap_ptr(b->levels, b->log_N(), b->cap_height)), cap, ((size_t)32) << b->cap_height,
+                     cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return QPZK_OK;
 }
 
 int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out) {

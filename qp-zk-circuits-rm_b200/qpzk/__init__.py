@@ -74,6 +74,7 @@ def load_library():
                                                  ctypes.POINTER(_vp)]),
         "qpzk_batch_cap": (i, [_vp, _u64p]),
         "qpzk_batch_cap_dev": (_vp, [_vp]),
+        "qpzk_batch_set_cap": (i, [_vp, _u64p]),
         "qpzk_batch_coeffs": (i, [_vp, _u64p]),
         "qpzk_batch_get_lde_rows": (i, [_vp, _u32p, u32, u32, _u64p]),
         "qpzk_batch_open": (i, [_vp, u64, _u64p, _u64p]),
@@ -311,6 +312,27 @@ class PolynomialBatch:
     def from_coeffs_dev(cls, ctx, dev_ptr, ncols, n, rate_bits, cap_height, salts=None):
         return cls._make(ctx, "qpzk_batch_from_coeffs_dev", dev_ptr, rate_bits, cap_height, salts, dev=True,
                          shape=(ncols, n))
+
+    @classmethod
+    def from_values_shard_dev(cls, ctx, dev_ptr, ncols, n, rate_bits, cap_height, subtree_begin, subtree_end,
+                              salts=None):
+        """One rank's part of a multi-GPU commit: cap subtrees [subtree_begin, subtree_end) only."""
+        L = load_library()
+        k = n.bit_length() - 1
+        sptr = _vp(salts[0]) if salts is not None else None
+        salt_cols = salts[1] if salts is not None else 0
+        h = _vp()
+        _check(L.qpzk_batch_from_values_shard_dev(ctx._h, _vp(dev_ptr), ncols, k, rate_bits, cap_height, sptr,
+                                                  salt_cols, subtree_begin, subtree_end, ctypes.byref(h)))
+        b = PolynomialBatch(ctx, h, ncols, k, rate_bits, cap_height, salt_cols)
+        b.subtrees = (subtree_begin, subtree_end)
+        return b
+
+    def set_cap(self, cap):
+        c = _arr(cap)
+        if c.shape != (1 << self.cap_height, 4):
+            raise ValueError("cap must be [2^cap_height][4]")
+        _check(load_library().qpzk_batch_set_cap(self._h, _ptr(c)))
 
     @property
     def width(self):
