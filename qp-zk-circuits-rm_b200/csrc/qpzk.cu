@@ -262,30 +262,43 @@ static const u64* cap_ptr(const u64* levels, u32 log_n, u32 cap_height) {
   return levels + (twoN - (twoN >> (log_n - cap_height))) * 4;
 }
 
-// ---- integer multiply-add peak ----
+// ---- integer multiply-add peak (the Poseidon roofline denominators) ----
+// KIND 0: IMAD (32-bit mad.lo, x = x*a + b chains). KIND 1: IMAD.WIDE.U32 with a 64-bit accumulator, the
+// instruction the field multiply and the MDS layer are made of: acc[i] += x[(i+j)&7] * c[j], with x
+// refreshed from the accumulators every trip so that no product is loop-invariant (an earlier
+// version multiplied two loop-invariant registers; ptxas hoisted the product and the "peak" it
+// reported was an add rate). cuobjdump -sass shows 64 IMAD.WIDE.U32 per trip for KIND 1.
 template <int KIND>
-__global__ void k_imad_peak(u64* out, int iters, u32 seed) {
-  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-  u64 acc[8];
-  u32 acc32[8];
+__global__ void __launch_bounds__(256) k_imad_peak(u64* out, int iters, u32 seed, u32 c0, u32 c1, u32 c2, u32 c3) {
+  const u32 cc[8] = {c0, c1, c2, c3, c0 ^ 5u, c1 ^ 9u, c2 ^ 3u, c3 ^ 6u};
+  u32 lo[8], hi[8], x[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    acc[i] = i + a;
-    acc32[i] = i + b;
+    lo[i] = seed + threadIdx.x * 8 + i;
+    hi[i] = seed * 3 + blockIdx.x + i;
+    x[i] = lo[i] ^ hi[i];
   }
   for (int it = 0; it < iters; it++) {
+    if (KIND == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (KIND == 0) {
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc32[i]) : "r"(a), "r"(b));
-      } else {
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a), "r"(b));
-      }
+      for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[i]) : "r"(cc[j]), "r"(hi[i]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
+                       : "+r"(lo[i]), "+r"(hi[i])
+                       : "r"(x[(i + j) & 7]), "r"(cc[j]));
+#pragma unroll
+      for (int i = 0; i < 8; i++) x[i] = lo[i] ^ hi[(i + 1) & 7];
     }
   }
   u64 s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; i++) s += acc[i] + acc32[i];
+  for (int i = 0; i < 8; i++) s += (((u64)hi[i] << 32) | lo[i]) + x[i];
   if (s == 0x123456789ULL) out[0] = s;  // keep the chains alive
 }
 
@@ -792,15 +805,15 @@ int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
   CU(cudaSetDevice(c->device));
   u64* d;
   QP(dev_alloc(c, 64, &d));
-  const int iters = 4096, threads = 256;
+  const int iters = 1024, threads = 256;
   const int blocks = c->sm_count * 8;
   float best = 1e30f;
   for (int rep = 0; rep < 5; rep++) {
     CU(cudaEventRecord(c->ev[0], c->stream));
     if (kind == 0)
-      k_imad_peak<0><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep);
+      k_imad_peak<0><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep, 17u, 15u, 41u, 16u);
     else
-      k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep);
+      k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep, 17u, 15u, 41u, 16u);
     c->launches++;
     CU(cudaEventRecord(c->ev[1], c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -809,7 +822,7 @@ int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
     if (rep > 0 && ms < best) best = ms;
   }
   dev_free(c, d);
-  double ops = (double)blocks * threads * iters * 8;
+  double ops = (double)blocks * threads * iters * 64;
   *out_ops_per_s = ops / (best * 1e-3);
   return QPZK_OK;
 }

@@ -9,8 +9,17 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# Reference fixtures are only present in the build container; tests that need them skip elsewhere.
-REFERENCE = "/root/reference"
+# The reference's shipped fixtures for this path are committed under tests/golden/ (copied, with
+# provenance, by scripts/make_golden.py) so that every box - including the GPU box, where /root/reference
+# does not exist - runs the same pins.
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_NAMES = {
+    "wormhole/bench-data/common.bin": "bench_common.bin",
+    "wormhole/bench-data/verifier.bin": "bench_verifier.bin",
+    "wormhole/bench-data/proof.bin": "bench_proof.bin",
+    "wormhole/aggregator/data/dummy_proof.bin": "dummy_proof.bin",
+    "wormhole/aggregator/data/dummy_proof_zk.bin": "dummy_proof_zk.bin",
+}
 
 
 def pytest_configure(config):
@@ -20,9 +29,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def ref_fixture():
     def _load(rel):
-        path = os.path.join(REFERENCE, rel)
+        path = os.path.join(GOLDEN, GOLDEN_NAMES[rel])
         if not os.path.exists(path):
-            pytest.skip("reference fixture %s not present on this box" % rel)
+            pytest.fail("golden fixture %s missing - run scripts/make_golden.py" % path)
         with open(path, "rb") as f:
             return f.read()
 
