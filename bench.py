@@ -382,6 +382,29 @@ def run_gpu(args, rank, local_rank, world):
     latency_ms = (time.perf_counter() - t0) * 1e3
     proof_stages = circuits[0].stage_ms()
 
+    # BASELINE configs[1]: voting-circuit-sized single proof (non-ZK `standard_recursion_config`,
+    # /root/reference/voting/src/lib.rs:348; degree ~2^9 - SURVEY 8(d)): per-proof fixed overhead / latency
+    voting = None
+    if rank == 0:
+        vk = 9
+        vc = synth.build(vk, zk=False, seed=5, provider=synth.GpuProvider(ctx0))
+        vcirc = qpzk.Circuit(ctx0, vc["common"], vc["digest"], vc["constants_sigmas"])
+        vd = ctx0.dev_alloc(vc["wires"].nbytes)
+        ctx0.h2d(vd, vc["wires"])
+        for _ in range(3):
+            vproof = vcirc.prove_dev(vd, vc["public_inputs"])
+        lat = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            vcirc.prove(vc["wires"], vc["public_inputs"])
+            lat.append((time.perf_counter() - t0) * 1e3)
+        voting = {"workload": "voting-circuit shape: 2^%d rows x 135 wires, non-ZK, one proof at a time through "
+                              "qpzk_prove with host buffers" % vk,
+                  "latency_ms_median": float(np.median(lat)), "latency_ms_min": float(np.min(lat)),
+                  "proof_bytes": len(vproof), "stage_ms": vcirc.stage_ms()}
+        ctx0.dev_free(vd)
+        vcirc.free()
+
     sharded = None
     if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
         sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
@@ -454,6 +477,8 @@ def run_gpu(args, rank, local_rank, world):
         }
         if sharded is not None:
             line["commit_microbench"]["sharded"] = sharded
+        if voting is not None:
+            line["voting_single_proof"] = voting
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

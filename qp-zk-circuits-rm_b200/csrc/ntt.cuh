@@ -54,40 +54,109 @@ __global__ void k_build_coset_pm(u64* pm, u64 shift0, u64 wN, int k, int r) {
   pm[i] = gl_canon(gl_pow(shift, m));
 }
 
-// In-shared-memory radix-2 DIF over `cnt` transforms of length 2^lg held in one tile.
-// Element e of transform c lives at sm[e*estride + c*cstride]. tw[e] = w_len^e, e < len/2.
-// C_FASTEST picks the thread->butterfly map so that a warp walks the unit-stride dimension:
-//   true  : transforms are interleaved (cstride == 1), adjacent threads take adjacent transforms
-//   false : each transform is contiguous (estride == 1), adjacent threads take adjacent elements
-// After the call position p holds X[rev_lg(p)].
-template <bool C_FASTEST>
-GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 estride, u32 cstride) {
-  const u32 cnt = 1u << cnt_log;
-  if (lg == 0) return;
-  const u32 hcount = 1u << (lg - 1);
-  const u32 half_total = hcount * cnt;
-  for (int s = lg - 1; s >= 0; s--) {
-    const u32 half = 1u << s;
-    for (u32 b = threadIdx.x; b < half_total; b += blockDim.x) {
-      u32 c, bb;
-      if (C_FASTEST) {
-        c = b & (cnt - 1);
-        bb = b >> cnt_log;
-      } else {
-        c = b >> (lg - 1);
-        bb = b & (hcount - 1);
-      }
-      u32 lowbits = bb & (half - 1);
-      u32 i = ((bb >> s) << (s + 1)) | lowbits;
-      u64* p0 = sm + (u64)i * estride + (u64)c * cstride;
-      u64* p1 = p0 + (u64)half * estride;
-      u64 u = *p0, v = *p1;
-      *p0 = gl_add(u, v);
-      u64 d = gl_sub(u, v);
-      *p1 = s == 0 ? d : gl_mul(d, tw[lowbits << (lg - 1 - s)]);
-    }
-    __syncthreads();
+// ---- register-resident radix-16 butterflies -------------------------------------------------------
+// plonky2's power-of-two roots of unity are powers of TWO in Goldilocks up to order 64:
+// POWER_OF_TWO_GENERATOR^(2^26) = 8, so w_16 = 2^12, w_8 = 2^24, w_4 = 2^48 (2^96 = -1, 2^192 = 1).
+// A 16-point DFT therefore needs no multiplier at all: its 17 non-trivial twiddles are shifts
+// followed by one fold, and a 2^lg-point transform is ceil(lg/4) such stages with ONE general
+// multiplication per element between stages (instead of one per butterfly per layer).
+
+// x * 2^s (mod p), 0 <= s < 96; s is a compile-time constant after unrolling.
+GL_DEV u64 gl_mul_pow2(u64 x, int s) {
+  typedef unsigned __int128 u128;
+  if (s == 0) return x;
+  if (s < 64) {
+    u128 v = (u128)x << s;
+    u64 hi = (u64)(v >> 64);
+    return gl_fold((u64)v, (u32)hi, hi >> 32);
   }
+  u128 w = (u128)x << (s - 64);  // x * 2^s = w * 2^64 = 2^64 * w0 + 2^96 * (w >> 32)
+  return gl_fold(0, (u32)(u64)w, (u64)(w >> 32));
+}
+
+// DIF butterfly with twiddle 2^e, 0 <= e < 192 (2^(96+t) = -2^t: swap the operands of the subtraction)
+GL_DEV void bfly_pow2(u64& a, u64& b, int e) {
+  u64 s = gl_add(a, b);
+  u64 d = e >= 96 ? gl_sub(b, a) : gl_sub(a, b);
+  a = s;
+  b = gl_mul_pow2(d, e >= 96 ? e - 96 : e);
+}
+
+// In-register 2^LOGR-point DIF DFT (LOGR <= 4); x[p] ends up holding X[rev_LOGR(p)].
+template <int LOGR, bool INV>
+GL_DEV void dft_regs(u64 (&x)[1 << LOGR]) {
+#pragma unroll
+  for (int l = 0; l < LOGR; l++) {
+    const int half = (1 << LOGR) >> (l + 1);
+    const int unit = 192 / (2 * half);  // w_{2*half} = 2^unit
+#pragma unroll
+    for (int blk = 0; blk < (1 << l); blk++) {
+#pragma unroll
+      for (int j = 0; j < half; j++) {
+        int e = (INV ? 192 - unit * j : unit * j) % 192;
+        bfly_pow2(x[blk * 2 * half + j], x[blk * 2 * half + j + half], e);
+      }
+    }
+  }
+}
+
+// Shared-memory tile layouts. `cnt` transforms of length len = 2^lg:
+//  INTERLEAVED : element e of transform c at e*cnt + c        (pass A: 16 adjacent columns)
+//  otherwise   : at c*pitch + e + (e >> 4), pitch = len + len/16 + 1. The 1-in-16 padding keeps every
+//                radix-16 stage (stride q = 1, 16, 256 ...) and the transposed read of the inverse
+//                pass free of bank conflicts.
+GL_HD u32 tile_pitch(u32 len) { return len + (len >> 4) + 1; }
+template <bool INTERLEAVED>
+GL_DEV u32 tile_pos(u32 c, u32 e, u32 cnt_log, u32 pitch) {
+  return INTERLEAVED ? (e << cnt_log) + c : c * pitch + e + (e >> 4);
+}
+
+// One stage: 2^LOGR-point DFTs over the elements base + i*q of every block of length m = 2^m_log,
+// then the inter-stage twiddle w_m^(e_lo * k1), results stored in DIF order (sub-block rev(k1)).
+// tw[e] = w_len^e for e < len.
+template <int LOGR, bool INTERLEAVED, bool INV>
+GL_DEV void dif_stage(u64* sm, const u64* tw, int lg, int m_log, u32 cnt_log, u32 pitch) {
+  constexpr int R = 1 << LOGR;
+  const u32 q_log = m_log - LOGR, q = 1u << q_log;
+  const u32 per_c_log = lg - LOGR;
+  const u32 total = 1u << (per_c_log + cnt_log);
+  for (u32 id = threadIdx.x; id < total; id += blockDim.x) {
+    u32 c, rest;
+    if (INTERLEAVED) {
+      c = id & ((1u << cnt_log) - 1);
+      rest = id >> cnt_log;
+    } else {
+      rest = id & ((1u << per_c_log) - 1);
+      c = id >> per_c_log;
+    }
+    const u32 e_lo = rest & (q - 1), blk = rest >> q_log;
+    const u32 base = (blk << m_log) + e_lo;
+    u64 x[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) x[i] = sm[tile_pos<INTERLEAVED>(c, base + ((u32)i << q_log), cnt_log, pitch)];
+    dft_regs<LOGR, INV>(x);
+#pragma unroll
+    for (int p = 0; p < R; p++) {
+      const u32 k1 = __brev((u32)p) >> (32 - LOGR);
+      u64 v = x[p];
+      if (p != 0 && q > 1) v = gl_mul(v, tw[(e_lo * k1) << (lg - m_log)]);
+      sm[tile_pos<INTERLEAVED>(c, base + ((u32)p << q_log), cnt_log, pitch)] = v;
+    }
+  }
+  __syncthreads();
+}
+
+// Full in-tile DIF: after the call, position p of every transform holds X[rev_lg(p)].
+template <bool INTERLEAVED, bool INV>
+GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch) {
+  int m_log = lg;
+  while (m_log >= 4) {
+    dif_stage<4, INTERLEAVED, INV>(sm, tw, lg, m_log, cnt_log, pitch);
+    m_log -= 4;
+  }
+  if (m_log == 3) dif_stage<3, INTERLEAVED, INV>(sm, tw, lg, 3, cnt_log, pitch);
+  if (m_log == 2) dif_stage<2, INTERLEAVED, INV>(sm, tw, lg, 2, cnt_log, pitch);
+  if (m_log == 1) dif_stage<1, INTERLEAVED, INV>(sm, tw, lg, 1, cnt_log, pitch);
 }
 
 // ---- single-CTA transform for n <= 2^12 ----
@@ -101,8 +170,9 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
             const u64* __restrict__ pm, RootTab tab, int k, int r, u64 scale, u32 blk0) {
   extern __shared__ u64 smem[];
   const u32 n = 1u << k;
+  const u32 pitch = tile_pitch(n);
   u64* x = smem;
-  u64* tw = smem + n;
+  u64* tw = smem + pitch;
   // leaf block blk (n consecutive bit-reversed leaves) holds coset t = rev_r(blk)
   const u32 col = blockIdx.x, blk = blk0 + blockIdx.y, t = brev(blk, r);
   const u64* s = src + (u64)col * src_stride;
@@ -110,14 +180,14 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
   for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
     u64 v = s[j];
     if (pmt) v = gl_mul(v, pmt[j]);
-    x[j] = v;
+    x[tile_pos<false>(0, j, 0, pitch)] = v;
   }
-  for (u32 e = threadIdx.x; e < n / 2; e += blockDim.x) tw[e] = root_pow(tab, e);
+  for (u32 e = threadIdx.x; e < n; e += blockDim.x) tw[e] = root_pow(tab, e);
   __syncthreads();
-  smem_dif<false>(x, tw, k, 0, 1, 0);
+  smem_dif<false, NATURAL_OUT>(x, tw, k, 0, pitch);   // the natural-order flavour is the inverse transform
   u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 q = threadIdx.x; q < n; q += blockDim.x) {
-    u64 v = NATURAL_OUT ? x[brev(q, k)] : x[q];
+    u64 v = x[tile_pos<false>(0, NATURAL_OUT ? brev(q, k) : q, 0, pitch)];
     if (scale != 1) v = gl_mul(v, scale);
     d[q] = gl_canon(v);
   }
@@ -136,7 +206,7 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   const int b = k - a;
   const u32 n1 = 1u << a;
   u64* x = smem;               // [n1][cols]
-  u64* tw = smem + n1 * cols;  // [n1/2]
+  u64* tw = smem + n1 * cols;  // [n1]
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z, t = brev(blk, r);
   const u32 j2_base = blockIdx.x * cols;
   const u64* s = src + (u64)col * src_stride;
@@ -148,9 +218,9 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
     if (pmt) v = gl_mul(v, pmt[j]);
     x[idx] = v;
   }
-  for (u32 e = threadIdx.x; e < n1 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << b);
+  for (u32 e = threadIdx.x; e < n1; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << b);
   __syncthreads();
-  smem_dif<true>(x, tw, a, cols_log, cols, 1);
+  smem_dif<true, !ROW_BITREV>(x, tw, a, cols_log, 0);   // ROW_BITREV = forward (LDE), otherwise inverse
   u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
     u32 p = idx >> cols_log, c = idx & (cols - 1);
@@ -170,17 +240,19 @@ k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a,
   extern __shared__ u64 smem[];
   const u32 rows_per_cta = 1u << rows_log;
   const int b = k - a;
-  const u32 n2 = 1u << b;
-  u64* x = smem;                      // [rows][n2]
-  u64* tw = smem + rows_per_cta * n2; // [n2/2]
+  const u32 n2 = 1u << b, pitch = tile_pitch(n2);
+  u64* x = smem;                         // [rows][pitch]
+  u64* tw = smem + rows_per_cta * pitch; // [n2]
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z;
   u64* d = data + (u64)col * stride + ((u64)blk << k) + (u64)blockIdx.x * rows_per_cta * n2;
   const u32 total = rows_per_cta * n2;
-  for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) x[idx] = d[idx];
-  for (u32 e = threadIdx.x; e < n2 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
+  for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x)
+    x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)] = d[idx];
+  for (u32 e = threadIdx.x; e < n2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
   __syncthreads();
-  smem_dif<false>(x, tw, b, rows_log, 1, n2);
-  for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x) d[idx] = gl_canon(x[idx]);
+  smem_dif<false, false>(x, tw, b, rows_log, pitch);
+  for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x)
+    d[idx] = gl_canon(x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)]);
 }
 
 // ---- pass B (IFFT flavour): n2-point DIF along rows k1, natural-order output X[k1 + n1*k2] ----
@@ -191,23 +263,21 @@ k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restr
   extern __shared__ u64 smem[];
   const u32 rc = 1u << rc_log;
   const int b = k - a;
-  const u32 n2 = 1u << b, pitch = n2 + 1;
+  const u32 n2 = 1u << b, pitch = tile_pitch(n2);
   u64* x = smem;               // [rc][pitch]
-  u64* tw = smem + rc * pitch; // [n2/2]
+  u64* tw = smem + rc * pitch; // [n2]
   const u32 col = blockIdx.y;
   const u32 k1_base = blockIdx.x * rc;
   const u64* s = tmp + (u64)col * tmp_stride + ((u64)k1_base << b);
-  for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x) {
-    u32 rr = idx >> b, j2 = idx & (n2 - 1);
-    x[rr * pitch + j2] = s[idx];
-  }
-  for (u32 e = threadIdx.x; e < n2 / 2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
+  for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x)
+    x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)] = s[idx];
+  for (u32 e = threadIdx.x; e < n2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
   __syncthreads();
-  smem_dif<false>(x, tw, b, rc_log, 1, pitch);
+  smem_dif<false, true>(x, tw, b, rc_log, pitch);
   u64* d = dst + (u64)col * dst_stride;
   for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x) {
     u32 k2 = idx >> rc_log, rr = idx & (rc - 1);
-    u64 v = gl_mul(x[rr * pitch + brev(k2, b)], scale);
+    u64 v = gl_mul(x[tile_pos<false>(rr, brev(k2, b), 0, pitch)], scale);
     d[((u64)k2 << a) + k1_base + rr] = gl_canon(v);
   }
 }

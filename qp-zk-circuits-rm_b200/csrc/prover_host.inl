@@ -621,10 +621,13 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     if (best.alloc(8) != QPZK_OK) { free_trees(); return QPZK_ERR_OOM; }
     unsigned long long init = ~0ull;
     cudaMemcpyAsync(best.p, &init, 8, cudaMemcpyHostToDevice, c->stream);
-    const u64 batch = 1ull << 20;
+    // candidate windows grow from the expected witness size (2^pow_bits) upwards: a window much larger
+    // than that only burns permutations behind the witness before the early exit can see it
+    u64 batch = 1ull << (cm.pow_bits < 12 ? 12 : (cm.pow_bits > 20 ? 20 : cm.pow_bits));
     u64 start = 0;
     unsigned long long found = ~0ull;
-    while (found == ~0ull) {
+    for (int round = 0; found == ~0ull; round++) {
+      if (round >= 2 && batch < (1ull << 22)) batch <<= 1;
       k_pow_grind<<<(unsigned)(batch / 128), 128, 0, c->stream>>>(ps, pos, cm.pow_bits, start, batch,
                                                                  (unsigned long long*)best.p);
       c->launches++;

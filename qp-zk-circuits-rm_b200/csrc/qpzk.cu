@@ -171,7 +171,7 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
   QP(get_coset_pm(c, k, r, shift, &pm));
   u32 ncosets = nblk;
   if (k <= kSmallMaxLog) {
-    size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
+    size_t smem = ((size_t)tile_pitch(1u << k) + ((size_t)1 << k)) * 8;
     k_ntt_small<false><<<dim3(ncols, ncosets), 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride,
                                                                        pm, tab, k, r, 1, blk0);
     c->launches++;
@@ -181,14 +181,14 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
     if (a > 8) a = 8;
     int b = k - a;
     u32 cols_log = 4, cols = 16;
-    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
+    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
     k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
         coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols_log, blk0);
     int rows_log = 12 - b;  // kTileElems / n2
     if (rows_log < 0) rows_log = 0;
     if (rows_log > a) rows_log = a;
     u32 rows = 1u << rows_log;
-    size_t smem_b = ((size_t)rows * (1u << b) + (1u << b) / 2) * 8;
+    size_t smem_b = ((size_t)rows * tile_pitch(1u << b) + (1u << b)) * 8;
     k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k,
                                                                                          a, r, (u32)rows_log, blk0);
     c->launches += 2;
@@ -209,7 +209,7 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   QP(get_root_tab(c, k, true, &tab));
   u64 ninv = glh::inv(((u64)1 << k) % GL_P);
   if (k <= kSmallMaxLog) {
-    size_t smem = ((size_t)1 << k) * 8 * 3 / 2 + 8;
+    size_t smem = ((size_t)tile_pitch(1u << k) + ((size_t)1 << k)) * 8;
     k_ntt_small<true><<<dim3(ncols, 1), 256, smem, c->stream>>>(values, src_stride, coeffs, dst_stride, nullptr,
                                                                 tab, k, 0, ninv, 0);
     c->launches++;
@@ -220,10 +220,10 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
     u32 rc_log = b <= 8 ? 4 : 3, rc = 1u << rc_log;
     u64* tmp;
     QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
-    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a) / 2) * 8;
+    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
     k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
         values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols_log, 0);
-    size_t smem_b = ((size_t)rc * ((1u << b) + 1) + (1u << b) / 2) * 8;
+    size_t smem_b = ((size_t)rc * tile_pitch(1u << b) + (1u << b)) * 8;
     k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs,
                                                                                     dst_stride, tab, k, a, rc_log, ninv);
     c->launches += 2;
