@@ -59,6 +59,42 @@ k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
   o[1] = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
 }
 
+// ---- low-latency variants (16 lanes per row / node) for trees too small to fill the machine ----
+#define QPZK_COOP_THREADS 128
+#define QPZK_COOP_GROUPS (QPZK_COOP_THREADS / 16)
+__global__ void __launch_bounds__(QPZK_COOP_THREADS)
+k_leaf_hash_coop(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 width, u64 nrows,
+                 u64* __restrict__ digests) {
+  __shared__ u64 xch[QPZK_COOP_GROUPS][24];
+  const u32 g = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  u64 row = (u64)blockIdx.x * QPZK_COOP_GROUPS + g;
+  const bool live = row < nrows;
+  if (!live) row = nrows - 1;  // keep the whole warp in the exchange; results are discarded
+  const u64* p = src + row * row_stride;
+  u64 s = 0;
+  if (width <= 4) {  // hash_or_noop: short rows are copied, zero padded
+    if (lane < width) s = p[lane * col_stride];
+  } else {
+    for (u32 off = 0; off < width; off += 8) {
+      if (lane < 8 && off + lane < width) s = __ldg(p + (u64)(off + lane) * col_stride);  // overwrite-mode absorb
+      s = poseidon_permute_coop(s, lane, xch[g]);
+    }
+  }
+  if (live && lane < 4) digests[row * 4 + lane] = gl_canon(s);
+}
+
+__global__ void __launch_bounds__(QPZK_COOP_THREADS)
+k_merkle_level_coop(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
+  __shared__ u64 xch[QPZK_COOP_GROUPS][24];
+  const u32 g = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  u64 t = (u64)blockIdx.x * QPZK_COOP_GROUPS + g;
+  const bool live = t < nout;
+  if (!live) t = nout - 1;
+  u64 s = lane < 8 ? in[t * 8 + lane] : 0;
+  s = poseidon_permute_coop(s, lane, xch[g]);
+  if (live && lane < 4) out[t * 4 + lane] = gl_canon(s);
+}
+
 // Generic batched sponge / permutation entry points (KATs, host API).
 __global__ void __launch_bounds__(128) k_permute(u64* states, u64 n) {
   u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;

@@ -192,4 +192,51 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
   }
 }
 
+
+// ---- low-latency variant: 16 lanes per permutation (12 active), one state word per lane ----------
+// The thread-per-permutation kernel above is the throughput path; one permutation there is ~20k
+// dependent-ish instructions = ~50 us. Small Merkle levels, FRI trees and voting-sized commits have too
+// few permutations to fill the machine, so their time is that latency times the number of dependent
+// steps. Here the 12 s-boxes of a full round run in parallel lanes and the MDS row of each lane reads
+// the other 11 words from a shared-memory exchange: ~4.8k serial instructions per permutation. Every
+// round is executed in the textbook form (constants, s-box on all lanes or on lane 0, MDS) - the same
+// permutation as the sparse partial-round form, so results are bit-identical.
+__device__ u64 g_rc[360];  // lane-indexed reads: global/L1, not the constant bank (divergent index)
+
+// s: this lane's state word (lanes 12..15 of the group carry garbage and must be ignored by the caller).
+// xch: 24 u64 of shared memory private to the 16-lane group (double buffer).
+GL_DEV u64 poseidon_permute_coop(u64 s, u32 lane, u64* xch) {
+  const bool act = lane < 12;
+  const u32 li = act ? lane : 0;
+#pragma unroll 1
+  for (int r = 0; r < 30; r++) {
+    s = gl_add_c(s, __ldg(&g_rc[r * 12 + li]));
+    const bool full = r < 4 || r >= 26;
+    if (full || lane == 0) s = sbox7(s);
+    u64* buf = xch + (r & 1) * 12;
+    if (act) buf[lane] = s;
+    __syncwarp();
+    u32 al0 = 0, al1 = 0, ah0 = 0, ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+      u32 j0 = li + i, j1 = li + i + 1;
+      j0 = j0 >= 12 ? j0 - 12 : j0;
+      j1 = j1 >= 12 ? j1 - 12 : j1;
+      const u64 v0 = buf[j0], v1 = buf[j1];
+      mad_wide(al0, al1, (u32)v0, c_mds_circ[i]);
+      mad_wide(ah0, ah1, (u32)(v0 >> 32), c_mds_circ[i]);
+      mad_wide(bl0, bl1, (u32)v1, c_mds_circ[i + 1]);
+      mad_wide(bh0, bh1, (u32)(v1 >> 32), c_mds_circ[i + 1]);
+    }
+    if (lane == 0) {
+      mad_wide(al0, al1, (u32)s, c_mds_diag0);
+      mad_wide(ah0, ah1, (u32)(s >> 32), c_mds_diag0);
+    }
+    u64 lo = (((u64)al1 << 32) | al0) + (((u64)bl1 << 32) | bl0);   // < 2^43: no overflow
+    u64 hi = (((u64)ah1 << 32) | ah0) + (((u64)bh1 << 32) | bh0);
+    s = mds_combine((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+  }
+  return s;
+}
+
 }  // namespace qpzk

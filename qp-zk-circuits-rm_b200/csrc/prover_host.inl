@@ -12,46 +12,67 @@
 namespace qpzk {
 
 // ---- host Poseidon for the transcript (same tables the device uses) ----
+// ~100 permutations per proof sit on the latency path between device stages, so this is written
+// branch-free on any-u64 representatives (canonical only at the end), like the device code.
 struct HostPoseidon {
+  typedef unsigned __int128 u128;
   const PoseidonTablesHost* T;
-  static u64 sbox(u64 x) {
-    u64 x2 = glh::mul(x, x), x4 = glh::mul(x2, x2), x3 = glh::mul(x, x2);
-    return glh::mul(x3, x4);
+  static inline u64 red(u128 x) {  // 2^64 == EPS, 2^96 == -1; neither correction can wrap twice
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hh = hi >> 32, hl = hi & GL_EPS;
+    u64 t0 = lo - hh;
+    t0 -= ((u64)0 - (u64)(lo < hh)) & GL_EPS;
+    u64 t1 = hl * GL_EPS;
+    u64 t2 = t0 + t1;
+    t2 += ((u64)0 - (u64)(t2 < t1)) & GL_EPS;
+    return t2;
+  }
+  static inline u64 mulr(u64 a, u64 b) { return red((u128)a * b); }
+  static inline u64 addr(u64 a, u64 b) {  // both operands any u64: the first correction may wrap once more
+    u64 s = a + b;
+    u64 s2 = s + (((u64)0 - (u64)(s < a)) & GL_EPS);
+    return s2 + (((u64)0 - (u64)(s2 < s)) & GL_EPS);
+  }
+  static inline u64 canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+  static inline u64 sbox(u64 x) {
+    u64 x2 = mulr(x, x), x4 = mulr(x2, x2), x3 = mulr(x, x2);
+    return mulr(x3, x4);
   }
   static void mds(u64* s) {
     u64 o[12];
     for (int r = 0; r < 12; r++) {
-      unsigned __int128 acc = 0;
-      for (int i = 0; i < 12; i++) acc += (unsigned __int128)s[(i + r) % 12] * kMdsCirc[i];
-      if (r == 0) acc += (unsigned __int128)s[0] * kMdsDiag0;
-      o[r] = (u64)(acc % GL_P);
+      u128 acc = 0;  // 12 terms of < 2^70: no overflow
+      for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * kMdsCirc[i];
+      if (r == 0) acc += (u128)s[0] * kMdsDiag0;
+      o[r] = red(acc);
     }
     memcpy(s, o, sizeof o);
   }
   void permute(u64* s) const {
     for (int r = 0; r < 4; r++) {
-      for (int i = 0; i < 12; i++) s[i] = sbox(glh::add(s[i], T->rc[12 * r + i]));
+      for (int i = 0; i < 12; i++) s[i] = sbox(addr(s[i], T->rc[12 * r + i]));
       mds(s);
     }
-    for (int i = 0; i < 12; i++) s[i] = glh::add(s[i], T->fast_first[i]);
+    for (int i = 0; i < 12; i++) s[i] = addr(s[i], T->fast_first[i]);
     u64 o[12] = {s[0]};
     for (int c = 1; c < 12; c++) {
       u64 acc = 0;
-      for (int r = 1; r < 12; r++) acc = glh::add(acc, glh::mul(s[r], T->fast_init[(r - 1) * 11 + (c - 1)]));
+      for (int r = 1; r < 12; r++) acc = addr(acc, mulr(s[r], T->fast_init[(r - 1) * 11 + (c - 1)]));
       o[c] = acc;
     }
     memcpy(s, o, sizeof o);
     for (int r = 0; r < 22; r++) {
-      u64 s0 = glh::add(sbox(s[0]), T->fast_rc[r]);
-      u64 d = glh::mul(s0, 25);
-      for (int i = 1; i < 12; i++) d = glh::add(d, glh::mul(s[i], T->fast_w_hat[r * 11 + i - 1]));
-      for (int i = 1; i < 12; i++) s[i] = glh::add(s[i], glh::mul(s0, T->fast_v[r * 11 + i - 1]));
+      u64 s0 = addr(sbox(s[0]), T->fast_rc[r]);
+      u64 d = mulr(s0, 25);
+      for (int i = 1; i < 12; i++) d = addr(d, mulr(s[i], T->fast_w_hat[r * 11 + i - 1]));
+      for (int i = 1; i < 12; i++) s[i] = addr(s[i], mulr(s0, T->fast_v[r * 11 + i - 1]));
       s[0] = d;
     }
     for (int r = 0; r < 4; r++) {
-      for (int i = 0; i < 12; i++) s[i] = sbox(glh::add(s[i], T->rc[12 * (26 + r) + i]));
+      for (int i = 0; i < 12; i++) s[i] = sbox(addr(s[i], T->rc[12 * (26 + r) + i]));
       mds(s);
     }
+    for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
   }
 };
 

@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -234,14 +235,21 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
 }
 
 // Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
+// Below this many independent permutations a launch cannot fill the machine with one thread per
+// permutation (148 SMs x 768 threads) and the 16-lane low-latency kernels win (measured crossover).
+static u64 kCoopMaxPerms = 8192;
 // [leaf0, leaf0 + nleaves) restricts the work to a range of whole cap subtrees (multi-GPU shard); the
 // default is the whole tree.
 static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u32 log_n, u32 cap_height,
                       u64* levels, cudaEvent_t after_leaves, u64 leaf0 = 0, u64 nleaves = 0) {
   u64 N = (u64)1 << log_n;
   if (nleaves == 0) nleaves = N - leaf0;
-  k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
-                                                                       levels + leaf0 * 4);
+  if (nleaves <= kCoopMaxPerms)
+    k_leaf_hash_coop<<<(unsigned)((nleaves + QPZK_COOP_GROUPS - 1) / QPZK_COOP_GROUPS), QPZK_COOP_THREADS, 0, c->stream>>>(
+        src + leaf0 * rs, rs, cs, width, nleaves, levels + leaf0 * 4);
+  else
+    k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
+                                                                         levels + leaf0 * 4);
   c->launches++;
   CU(cudaGetLastError());
   if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
@@ -250,7 +258,11 @@ static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u3
     u64 nout = nleaves >> (l + 1), first = leaf0 >> (l + 1);
     const u64* in = levels + (twoN - (twoN >> l) + 2 * first) * 4;
     u64* out = levels + (twoN - (twoN >> (l + 1)) + first) * 4;
-    k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
+    if (nout <= kCoopMaxPerms)
+      k_merkle_level_coop<<<(unsigned)((nout + QPZK_COOP_GROUPS - 1) / QPZK_COOP_GROUPS), QPZK_COOP_THREADS, 0, c->stream>>>(
+          in, out, nout);
+    else
+      k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -314,6 +326,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
   CU(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(QPZK_ERR_BAD_ARG, "no such CUDA device (there is no CPU fallback)");
   CU(cudaSetDevice(device));
+  if (const char* e = getenv("QPZK_COOP_MAX")) kCoopMaxPerms = strtoull(e, nullptr, 10);  // tuning knob
   qpzk_ctx* c = new qpzk_ctx();
   c->device = device;
   cudaDeviceProp prop;
@@ -336,6 +349,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
       build_poseidon_tables(T);
     }
     CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
+    CU(cudaMemcpyToSymbol(g_rc, T->rc, sizeof T->rc));
     CU(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
     CU(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
     CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));

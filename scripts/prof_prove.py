@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Driver for timing / ncu: a few proofs of a synthetic wormhole-shaped circuit (no oracle)."""
+"""Tiny driver: single-stream proof latency and stage times for a synthetic circuit of 2^k rows."""
 import os
 import sys
 import time
@@ -11,20 +11,27 @@ import qpzk  # noqa: E402
 from qpzk import synth  # noqa: E402
 
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 14
-zk = (sys.argv[2] == "1") if len(sys.argv) > 2 else True
-reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+zk = bool(int(sys.argv[2])) if len(sys.argv) > 2 else (k == 14)
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 ctx = qpzk.Context(0)
-t0 = time.time()
 circ = synth.build(k, zk=zk, seed=1, provider=synth.GpuProvider(ctx))
-print("synth %.1fs" % (time.time() - t0))
-t0 = time.time()
-c = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
-print("circuit_create %.2f ms" % ((time.time() - t0) * 1e3), ctx.stage_ms())
-for i in range(reps):
-    l0 = ctx.launch_count()
-    t0 = time.time()
-    proof = c.prove(circ["wires"], circ["public_inputs"], circ["salts"])
-    dt = (time.time() - t0) * 1e3
-    st = c.stage_ms()
-    print("prove %.2f ms wall, launches %d, stages sum %.2f: %s" % (dt, ctx.launch_count() - l0, sum(st.values()),
-          {a: round(b, 3) for a, b in st.items()}), len(proof))
+gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+d = ctx.dev_alloc(circ["wires"].nbytes)
+ctx.h2d(d, circ["wires"])
+ds = None
+if circ["salts"] is not None:
+    ds = []
+    for s in circ["salts"]:
+        p = ctx.dev_alloc(s.nbytes)
+        ctx.h2d(p, s)
+        ds.append(p)
+lat = []
+for i in range(reps + 3):
+    t0 = time.perf_counter()
+    proof = gc.prove_dev(d, circ["public_inputs"], ds)
+    if i >= 3:
+        lat.append((time.perf_counter() - t0) * 1e3)
+st = gc.stage_ms()
+print("k=%d zk=%d coop_max=%s latency median %.3f ms min %.3f | %s" % (
+    k, zk, os.environ.get("QPZK_COOP_MAX", "default"), float(np.median(lat)), float(np.min(lat)),
+    " ".join("%s=%.3f" % (a, b) for a, b in st.items())))
