@@ -44,18 +44,23 @@ GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 // two-input adds with a single carry flag; SASS IADD3 has three inputs and two carries).
 // The single correction never wraps again: if k = 1 then t mod 2^64 <= 2^64 - 2^33, and if k = -1
 // then t mod 2^64 >= 2^64 - h.
-GL_DEV u64 gl_fold(u64 lo, u32 r2, u64 h) {
-#if GL_FOLD_ALU
-  // same fold with r2*EPS = (r2 << 32) - r2 and k*EPS = (k << 32) - k spelled as adds: no multiplier use
+// Two spellings of the same fold. They differ only in which pipe pays for r2*EPS and k*EPS:
+//  gl_fold_alu: (r2 << 32) - r2 and (k << 32) - k as adds. Default: Poseidon saturates the multiplier
+//               (FMA-heavy) pipe (ncu: 88 % with the multiplier spelling, ALU at 43 %).
+//  gl_fold_mul: two IMAD.WIDE. Measured on the NTT kernels, which saturate the ALU pipe instead
+//               (ALU 76 %): no difference there - ptxas rewrites multiplications by 2^32 - 1 into
+//               shift/subtract itself - so it is kept only as the -DGL_FOLD_ALU=0 experiment.
+GL_DEV u64 gl_fold_alu(u64 lo, u32 r2, u64 h) {
   __int128 t = (__int128)(unsigned __int128)lo - (__int128)(unsigned __int128)((u64)r2 + h) +
                (__int128)(unsigned __int128)((u64)r2 << 32);
   u64 tl = (u64)t;
-  u32 k = (u32)(u64)(t >> 64);
+  u32 k = (u32)(u64)(t >> 64);  // 0, 1 or 0xffffffff
   u32 tl0 = (u32)tl, tl1 = (u32)(tl >> 32);
   u32 sx = (u32)((int32_t)k >> 31);
   asm("sub.cc.u32 %0, %0, %2; subc.u32 %1, %1, %3; add.u32 %1, %1, %2;" : "+r"(tl0), "+r"(tl1) : "r"(k), "r"(sx));
   return ((u64)tl1 << 32) | tl0;
-#else
+}
+GL_DEV u64 gl_fold_mul(u64 lo, u32 r2, u64 h) {
   __int128 t = (__int128)(unsigned __int128)lo + (__int128)((u64)r2 * GL_EPS) - (__int128)(unsigned __int128)h;
   u64 tl = (u64)t;
   u32 k = (u32)(u64)(t >> 64);  // 0, 1 or 0xffffffff
@@ -63,6 +68,12 @@ GL_DEV u64 gl_fold(u64 lo, u32 r2, u64 h) {
   u32 rl = (u32)r, rh = (u32)(r >> 32);
   asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(rh) : "r"(k));  // ... so give the 2^32 back: hi += k >> 31
   return ((u64)rh << 32) | rl;
+}
+GL_DEV u64 gl_fold(u64 lo, u32 r2, u64 h) {
+#if GL_FOLD_ALU
+  return gl_fold_alu(lo, r2, h);
+#else
+  return gl_fold_mul(lo, r2, h);
 #endif
 }
 // x = r0 + 2^32 r1 + 2^64 r2 + 2^96 r3 (+ 2^128 r4, r4 < 2^31)  ->  (r1:r0) + r2*EPS - (r4:r3)

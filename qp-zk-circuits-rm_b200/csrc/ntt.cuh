@@ -111,17 +111,39 @@ GL_DEV u32 tile_pos(u32 c, u32 e, u32 cnt_log, u32 pitch) {
   return INTERLEAVED ? (e << cnt_log) + c : c * pitch + e + (e >> 4);
 }
 
+// Tile accessors for the stages. A stage reads its 2^LOGR inputs through LD and writes its outputs
+// through ST; inside a pass both are the shared-memory tile, but the FIRST stage of a kernel reads
+// straight from global memory (all of a thread's loads are issued before any arithmetic, and one
+// shared-memory round trip disappears) and the LAST stage may write straight to global memory.
+template <bool INTERLEAVED>
+struct TileLd {
+  const u64* sm; u32 cnt_log, pitch;
+  GL_DEV u64 operator()(u32 c, u32 e) const { return sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)]; }
+};
+template <bool INTERLEAVED>
+struct TileSt {
+  u64* sm; u32 cnt_log, pitch;
+  GL_DEV void operator()(u32 c, u32 e, u64 v) const { sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)] = v; }
+};
+struct NoPre {
+  GL_DEV void operator()() const {}
+};
+
 // One stage: 2^LOGR-point DFTs over the elements base + i*q of every block of length m = 2^m_log,
-// then the inter-stage twiddle w_m^(e_lo * k1), results stored in DIF order (sub-block rev(k1)).
-// tw[e] = w_len^e for e < len.
-template <int LOGR, bool INTERLEAVED, bool INV>
-GL_DEV void dif_stage(u64* sm, const u64* tw, int lg, int m_log, u32 cnt_log, u32 pitch) {
+// then the inter-stage twiddle w_m^(e_lo * k1); output k1 goes to sub-block rev(k1) (DIF order).
+// tw[e] = w_len^e for e < len. `pre` runs after the first item's loads have been issued and before any
+// twiddle is read (a first stage uses it to fill the twiddle table and __syncthreads()).
+template <int LOGR, bool INTERLEAVED, bool INV, class LD, class ST, class PRE>
+GL_DEV void dif_stage(const u64* tw, int lg, int m_log, u32 cnt_log, LD ld, ST st, PRE pre) {
   constexpr int R = 1 << LOGR;
   const u32 q_log = m_log - LOGR, q = 1u << q_log;
   const u32 per_c_log = lg - LOGR;
   const u32 total = 1u << (per_c_log + cnt_log);
-  for (u32 id = threadIdx.x; id < total; id += blockDim.x) {
-    u32 c, rest;
+  u32 id = threadIdx.x;
+  u32 c = 0, e_lo = 0, base = 0;
+  u64 x[R];
+  auto fetch = [&]() {
+    u32 rest;
     if (INTERLEAVED) {
       c = id & ((1u << cnt_log) - 1);
       rest = id >> cnt_log;
@@ -129,41 +151,88 @@ GL_DEV void dif_stage(u64* sm, const u64* tw, int lg, int m_log, u32 cnt_log, u3
       rest = id & ((1u << per_c_log) - 1);
       c = id >> per_c_log;
     }
-    const u32 e_lo = rest & (q - 1), blk = rest >> q_log;
-    const u32 base = (blk << m_log) + e_lo;
-    u64 x[R];
+    e_lo = rest & (q - 1);
+    base = ((rest >> q_log) << m_log) + e_lo;
 #pragma unroll
-    for (int i = 0; i < R; i++) x[i] = sm[tile_pos<INTERLEAVED>(c, base + ((u32)i << q_log), cnt_log, pitch)];
+    for (int i = 0; i < R; i++) x[i] = ld(c, base + ((u32)i << q_log));
+  };
+  bool has = id < total;
+  if (has) fetch();
+  pre();
+  while (has) {
     dft_regs<LOGR, INV>(x);
 #pragma unroll
     for (int p = 0; p < R; p++) {
       const u32 k1 = __brev((u32)p) >> (32 - LOGR);
       u64 v = x[p];
       if (p != 0 && q > 1) v = gl_mul(v, tw[(e_lo * k1) << (lg - m_log)]);
-      sm[tile_pos<INTERLEAVED>(c, base + ((u32)p << q_log), cnt_log, pitch)] = v;
+      st(c, base + ((u32)p << q_log), v);
     }
+    id += blockDim.x;
+    has = id < total;
+    if (has) fetch();
   }
   __syncthreads();
 }
 
-// Full in-tile DIF: after the call, position p of every transform holds X[rev_lg(p)].
-template <bool INTERLEAVED, bool INV>
-GL_DEV void smem_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch) {
+// Full tile DIF of `cnt` transforms of length 2^lg: first stage reads through `ld0` (after which
+// `pre` runs once), stages in between use the shared-memory tile, the last stage writes through `stN`.
+// Afterwards position p of every transform holds X[rev_lg(p)].
+template <bool INTERLEAVED, bool INV, class LD0, class STN, class PRE>
+GL_DEV void tile_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch, LD0 ld0, STN stN, PRE pre) {
+  TileLd<INTERLEAVED> tl{sm, cnt_log, pitch};
+  TileSt<INTERLEAVED> ts{sm, cnt_log, pitch};
+  if (lg == 0) {  // nothing to transform: copy through
+    pre();
+    for (u32 c = threadIdx.x; c < (1u << cnt_log); c += blockDim.x) stN(c, 0, ld0(c, 0));
+    __syncthreads();
+    return;
+  }
+  const int first = lg >= 4 ? 4 : lg;
+#define QPZK_STAGE(LOGR, LD, ST, PRE_) dif_stage<LOGR, INTERLEAVED, INV>(tw, lg, m_log, cnt_log, LD, ST, PRE_)
   int m_log = lg;
-  while (m_log >= 4) {
-    dif_stage<4, INTERLEAVED, INV>(sm, tw, lg, m_log, cnt_log, pitch);
+  if (lg <= 4) {  // single stage: global in, `stN` out
+    if (lg == 4) QPZK_STAGE(4, ld0, stN, pre);
+    if (lg == 3) QPZK_STAGE(3, ld0, stN, pre);
+    if (lg == 2) QPZK_STAGE(2, ld0, stN, pre);
+    if (lg == 1) QPZK_STAGE(1, ld0, stN, pre);
+    return;
+  }
+  QPZK_STAGE(4, ld0, ts, pre);
+  m_log -= first;
+  while (m_log > 4) {
+    QPZK_STAGE(4, tl, ts, NoPre());
     m_log -= 4;
   }
-  if (m_log == 3) dif_stage<3, INTERLEAVED, INV>(sm, tw, lg, 3, cnt_log, pitch);
-  if (m_log == 2) dif_stage<2, INTERLEAVED, INV>(sm, tw, lg, 2, cnt_log, pitch);
-  if (m_log == 1) dif_stage<1, INTERLEAVED, INV>(sm, tw, lg, 1, cnt_log, pitch);
+  if (m_log == 4) QPZK_STAGE(4, tl, stN, NoPre());
+  if (m_log == 3) QPZK_STAGE(3, tl, stN, NoPre());
+  if (m_log == 2) QPZK_STAGE(2, tl, stN, NoPre());
+  if (m_log == 1) QPZK_STAGE(1, tl, stN, NoPre());
+#undef QPZK_STAGE
 }
+
+// Twiddle-table fill used as the `pre` step of a kernel's first stage.
+struct TwFill {
+  u64* tw; RootTab tab; u32 len; int shift;
+  GL_DEV void operator()() const {
+    for (u32 e = threadIdx.x; e < len; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << shift);
+    __syncthreads();
+  }
+};
 
 // ---- single-CTA transform for n <= 2^12 ----
 // grid (ncols, ncosets). src column c at src + c*src_stride (natural order).
 // Output column c, coset t at dst + c*dst_stride + brev(t, r)*n:
 //   NATURAL_OUT = false : DIF order (position = bit-reversed index)  [LDE flavour]
 //   NATURAL_OUT = true  : natural order                              [IFFT flavour]
+struct SmallLd {  // natural-order input column, optional coset pre-multiplier
+  const u64* s; const u64* pmt;
+  GL_DEV u64 operator()(u32, u32 j) const {
+    u64 v = s[j];
+    if (pmt) v = gl_mul(v, pmt[j]);
+    return v;
+  }
+};
 template <bool NATURAL_OUT>
 __global__ void __launch_bounds__(256)
 k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
@@ -175,16 +244,9 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
   u64* tw = smem + pitch;
   // leaf block blk (n consecutive bit-reversed leaves) holds coset t = rev_r(blk)
   const u32 col = blockIdx.x, blk = blk0 + blockIdx.y, t = brev(blk, r);
-  const u64* s = src + (u64)col * src_stride;
-  const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
-  for (u32 j = threadIdx.x; j < n; j += blockDim.x) {
-    u64 v = s[j];
-    if (pmt) v = gl_mul(v, pmt[j]);
-    x[tile_pos<false>(0, j, 0, pitch)] = v;
-  }
-  for (u32 e = threadIdx.x; e < n; e += blockDim.x) tw[e] = root_pow(tab, e);
-  __syncthreads();
-  smem_dif<false, NATURAL_OUT>(x, tw, k, 0, pitch);   // the natural-order flavour is the inverse transform
+  SmallLd ld{src + (u64)col * src_stride, pm ? pm + ((u64)t << k) : nullptr};
+  // the natural-order flavour is the inverse transform
+  tile_dif<false, NATURAL_OUT>(x, tw, k, 0, pitch, ld, TileSt<false>{x, 0, pitch}, TwFill{tw, tab, n, 0});
   u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 q = threadIdx.x; q < n; q += blockDim.x) {
     u64 v = x[tile_pos<false>(0, NATURAL_OUT ? brev(q, k) : q, 0, pitch)];
@@ -197,6 +259,24 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
 // View column as [n1 = 2^a][n2 = 2^b]. grid (n2/COLS, ncols, ncosets); tile [n1][COLS].
 //   ROW_BITREV = true  : result for frequency k1 is stored at row rev_a(k1)   [LDE flavour]
 //   ROW_BITREV = false : stored at row k1                                     [IFFT flavour]
+struct PassALd {  // element j1 of column j2_base + c of the [n1][n2] view, optional coset pre-multiplier
+  const u64* s; const u64* pmt; int b; u32 j2_base;
+  GL_DEV u64 operator()(u32 c, u32 j1) const {
+    u64 j = ((u64)j1 << b) + j2_base + c;
+    u64 v = s[j];
+    if (pmt) v = gl_mul(v, pmt[j]);
+    return v;
+  }
+};
+template <bool ROW_BITREV>
+struct PassASt {  // DIF position p = frequency k1 = rev_a(p): inter-pass twiddle w_n^(j2*k1), row p or k1
+  u64* d; RootTab tab; int a, b; u32 j2_base;
+  GL_DEV void operator()(u32 c, u32 p, u64 v) const {
+    u32 k1 = brev(p, a), j2 = j2_base + c;
+    v = gl_mul(v, root_pow(tab, (u64)j2 * k1));
+    d[((u64)(ROW_BITREV ? p : k1) << b) + j2] = v;  // non-canonical is fine: pass B canonicalises
+  }
+};
 template <bool ROW_BITREV>
 __global__ void __launch_bounds__(256)
 k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
@@ -209,31 +289,18 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   u64* tw = smem + n1 * cols;  // [n1]
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z, t = brev(blk, r);
   const u32 j2_base = blockIdx.x * cols;
-  const u64* s = src + (u64)col * src_stride;
-  const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
-  for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
-    u32 j1 = idx >> cols_log, c = idx & (cols - 1);
-    u64 j = ((u64)j1 << b) + j2_base + c;
-    u64 v = s[j];
-    if (pmt) v = gl_mul(v, pmt[j]);
-    x[idx] = v;
-  }
-  for (u32 e = threadIdx.x; e < n1; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << b);
-  __syncthreads();
-  smem_dif<true, !ROW_BITREV>(x, tw, a, cols_log, 0);   // ROW_BITREV = forward (LDE), otherwise inverse
-  u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
-  for (u32 idx = threadIdx.x; idx < n1 * cols; idx += blockDim.x) {
-    u32 p = idx >> cols_log, c = idx & (cols - 1);
-    u32 k1 = brev(p, a);
-    u32 j2 = j2_base + c;
-    u64 v = gl_mul(x[idx], root_pow(tab, (u64)j2 * k1));
-    u32 row = ROW_BITREV ? p : k1;
-    d[((u64)row << b) + j2] = v;  // non-canonical is fine: pass B canonicalises
-  }
+  PassALd ld{src + (u64)col * src_stride, pm ? pm + ((u64)t << k) : nullptr, b, j2_base};
+  PassASt<ROW_BITREV> st{dst + (u64)col * dst_stride + ((u64)blk << k), tab, a, b, j2_base};
+  // ROW_BITREV = forward (LDE), otherwise inverse
+  tile_dif<true, !ROW_BITREV>(x, tw, a, cols_log, 0, ld, st, TwFill{tw, tab, n1, b});
 }
 
 // ---- pass B (LDE flavour): n2-point DIF along contiguous rows, in place, DIF output order ----
 // grid (n1/rows_per_cta, ncols, ncosets)
+struct RowsLd {
+  const u64* d; int b;
+  GL_DEV u64 operator()(u32 row, u32 e) const { return d[((u64)row << b) + e]; }
+};
 __global__ void __launch_bounds__(256)
 k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a, int r,
                   u32 rows_log, u32 blk0) {
@@ -246,11 +313,8 @@ k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a,
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z;
   u64* d = data + (u64)col * stride + ((u64)blk << k) + (u64)blockIdx.x * rows_per_cta * n2;
   const u32 total = rows_per_cta * n2;
-  for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x)
-    x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)] = d[idx];
-  for (u32 e = threadIdx.x; e < n2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
-  __syncthreads();
-  smem_dif<false, false>(x, tw, b, rows_log, pitch);
+  tile_dif<false, false>(x, tw, b, rows_log, pitch, RowsLd{d, b}, TileSt<false>{x, rows_log, pitch},
+                         TwFill{tw, tab, n2, a});
   for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x)
     d[idx] = gl_canon(x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)]);
 }
@@ -269,11 +333,8 @@ k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restr
   const u32 col = blockIdx.y;
   const u32 k1_base = blockIdx.x * rc;
   const u64* s = tmp + (u64)col * tmp_stride + ((u64)k1_base << b);
-  for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x)
-    x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)] = s[idx];
-  for (u32 e = threadIdx.x; e < n2; e += blockDim.x) tw[e] = root_pow(tab, (u64)e << a);
-  __syncthreads();
-  smem_dif<false, true>(x, tw, b, rc_log, pitch);
+  tile_dif<false, true>(x, tw, b, rc_log, pitch, RowsLd{s, b}, TileSt<false>{x, rc_log, pitch},
+                        TwFill{tw, tab, n2, a});
   u64* d = dst + (u64)col * dst_stride;
   for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x) {
     u32 k2 = idx >> rc_log, rr = idx & (rc - 1);
