@@ -29,6 +29,14 @@ def test_library_exports_every_declared_symbol():
     assert set(syms) <= set(L._declared), set(syms) - set(L._declared)
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/qpzk-sys/src/lib.rs (the FFI crate a patched qp-plonky2 links) must declare
+    exactly the header's symbols; it cannot be compiled in this image, so at least keep it in sync."""
+    rs = open(os.path.join(ROOT, "rust", "qpzk-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (qpzk_[a-z0-9_]+)\(", rs))
+    assert declared == set(_header_symbols()), declared ^ set(_header_symbols())
+
+
 def test_no_torch_types_in_abi():
     src = open(os.path.join(ROOT, "include", "qpzk.h")).read()
     assert "torch" not in src and "at::" not in src and "#include <cuda" not in src
