@@ -46,6 +46,11 @@ WORKLOAD = ("wormhole single-proof generation, bench-data shape (2^14 x 135 wire
             "Noop/Constant/PublicInput/BaseSum63/Arithmetic20/Poseidon, FRI [4,4,4], salted), synthetic satisfying witness")
 
 
+NTT_DRAM_BYTES_PER_COMMIT = int((70.916096 + 70.898688 + 558.888192 + 566.393088 +
+                                 26.451968 + 25.257216 + 522.532096 + 505.859584) * 1e6)
+LEAF_HASH_DRAM_BYTES_PER_COMMIT = int((572.058624 + 46.661888) * 1e6)   # profiles/r1_poseidon_v3_ncu_full.txt
+
+
 def algorithmic_counts(k=DEGREE_BITS, c=NCOLS, s=0, r=RATE_BITS, h=CAP_HEIGHT):
     """SURVEY.md §8(d) / BASELINE.md §4 per-commit work."""
     n, N = 1 << k, 1 << (k + r)
@@ -461,7 +466,11 @@ def run_gpu(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "commit microbench: IFFT + coset-LDE NTT passes "
                                                    "(k_ntt_pass_a / k_ntt_pass_b_*)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg["ntt_bytes"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the four NTT launches of one commit,
+                         # from the ncu --set full capture profiles/r1_ntt_fused_ncu_full.txt (two passes over
+                         # HBM: 3.7x the algorithmic bytes - the second pass re-reads and re-writes the LDE)
+                         "traffic": NTT_DRAM_BYTES_PER_COMMIT, "traffic_source": "profiles/r1_ntt_fused_ncu_full.txt",
+                         "peak_source": peak_src, "algorithmic_bytes": alg["ntt_bytes"],
                          "stage_ms": ntt_ms},
             "roofline_int": {"bound": "int32-multiply", "kernel": "commit microbench: k_leaf_hash + k_merkle_level "
                                                                   "(Poseidon; the dominant kernel of every step)",
@@ -472,6 +481,7 @@ def run_gpu(args, rank, local_rank, world):
                                             "per thread, SASS-checked; 6612 such multiplies per permutation is the "
                                             "algorithmic minimum (SURVEY 8(d))",
                              "peak_imad_32bit": imad_lo / 1e12, "permutations": alg["perms"],
+                             "traffic": LEAF_HASH_DRAM_BYTES_PER_COMMIT,
                              "perms_per_s": alg["perms"] / (hash_ms * 1e-3), "stage_ms": hash_ms},
             "clocks": clocks,
         }
