@@ -239,6 +239,33 @@ def commit_microbench(ctx, qpzk, steps, warmup, rank):
     return {k2: float(np.mean([s[k2] for s in stages])) for k2 in stages[0]}
 
 
+def commit_sweep(ctx, qpzk, ks=(12, 13, 14, 15, 16, 17, 18, 19, 20)):
+    """The metric's "LDE+Merkle commit ms @ 2^k rows" curve (SURVEY 8(d)): PolynomialBatch::from_values of a
+    2^k x 135 trace, rate_bits 3, cap_height 4, device-resident input, CUDA-event stage times (best of 3)."""
+    out = {}
+    for k in ks:
+        n = 1 << k
+        tr = splitmix_trace(0x5EED0001 + k, NCOLS, n)
+        d = ctx.dev_alloc(tr.nbytes)
+        ctx.h2d(d, tr)
+        best = None
+        for _ in range(4):
+            b = qpzk.PolynomialBatch.from_values_dev(ctx, d, NCOLS, n, RATE_BITS, CAP_HEIGHT)
+            st = ctx.stage_ms()
+            b.free()
+            tot = sum(st.values())
+            if best is None or tot < best[0]:
+                best = (tot, st)
+        ctx.dev_free(d)
+        alg = algorithmic_counts(k=k)
+        ntt = best[1]["ifft"] + best[1]["lde"]
+        hsh = best[1]["leaf_hash"] + best[1]["merkle_levels"]
+        out["2^%d" % k] = {"ms": best[0], "ntt_ms": ntt, "poseidon_ms": hsh,
+                           "ntt_GBps_algorithmic": alg["ntt_bytes"] / (ntt * 1e-3) / 1e9,
+                           "Mperm_per_s": alg["perms"] / (hsh * 1e-3) / 1e6}
+    return out
+
+
 def sharded_commit_bench(ctx, qpzk, torch, dist, rank, world, steps, warmup):
     """BASELINE configs[2] at N GPUs: ONE 2^16 x 135 commit sharded over the ranks by cap subtrees (whole
     LDE cosets), every rank holding the trace; the only exchange is the NCCL all-gather of the 16 subtree
@@ -414,6 +441,7 @@ def run_gpu(args, rank, local_rank, world):
     if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
         sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
     micro = commit_microbench(ctx0, qpzk, 5, 3, rank) if rank == 0 else None
+    sweep = commit_sweep(ctx0, qpzk) if rank == 0 else None
     imad_wide = ctx0.measure_imad_peak(1)
     imad_lo = ctx0.measure_imad_peak(0)
 
@@ -485,6 +513,7 @@ def run_gpu(args, rank, local_rank, world):
                              "perms_per_s": alg["perms"] / (hash_ms * 1e-3), "stage_ms": hash_ms},
             "clocks": clocks,
         }
+        line["commit_microbench"]["ms_at_2^k_rows"] = sweep
         if sharded is not None:
             line["commit_microbench"]["sharded"] = sharded
         if voting is not None:

@@ -215,10 +215,11 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
                                                                 tab, k, 0, ninv, 0);
     c->launches++;
   } else {
-    if (k > 18) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 18 not supported");
+    if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 20 not supported");
     int a = (k + 1) / 2, b = k - a;
-    u32 cols_log = a <= 8 ? 4 : 3, cols = 1u << cols_log;
-    u32 rc_log = b <= 8 ? 4 : 3, rc = 1u << rc_log;
+    // tiles of 4096 elements: [2^a][cols] in pass A, [rc][2^b] in pass B
+    u32 cols_log = a <= 8 ? 4 : 12 - a, cols = 1u << cols_log;
+    u32 rc_log = b <= 8 ? 4 : 12 - b, rc = 1u << rc_log;
     u64* tmp;
     QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
     size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;

@@ -212,3 +212,26 @@ def test_microbench_full_size(ctx):
     assert np.array_equal(((ra.astype(object) + rb.astype(object)) % P).astype(np.uint64), rs)
     for x in (b, ba, bb, bs):
         x.free()
+
+
+@pytest.mark.parametrize("k", [17, 19, 20])
+def test_large_degrees_roundtrip_and_paths(ctx, k):
+    """degree_bits above the microbench (up to 2^20 rows): interpolation round trip against the oracle's FFT
+    on a few columns, LDE rows are evaluations of the committed polynomials, paths verify against the cap."""
+    import qpzk
+    ncols, r, cap_h = 3, 3, 4
+    n, N = 1 << k, 1 << (k + r)
+    vals = splitmix64(0x5EED0100 + k, ncols * n).reshape(ncols, n)
+    b = qpzk.PolynomialBatch.from_values(ctx, vals, r, cap_h)
+    coeffs = b.polynomials
+    for c in range(ncols):
+        assert np.array_equal(orc.fft(coeffs[c]), vals[c])
+    cap = b.cap
+    rng = np.random.default_rng(k)
+    wN = orc.root_of_unity(k + r)
+    lde0 = orc.coset_fft(np.concatenate([coeffs[0], np.zeros(N - n, np.uint64)]))   # natural order on g*<w_N>
+    for leaf in [0, N - 1] + [int(x) for x in rng.integers(0, N, 6)]:
+        row, sib = b.open(leaf)
+        assert orc.merkle_verify(row, leaf, cap, sib)
+        assert int(row[0]) == int(lde0[bitrev(leaf, k + r)])
+    b.free()
