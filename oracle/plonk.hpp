@@ -7,6 +7,7 @@
 // /root/reference/wormhole/verifier/src/lib.rs:102-106 and
 // /root/reference/wormhole/verifier/benches/verifier.rs:22-25 read and write.
 #pragma once
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -31,17 +32,30 @@ template <> struct FieldOps<E2> {
   static E2 from(u64 x) { return E2{canon(x), 0}; }
 };
 
+// Gate ids = position in plonky2's default gate serializer list (the six wormhole ids are read off
+// wormhole/bench-data/common.bin; the recursion gates follow the same alphabetical list).
 enum GateId : uint32_t {
   GATE_ARITHMETIC = 0,
+  GATE_ARITHMETIC_EXT = 1,
   GATE_BASE_SUM_2 = 2,
   GATE_CONSTANT = 3,
+  GATE_COSET_INTERPOLATION = 4,
+  GATE_EXPONENTIATION = 5,
+  GATE_MUL_EXT = 8,
   GATE_NOOP = 9,
+  GATE_POSEIDON_MDS = 10,
   GATE_POSEIDON = 11,
   GATE_PUBLIC_INPUT = 12,
+  GATE_RANDOM_ACCESS = 13,
+  GATE_REDUCING_EXT = 14,
+  GATE_REDUCING = 15,
 };
 struct GateInfo {
-  uint32_t id;
-  u64 param;  // num_consts / num_limbs / num_ops; 0 when the gate has none
+  uint32_t id = 0;
+  u64 param = 0;   // num_consts / num_limbs / num_ops / num_coeffs / num_power_bits / bits / subgroup_bits
+  u64 param2 = 0;  // RandomAccess: num_copies; CosetInterpolation: degree
+  u64 param3 = 0;  // RandomAccess: num_extra_constants
+  std::vector<u64> weights;  // CosetInterpolation: barycentric weights
 };
 
 struct CommonData {
@@ -139,10 +153,24 @@ static inline CommonData parse_common(const uint8_t* p, size_t n, size_t* consum
     throw std::runtime_error("lookup tables are not supported");
   u64 ngates = r.usize();
   for (u64 i = 0; i < ngates; i++) {
-    GateInfo g{r.u32(), 0};
+    GateInfo g;
+    g.id = r.u32();
     switch (g.id) {
-      case GATE_NOOP: case GATE_PUBLIC_INPUT: case GATE_POSEIDON: break;
-      case GATE_CONSTANT: case GATE_BASE_SUM_2: case GATE_ARITHMETIC: g.param = r.usize(); break;
+      case GATE_NOOP: case GATE_PUBLIC_INPUT: case GATE_POSEIDON: case GATE_POSEIDON_MDS: break;
+      case GATE_CONSTANT: case GATE_BASE_SUM_2: case GATE_ARITHMETIC: case GATE_ARITHMETIC_EXT:
+      case GATE_MUL_EXT: case GATE_REDUCING: case GATE_REDUCING_EXT: case GATE_EXPONENTIATION:
+        g.param = r.usize();
+        break;
+      case GATE_RANDOM_ACCESS:
+        g.param = r.usize(); g.param2 = r.usize(); g.param3 = r.usize();
+        break;
+      case GATE_COSET_INTERPOLATION: {
+        g.param = r.usize(); g.param2 = r.usize();
+        u64 nw = r.usize();
+        if (nw != ((u64)1 << g.param)) throw std::runtime_error("coset interpolation: weight count");
+        for (u64 j = 0; j < nw; j++) g.weights.push_back(r.felt());
+        break;
+      }
       default: throw std::runtime_error("unsupported gate id " + std::to_string(g.id));
     }
     c.gates.push_back(g);
@@ -335,6 +363,41 @@ template <class T> static inline void poseidon_gate_constraints(const T* w, T* o
   for (int i = 0; i < 12; i++) out[k++] = s[i] - w[12 + i];
 }
 
+// ---- the recursion gate set (restated from upstream plonky2's gates/*.rs - qp-plonky2 is
+// un-vendored and the reference ships no aggregator circuit data, so unlike the six wormhole gates
+// these are NOT pinned by a fixture: "parity unpinned" until a cargo-side comparison can run) ----
+// ExtensionAlgebra over T: pairs (a, b) = a + b*X with X^2 = 7, components in T (T = F_p on the prover's
+// coset, T = F_p^2 at zeta in the verifier).
+template <class T> struct Alg {
+  T a, b;
+};
+template <class T> static inline Alg<T> operator+(Alg<T> x, Alg<T> y) { return Alg<T>{x.a + y.a, x.b + y.b}; }
+template <class T> static inline Alg<T> operator-(Alg<T> x, Alg<T> y) { return Alg<T>{x.a - y.a, x.b - y.b}; }
+template <class T> static inline Alg<T> operator*(Alg<T> x, Alg<T> y) {
+  T seven = FieldOps<T>::from(7);
+  return Alg<T>{x.a * y.a + seven * (x.b * y.b), x.a * y.b + x.b * y.a};
+}
+template <class T> static inline Alg<T> alg_scale(Alg<T> x, T s) { return Alg<T>{x.a * s, x.b * s}; }
+template <class T> static inline Alg<T> alg_at(const T* w, size_t i) { return Alg<T>{w[i], w[i + 1]}; }
+template <class T> static inline Alg<T> alg_const(u64 v) { return Alg<T>{FieldOps<T>::from(v), FieldOps<T>::from(0)}; }
+template <class T> static inline void alg_push(T* out, size_t& nc, Alg<T> x) { out[nc++] = x.a; out[nc++] = x.b; }
+
+// CosetInterpolationGate layout helpers (D = 2)
+struct CosetLayout {
+  u64 npoints, degree, nint, start_eval_point, start_eval_value, start_int, start_shifted;
+  CosetLayout(u64 subgroup_bits, u64 deg) {
+    npoints = (u64)1 << subgroup_bits;
+    degree = deg;
+    nint = (npoints - 2) / (degree - 1);
+    start_eval_point = 1 + 2 * npoints;
+    start_eval_value = start_eval_point + 2;
+    start_int = start_eval_value + 2;
+    start_shifted = start_int + 4 * nint;
+  }
+  u64 num_wires() const { return start_shifted + 2; }
+  u64 num_constraints() const { return 2 + 4 * nint + 2; }
+};
+
 // evaluate_gate_constraints: out[num_gate_constraints] = sum_g filter_g * constraint_{g,slot}.
 // local_constants has num_constants entries (selectors first), local_wires num_wires.
 template <class T>
@@ -382,6 +445,106 @@ static inline void eval_gate_constraints(const CommonData& c, const T* local_con
         poseidon_gate_constraints(local_wires, tmp.data());
         nc = 123;
         break;
+      case GATE_ARITHMETIC_EXT:  // output - (m0*m1*c0 + addend*c1), 4*D wires per op
+        for (u64 i = 0; i < gi.param; i++) {
+          const T* w = local_wires + 8 * i;
+          Alg<T> m0 = alg_at(w, 0), m1 = alg_at(w, 2), ad = alg_at(w, 4), o = alg_at(w, 6);
+          alg_push(tmp.data(), nc, o - (alg_scale(m0 * m1, gc[0]) + alg_scale(ad, gc[1])));
+        }
+        break;
+      case GATE_MUL_EXT:  // output - m0*m1*c0, 3*D wires per op
+        for (u64 i = 0; i < gi.param; i++) {
+          const T* w = local_wires + 6 * i;
+          alg_push(tmp.data(), nc, alg_at(w, 4) - alg_scale(alg_at(w, 0) * alg_at(w, 2), gc[0]));
+        }
+        break;
+      case GATE_POSEIDON_MDS:  // out_r - sum_i circ[i]*in[(i+r)%12] - diag[r]*in[r], on algebra elements
+        for (int r = 0; r < 12; r++) {
+          Alg<T> acc = alg_const<T>(0);
+          for (int i = 0; i < 12; i++)
+            acc = acc + alg_scale(alg_at(local_wires, 2 * ((i + r) % 12)), FO::from(MDS_CIRC[i]));
+          acc = acc + alg_scale(alg_at(local_wires, 2 * r), FO::from(MDS_DIAG[r]));
+          alg_push(tmp.data(), nc, alg_at(local_wires, 2 * (12 + r)) - acc);
+        }
+        break;
+      case GATE_RANDOM_ACCESS: {
+        const u64 bits = gi.param, copies = gi.param2, extra = gi.param3, vec = (u64)1 << bits;
+        const u64 routed = (2 + vec) * copies + extra;
+        for (u64 cp = 0; cp < copies; cp++) {
+          const T* w = local_wires + (2 + vec) * cp;
+          const T* b = local_wires + routed + cp * bits;
+          for (u64 i = 0; i < bits; i++) tmp[nc++] = b[i] * (b[i] - FO::from(1));
+          T rec = FO::from(0);
+          for (u64 i = bits; i-- > 0;) rec = rec + rec + b[i];
+          tmp[nc++] = rec - w[0];
+          std::vector<T> items(w + 2, w + 2 + vec);
+          for (u64 i = 0; i < bits; i++) {
+            std::vector<T> nxt;
+            for (size_t j = 0; j + 1 < items.size(); j += 2) nxt.push_back(items[j] + b[i] * (items[j + 1] - items[j]));
+            items.swap(nxt);
+          }
+          tmp[nc++] = items[0] - w[1];
+        }
+        for (u64 i = 0; i < extra; i++) tmp[nc++] = gc[i] - local_wires[(2 + vec) * copies + i];
+        break;
+      }
+      case GATE_REDUCING: case GATE_REDUCING_EXT: {  // acc*alpha + coeff_i - acc_i
+        const bool ext = gi.id == GATE_REDUCING_EXT;
+        const u64 ncf = gi.param, cw = ext ? 2 : 1;
+        const u64 start_accs = 6 + ncf * cw;
+        Alg<T> alpha = alg_at(local_wires, 2), acc = alg_at(local_wires, 4);
+        for (u64 i = 0; i < ncf; i++) {
+          Alg<T> cf = ext ? alg_at(local_wires, 6 + 2 * i) : Alg<T>{local_wires[6 + i], FO::from(0)};
+          Alg<T> ai = i == ncf - 1 ? alg_at(local_wires, 0) : alg_at(local_wires, start_accs + 2 * i);
+          alg_push(tmp.data(), nc, acc * alpha + cf - ai);
+          acc = ai;
+        }
+        break;
+      }
+      case GATE_EXPONENTIATION: {
+        const u64 nb = gi.param;
+        T base = local_wires[0];
+        const T* iv = local_wires + 2 + nb;
+        for (u64 i = 0; i < nb; i++) {
+          T prev = i == 0 ? FO::from(1) : iv[i - 1] * iv[i - 1];
+          T bit = local_wires[1 + (nb - 1 - i)];   // bits are little-endian, accumulated big-endian
+          tmp[nc++] = prev * (bit * base + (FO::from(1) - bit)) - iv[i];
+        }
+        tmp[nc++] = local_wires[1 + nb] - iv[nb - 1];
+        break;
+      }
+      case GATE_COSET_INTERPOLATION: {
+        CosetLayout L(gi.param, gi.param2);
+        T shift = local_wires[0];
+        Alg<T> x = alg_at(local_wires, L.start_eval_point), xs = alg_at(local_wires, L.start_shifted);
+        alg_push(tmp.data(), nc, x - alg_scale(xs, shift));
+        u64 g16 = root_of_unity((unsigned)gi.param);
+        std::vector<u64> dom(L.npoints);
+        dom[0] = 1;
+        for (u64 i = 1; i < L.npoints; i++) dom[i] = mul(dom[i - 1], g16);
+        // partial barycentric interpolation over points [lo, hi), continuing from (eval, prod)
+        auto partial = [&](u64 lo, u64 hi, Alg<T> eval, Alg<T> prod, Alg<T>& oe, Alg<T>& op) {
+          for (u64 i = lo; i < hi; i++) {
+            Alg<T> term = xs - alg_const<T>(dom[i]);
+            Alg<T> val = alg_at(local_wires, 1 + 2 * i);
+            eval = eval * term + alg_scale(val * prod, FO::from(gi.weights[i]));
+            prod = prod * term;
+          }
+          oe = eval;
+          op = prod;
+        };
+        Alg<T> ce, cp;
+        partial(0, L.degree, alg_const<T>(0), alg_const<T>(1), ce, cp);
+        for (u64 i = 0; i < L.nint; i++) {
+          Alg<T> ie = alg_at(local_wires, L.start_int + 2 * i), ip = alg_at(local_wires, L.start_int + 2 * (L.nint + i));
+          alg_push(tmp.data(), nc, ie - ce);
+          alg_push(tmp.data(), nc, ip - cp);
+          u64 lo = 1 + (L.degree - 1) * (i + 1), hi = std::min(lo + L.degree - 1, L.npoints);
+          partial(lo, hi, ie, ip, ce, cp);
+        }
+        alg_push(tmp.data(), nc, alg_at(local_wires, L.start_eval_value) - ce);
+        break;
+      }
       default: throw std::runtime_error("unsupported gate");
     }
     for (size_t j = 0; j < nc; j++) out[j] = out[j] + filter * tmp[j];

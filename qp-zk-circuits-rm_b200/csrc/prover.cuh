@@ -19,14 +19,27 @@
 
 namespace qpzk {
 
+// ids = position in plonky2's default gate serializer list
 enum : u32 {
   G_ARITHMETIC = 0,
+  G_ARITHMETIC_EXT = 1,
   G_BASE_SUM_2 = 2,
   G_CONSTANT = 3,
+  G_COSET_INTERPOLATION = 4,
+  G_EXPONENTIATION = 5,
+  G_MUL_EXT = 8,
   G_NOOP = 9,
+  G_POSEIDON_MDS = 10,
   G_POSEIDON = 11,
   G_PUBLIC_INPUT = 12,
+  G_RANDOM_ACCESS = 13,
+  G_REDUCING_EXT = 14,
+  G_REDUCING = 15,
 };
+GL_HD bool gate_is_recursion_only(u32 id) {
+  return id == G_ARITHMETIC_EXT || id == G_COSET_INTERPOLATION || id == G_EXPONENTIATION || id == G_MUL_EXT ||
+         id == G_POSEIDON_MDS || id == G_RANDOM_ACCESS || id == G_REDUCING_EXT || id == G_REDUCING;
+}
 
 #define QPZK_MAX_GATES 16
 #define QPZK_MAX_CHALLENGES 4
@@ -37,7 +50,9 @@ struct CircuitDesc {
   u32 num_wires, num_routed, num_constants, num_challenges, num_partial_products, qdf;
   u32 num_selectors, num_gates, num_gate_constraints;
   u32 gate_id[QPZK_MAX_GATES], gate_param[QPZK_MAX_GATES], gate_selector[QPZK_MAX_GATES];
+  u32 gate_param2[QPZK_MAX_GATES], gate_param3[QPZK_MAX_GATES];  // RandomAccess copies / extra constants; CosetInterpolation degree
   u32 group_lo[QPZK_MAX_GATES], group_hi[QPZK_MAX_GATES];  // indexed by selector index
+  const u64* coset_aux;  // CosetInterpolation: [2^bits] subgroup points then [2^bits] barycentric weights (device)
 };
 
 struct Challenges {
@@ -258,7 +273,134 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
   }
 }
 
+// ---- the recursion gate set: constraint order as in oracle/plonk.hpp ----
+GL_DEV gl2 ext_at(const WireRow& w, u32 i) { return gl2_make(w[i], w[i + 1]); }
+GL_DEV void aa_emit_ext(AlphaAcc& a, gl2 v) {
+  aa_emit(a, v.a);
+  aa_emit(a, v.b);
+}
+GL_DEV void recursion_gate_eval(u32 id, u32 p1, u32 p2, u32 p3, const u64* __restrict__ aux, const WireRow& w,
+                                u64 c0, u64 c1, AlphaAcc& a) {
+  switch (id) {
+    case G_ARITHMETIC_EXT:
+      for (u32 t = 0; t < p1; t++) {
+        gl2 m0 = ext_at(w, 8 * t), m1 = ext_at(w, 8 * t + 2), ad = ext_at(w, 8 * t + 4), o = ext_at(w, 8 * t + 6);
+        aa_emit_ext(a, gl2_sub(o, gl2_add(gl2_scale(gl2_mul(m0, m1), c0), gl2_scale(ad, c1))));
+      }
+      break;
+    case G_MUL_EXT:
+      for (u32 t = 0; t < p1; t++) {
+        gl2 m0 = ext_at(w, 6 * t), m1 = ext_at(w, 6 * t + 2), o = ext_at(w, 6 * t + 4);
+        aa_emit_ext(a, gl2_sub(o, gl2_scale(gl2_mul(m0, m1), c0)));
+      }
+      break;
+    case G_POSEIDON_MDS:
+      for (u32 r = 0; r < 12; r++) {
+        Acc160 sa, sb;
+        acc_init(sa);
+        acc_init(sb);
+        for (u32 i = 0; i < 12; i++) {
+          u32 j = i + r >= 12 ? i + r - 12 : i + r;
+          acc_mac(sa, w[2 * j], c_mds_circ[i]);
+          acc_mac(sb, w[2 * j + 1], c_mds_circ[i]);
+        }
+        if (r == 0) {
+          acc_mac(sa, w[0], c_mds_diag0);
+          acc_mac(sb, w[1], c_mds_diag0);
+        }
+        aa_emit_ext(a, gl2_sub(ext_at(w, 2 * (12 + r)), gl2_make(acc_reduce(sa), acc_reduce(sb))));
+      }
+      break;
+    case G_RANDOM_ACCESS: {
+      const u32 bits = p1, copies = p2, extra = p3, vec = 1u << bits;
+      const u32 routed = (2 + vec) * copies + extra;
+      for (u32 cp = 0; cp < copies; cp++) {
+        const u32 w0 = (2 + vec) * cp, b0 = routed + cp * bits;
+        u64 rec = 0;
+        for (u32 i = 0; i < bits; i++) {
+          u64 b = w[b0 + i];
+          aa_emit(a, gl_mul(b, gl_sub(b, 1)));
+        }
+        for (u32 i = bits; i-- > 0;) rec = gl_add(gl_add(rec, rec), w[b0 + i]);
+        aa_emit(a, gl_sub(rec, w[w0]));
+        u64 items[64];  // vec <= 64 (checked at circuit creation)
+        for (u32 i = 0; i < vec; i++) items[i] = w[w0 + 2 + i];
+        u32 len = vec;
+        for (u32 i = 0; i < bits; i++) {
+          u64 b = w[b0 + i];
+          len >>= 1;
+          for (u32 j = 0; j < len; j++) items[j] = gl_add(items[2 * j], gl_mul(b, gl_sub(items[2 * j + 1], items[2 * j])));
+        }
+        aa_emit(a, gl_sub(items[0], w[w0 + 1]));
+      }
+      for (u32 i = 0; i < extra; i++) aa_emit(a, gl_sub(i == 0 ? c0 : c1, w[(2 + vec) * copies + i]));
+      break;
+    }
+    case G_REDUCING:
+    case G_REDUCING_EXT: {
+      const bool ext = id == G_REDUCING_EXT;
+      const u32 ncf = p1, start_accs = 6 + ncf * (ext ? 2 : 1);
+      gl2 alpha = ext_at(w, 2), acc = ext_at(w, 4);
+      for (u32 i = 0; i < ncf; i++) {
+        gl2 cf = ext ? ext_at(w, 6 + 2 * i) : gl2_make(w[6 + i], 0);
+        gl2 ai = i == ncf - 1 ? ext_at(w, 0) : ext_at(w, start_accs + 2 * i);
+        aa_emit_ext(a, gl2_sub(gl2_add(gl2_mul(acc, alpha), cf), ai));
+        acc = ai;
+      }
+      break;
+    }
+    case G_EXPONENTIATION: {
+      const u32 nb = p1;
+      const u64 base = w[0];
+      u64 prev_iv = 1;
+      for (u32 i = 0; i < nb; i++) {
+        u64 prev = i == 0 ? 1 : gl_sqr(prev_iv);
+        u64 bit = w[1 + (nb - 1 - i)];
+        u64 iv = w[2 + nb + i];
+        aa_emit(a, gl_sub(gl_mul(prev, gl_add(gl_mul(bit, base), gl_sub(1, bit))), iv));
+        prev_iv = iv;
+      }
+      aa_emit(a, gl_sub(w[1 + nb], prev_iv));
+      break;
+    }
+    case G_COSET_INTERPOLATION: {
+      const u32 npoints = 1u << p1, degree = p2, nint = (npoints - 2) / (degree - 1);
+      const u32 sp = 1 + 2 * npoints, sv = sp + 2, si = sv + 2, ss = si + 4 * nint;
+      const u64* dom = aux;
+      const u64* wt = aux + npoints;
+      const u64 shift = w[0];
+      const gl2 x = ext_at(w, sp), xs = ext_at(w, ss);
+      aa_emit_ext(a, gl2_sub(x, gl2_scale(xs, shift)));
+      gl2 ev = gl2_make(0, 0), pr = gl2_make(1, 0);
+      u32 lo = 0, hi = degree;
+      for (u32 seg = 0; seg <= nint; seg++) {
+        for (u32 i = lo; i < hi; i++) {
+          gl2 term = gl2_sub(xs, gl2_make(dom[i], 0));
+          gl2 val = ext_at(w, 1 + 2 * i);
+          ev = gl2_add(gl2_mul(ev, term), gl2_scale(gl2_mul(val, pr), wt[i]));
+          pr = gl2_mul(pr, term);
+        }
+        if (seg == nint) break;
+        gl2 ie = ext_at(w, si + 2 * seg), ip = ext_at(w, si + 2 * (nint + seg));
+        aa_emit_ext(a, gl2_sub(ie, ev));
+        aa_emit_ext(a, gl2_sub(ip, pr));
+        ev = ie;
+        pr = ip;
+        lo = 1 + (degree - 1) * (seg + 1);
+        hi = lo + degree - 1 < npoints ? lo + degree - 1 : npoints;
+      }
+      aa_emit_ext(a, gl2_sub(ext_at(w, sv), ev));
+      break;
+    }
+    default:
+      break;
+  }
+}
+
 // One thread per LDE leaf position. out[ch][i] (natural index i) = vanishing(x_i) / Z_H(x_i).
+// RECURSION = false is the wormhole / voting gate set; the recursion gates are compiled only into the
+// <true> instantiation so that they cost the common case neither registers nor instruction cache.
+template <bool RECURSION>
 __global__ void __launch_bounds__(128)
 k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, const u64* __restrict__ zs_lde,
            u64 cs_stride, u64 wires_stride, u64 zs_stride, u32 step_bits, const u64* __restrict__ k_is,
@@ -357,6 +499,9 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
         poseidon_gate_eval(w, a);
         break;
       default:
+        if (RECURSION)
+          recursion_gate_eval(d.gate_id[g], d.gate_param[g], d.gate_param2[g], d.gate_param3[g], d.coset_aux, w,
+                              cs[d.num_selectors], cs[d.num_selectors + 1], a);
         break;
     }
   }

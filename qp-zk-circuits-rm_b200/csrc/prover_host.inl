@@ -141,6 +141,9 @@ struct CommonHost {
   std::vector<u64> k_is;
   u64 num_partial_products;
   std::vector<std::pair<u32, u64>> gates;
+  std::vector<u64> gate_p2, gate_p3;        // RandomAccess copies / extra constants; CosetInterpolation degree
+  std::vector<u64> coset_weights;           // CosetInterpolation barycentric weights
+  bool recursion = false;                   // any gate outside the wormhole / voting set
 };
 
 struct ByteReader {
@@ -193,13 +196,33 @@ static bool parse_common_host(const uint8_t* p, size_t n, CommonHost* c, std::st
   if (ngates != ns) { *err = "gate/selector count mismatch"; return false; }
   for (u64 i = 0; i < ngates; i++) {
     u32 id = (u32)r.u(4);
-    u64 param = 0;
+    u64 param = 0, p2 = 0, p3 = 0;
     switch (id) {
-      case G_NOOP: case G_PUBLIC_INPUT: case G_POSEIDON: break;
-      case G_CONSTANT: case G_BASE_SUM_2: case G_ARITHMETIC: param = r.u(8); break;
-      default: *err = "unsupported gate id " + std::to_string(id) + " (only the wormhole/voting gate set is built)"; return false;
+      case G_NOOP: case G_PUBLIC_INPUT: case G_POSEIDON: case G_POSEIDON_MDS: break;
+      case G_CONSTANT: case G_BASE_SUM_2: case G_ARITHMETIC: case G_ARITHMETIC_EXT: case G_MUL_EXT:
+      case G_REDUCING: case G_REDUCING_EXT: case G_EXPONENTIATION:
+        param = r.u(8);
+        break;
+      case G_RANDOM_ACCESS:
+        param = r.u(8); p2 = r.u(8); p3 = r.u(8);
+        if (param > 6 || p3 > 2) { *err = "RandomAccessGate: bits > 6 or more than 2 extra constants"; return false; }
+        break;
+      case G_COSET_INTERPOLATION: {
+        param = r.u(8); p2 = r.u(8);
+        u64 nw = r.u(8);
+        if (param > 6 || p2 < 2 || nw != (1ull << param) || !c->coset_weights.empty()) {
+          *err = "CosetInterpolationGate: unsupported parameters";
+          return false;
+        }
+        for (u64 j = 0; j < nw; j++) c->coset_weights.push_back(r.u(8));
+        break;
+      }
+      default: *err = "unsupported gate id " + std::to_string(id) + " (lookup gates are not built)"; return false;
     }
+    if (gate_is_recursion_only(id)) c->recursion = true;
     c->gates.push_back({id, param});
+    c->gate_p2.push_back(p2);
+    c->gate_p3.push_back(p3);
   }
   if (!r.ok) { *err = "truncated common data"; return false; }
   return true;
@@ -219,6 +242,7 @@ struct qpzk_circuit {
   CircuitDesc desc;
   u64 digest[4];
   u64* k_is_dev = nullptr;
+  u64* coset_aux_dev = nullptr;
   u64* cs_values = nullptr;  // [num_constants + num_routed][n] values on the subgroup (for Z)
   qpzk_batch* cs_batch = nullptr;
   std::vector<u64> cs_cap;
@@ -270,6 +294,8 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
   for (size_t g = 0; g < cm.gates.size(); g++) {
     d.gate_id[g] = cm.gates[g].first;
     d.gate_param[g] = (u32)cm.gates[g].second;
+    d.gate_param2[g] = (u32)cm.gate_p2[g];
+    d.gate_param3[g] = (u32)cm.gate_p3[g];
     d.gate_selector[g] = (u32)cm.selector_indices[g];
   }
   for (size_t s = 0; s < cm.groups.size(); s++) {
@@ -281,6 +307,20 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
   const u32 ncs = (u32)(cm.num_constants + cm.num_routed);
   QP(dev_alloc(c, cm.k_is.size() * 8, &q->k_is_dev));
   CU(cudaMemcpyAsync(q->k_is_dev, cm.k_is.data(), cm.k_is.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  if (!cm.coset_weights.empty()) {  // subgroup points, then the barycentric weights from the common data
+    const size_t np = cm.coset_weights.size();
+    u32 bits = 0;
+    while ((1ull << bits) < np) bits++;
+    std::vector<u64> aux(2 * np);
+    u64 g = glh::root_of_unity(bits);
+    aux[0] = 1;
+    for (size_t i = 1; i < np; i++) aux[i] = glh::mul(aux[i - 1], g);
+    for (size_t i = 0; i < np; i++) aux[np + i] = cm.coset_weights[i];
+    QP(dev_alloc(c, aux.size() * 8, &q->coset_aux_dev));
+    CU(cudaMemcpyAsync(q->coset_aux_dev, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    d.coset_aux = q->coset_aux_dev;
+  }
   QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
   CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
   // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
@@ -317,6 +357,7 @@ void qpzk_circuit_free(qpzk_circuit* q) {
   if (!q) return;
   cudaSetDevice(q->ctx->device);
   dev_free(q->ctx, q->k_is_dev);
+  dev_free(q->ctx, q->coset_aux_dev);
   dev_free(q->ctx, q->cs_values);
   qpzk_batch_free(q->cs_batch);
   delete q;
@@ -451,9 +492,14 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   QP(qcoeffs.alloc((size_t)nch * qlde * 8));
   RootTab tab_q;
   QP(get_root_tab(c, (int)qlb, false, &tab_q));
-  k_quotient<<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
-      q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-      small.p + 4 + zh.size(), tab_q, qvals.p);
+  if (cm.recursion)
+    k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
+        small.p + 4 + zh.size(), tab_q, qvals.p);
+  else
+    k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
+        small.p + 4 + zh.size(), tab_q, qvals.p);
   c->launches++;
   CU(cudaGetLastError());
   // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)

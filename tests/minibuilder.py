@@ -12,3 +12,7 @@ class OracleProvider:
 
 def build(degree_bits, zk=False, seed=1, **kw):
     return synth.build(degree_bits, zk=zk, seed=seed, provider=OracleProvider(), **kw)
+
+
+def build_recursion(degree_bits, zk=False, seed=1, **kw):
+    return synth.build_recursion(degree_bits, zk=zk, seed=seed, provider=OracleProvider(), **kw)
