@@ -437,6 +437,45 @@ def run_gpu(args, rank, local_rank, world):
         ctx0.dev_free(vd)
         vcirc.free()
 
+    # BASELINE configs[4]: one aggregation-tree node - a recursion-shaped circuit (the 14-gate set an
+    # in-circuit verifier instantiates, /root/reference/wormhole/aggregator/src/circuits/tree.rs:111-136) of
+    # 2^13 rows, the size SURVEY 8(d) estimates for the reference's default binary tree nodes.
+    aggregator = None
+    if rank == 0 and not args.no_aggregator:
+        ak = 13
+        ac = synth.build_recursion(ak, zk=True, seed=9, provider=synth.GpuProvider(ctx0))
+        acircs = [qpzk.Circuit(c, ac["common"], ac["digest"], ac["constants_sigmas"]) for c in ctxs]
+        for _ in range(3):
+            aproof = acircs[0].prove(ac["wires"], ac["public_inputs"], ac["salts"])
+        lat = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            acircs[0].prove(ac["wires"], ac["public_inputs"], ac["salts"])
+            lat.append((time.perf_counter() - t0) * 1e3)
+        astages = acircs[0].stage_ms()
+        per = 8
+
+        def aworker(s):
+            for _ in range(per):
+                acircs[s].prove(ac["wires"], ac["public_inputs"], ac["salts"])
+
+        th = [threading.Thread(target=aworker, args=(s,)) for s in range(S)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        aggregator = {"workload": "aggregation-node shape: 2^%d rows x 135 wires, 14-gate recursion set, ZK, host "
+                                  "buffers through qpzk_prove" % ak,
+                      "latency_ms_median": float(np.median(lat)), "proofs_per_s_%d_streams" % S: S * per / dt,
+                      "proof_bytes": len(aproof), "stage_ms": astages,
+                      "note": "gate definitions restated from upstream plonky2, not pinned by a reference fixture"}
+        for q in acircs:
+            q.free()
+
     sharded = None
     if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
         sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
@@ -518,6 +557,8 @@ def run_gpu(args, rank, local_rank, world):
             line["commit_microbench"]["sharded"] = sharded
         if voting is not None:
             line["voting_single_proof"] = voting
+        if aggregator is not None:
+            line["aggregator_node_proof"] = aggregator
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -542,6 +583,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="proofs in flight per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-aggregator", action="store_true", help="skip the aggregation-node proof (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
