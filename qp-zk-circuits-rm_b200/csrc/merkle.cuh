@@ -16,7 +16,10 @@
 namespace qpzk {
 
 // hash_or_noop of one row per thread. Element (row, c) lives at src[row*row_stride + c*col_stride].
-__global__ void __launch_bounds__(128, 6)
+#ifndef QPZK_LEAF_MINB
+#define QPZK_LEAF_MINB 5
+#endif
+__global__ void __launch_bounds__(128, QPZK_LEAF_MINB)
 k_leaf_hash(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 width, u64 nrows,
             u64* __restrict__ digests) {
   u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -46,7 +49,7 @@ k_leaf_hash(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wid
 }
 
 // One Merkle level: out[t] = two_to_one(in[2t], in[2t+1]).
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, QPZK_LEAF_MINB)
 k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
   u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nout) return;

@@ -102,7 +102,45 @@ GL_DEV void mad_wide(u32& lo, u32& hi, u32 a, u32 b) {
       : "r"(a), "r"(b));
 }
 
-GL_DEV void mds_layer(u64 (&s)[12]) {
+#ifndef PV_MDS_F64
+#define PV_MDS_F64 1
+#endif
+// MDS on the FP64 pipe. The integer multiplier (FMA-heavy) pipe is the one Poseidon saturates, while
+// the DFMA pipe of the B200 (64 per clock per SM) idles. The circulant has entries < 2^6, so the state
+// is cut into three limbs of 22/22/20 bits, each plane's 12x12 product runs as exact integer arithmetic
+// in doubles (|sum| < 2^31 << 2^53), and the three 31-bit plane sums are stitched back with shifts
+// and one fold. int <-> double through the 2^52 bias (one DADD each way), no conversion instructions.
+__constant__ double c_mds_circ_d[12];
+GL_DEV double u32_to_f64(u32 v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+GL_DEV u32 f64_to_u32(double d) { return (u32)__double2loint(d + 4503599627370496.0); }
+GL_DEV void mds_layer_f64(u64 (&s)[12]) {
+  u32 S[3][12];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double d[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      u32 limb = k == 0 ? (u32)s[i] & 0x3FFFFFu : (k == 1 ? (u32)(s[i] >> 22) & 0x3FFFFFu : (u32)(s[i] >> 44));
+      d[i] = u32_to_f64(limb);
+    }
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+      double acc = r == 0 ? d[0] * 8.0 : 0.0;
+#pragma unroll
+      for (int i = 0; i < 12; i++) acc = fma(d[(i + r) % 12], c_mds_circ_d[i], acc);
+      S[k][r] = f64_to_u32(acc);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    // T = S0 + S1*2^22 + S2*2^44 < 2^76: low 64 bits + top*2^64, 2^64 == EPS
+    unsigned __int128 t = (unsigned __int128)S[0][r] + ((unsigned __int128)S[1][r] << 22) + ((unsigned __int128)S[2][r] << 44);
+    s[r] = gl_fold((u64)t, (u32)(u64)(t >> 64), 0);
+  }
+}
+// MDS on the integer multiplier: 32-bit halves, IMAD.WIDE accumulate, one fold per lane. Used where the
+// FP64 variant's extra registers hurt (the quotient kernel's PoseidonGate evaluation).
+GL_DEV void mds_layer_int(u64 (&s)[12]) {
   u32 lo[12], hi[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
@@ -123,6 +161,13 @@ GL_DEV void mds_layer(u64 (&s)[12]) {
     }
     s[r] = mds_combine(al0, al1, ah0, ah1);
   }
+}
+GL_DEV void mds_layer(u64 (&s)[12]) {
+#if PV_MDS_F64
+  mds_layer_f64(s);
+#else
+  mds_layer_int(s);
+#endif
 }
 
 // Full round: add constants, x^7 on every lane, MDS.

@@ -211,7 +211,7 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer(s);
+    mds_layer_int(s);
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
@@ -260,7 +260,7 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer(s);
+    mds_layer_int(s);
   }
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {

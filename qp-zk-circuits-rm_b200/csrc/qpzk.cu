@@ -158,7 +158,7 @@ static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
 // Batched n-point transforms. flavour LDE: src natural -> dst DIF order per coset (ncosets = 2^r,
 // coset pre-multipliers applied). flavour IFFT: src natural values -> dst natural coefficients.
 static const int kSmallMaxLog = 12;
-static const u32 kTileElems = 4096;
+
 
 // blk0 / nblk: which of the 2^r leaf blocks (n bit-reversed leaves each, block b = coset rev_r(b)) to
 // evaluate; the full commit passes (0, 2^r), a multi-GPU shard its own range.
@@ -361,6 +361,11 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
     u32 diag0 = (u32)kMdsDiag0;
     CU(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
     CU(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
+#if PV_MDS_F64
+    double circ_d[12];
+    for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
+    CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
+#endif
     // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
     const int kMaxSmem = 72 * 1024;
     CU(cudaFuncSetAttribute(k_ntt_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "libqpzk.so")
+LIB_PATH = os.environ.get("QPZK_LIB") or os.path.join(_PKG, "libqpzk.so")   # QPZK_LIB: A/B builds of the kernels
 
 P = 0xFFFFFFFF00000001
 SALT_SIZE = 4

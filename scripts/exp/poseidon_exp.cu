@@ -76,8 +76,12 @@ int main(int argc, char** argv) {
   u32 diag0 = (u32)kMdsDiag0;
   CK(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
   CK(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
-#ifdef PV_UPLOAD_EXTRA
-  PV_UPLOAD_EXTRA
+#if PV_MDS_F64
+  {
+    double cd[12];
+    for (int i = 0; i < 12; i++) cd[i] = (double)kMdsCirc[i];
+    CK(cudaMemcpyToSymbol(c_mds_circ_d, cd, sizeof cd));
+  }
 #endif
   const u64 n = 1 << 19;
   const int reps = argc > 1 ? atoi(argv[1]) : 17;
