@@ -538,7 +538,10 @@ def run_gpu(args, rank, local_rank, world):
                          # HBM: 3.7x the algorithmic bytes - the second pass re-reads and re-writes the LDE)
                          "traffic": NTT_DRAM_BYTES_PER_COMMIT, "traffic_source": "profiles/r1_ntt_fused_ncu_full.txt",
                          "peak_source": peak_src, "algorithmic_bytes": alg["ntt_bytes"],
-                         "stage_ms": ntt_ms},
+                         "stage_ms": ntt_ms,
+                         "note": "the north star's split: HBM roofline for the NTT/transpose stages (integer-issue-bound "
+                                 "in practice, DESIGN.md 4), integer-multiplier roofline for Poseidon - the dominant "
+                                 "kernel of the step - under roofline_int"},
             "roofline_int": {"bound": "int32-multiply", "kernel": "commit microbench: k_leaf_hash + k_merkle_level "
                                                                   "(Poseidon; the dominant kernel of every step)",
                              "achieved": alg["mults"] / (hash_ms * 1e-3) / 1e12, "peak": imad_wide / 1e12,
