@@ -235,3 +235,19 @@ def test_large_degrees_roundtrip_and_paths(ctx, k):
         assert orc.merkle_verify(row, leaf, cap, sib)
         assert int(row[0]) == int(lde0[bitrev(leaf, k + r)])
     b.free()
+
+
+@pytest.mark.parametrize("k", list(range(0, 19)))
+def test_every_degree_matches_oracle(ctx, k):
+    """Each transform length exercises a different stage decomposition of the radix-16 NTT (16 | 8 | 4 | 2
+    remainders, one or two passes); compare coefficients and cap for every degree_bits 0..18."""
+    import qpzk
+    rng = np.random.default_rng(5000 + k)
+    r = 3
+    cap_h = min(4, k + r)
+    vals = rand_felts(rng, (2, 1 << k))
+    want = orc.batch_commit(vals, r, cap_h, threads=8, want_leaves=False, want_digests=False)
+    b = qpzk.PolynomialBatch.from_values(ctx, vals, r, cap_h)
+    assert np.array_equal(b.polynomials, want["coeffs"])
+    assert np.array_equal(b.cap, want["cap"])
+    b.free()
