@@ -237,8 +237,11 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
 
 // Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
 // Below this many independent permutations a launch cannot fill the machine with one thread per
-// permutation (148 SMs x 768 threads) and the 16-lane low-latency kernels win (measured crossover).
-static u64 kCoopMaxPerms = 8192;
+// permutation and the 16-lane low-latency kernels win. They spend ~3.8x the lane-instructions per
+// permutation, so the threshold trades single-proof latency against throughput with several proofs in
+// flight. Measured (2^14 ZK proof, 6 streams): 0 -> 171 proofs/s / 9.8 ms latency; 1024 -> 175 / 8.9;
+// 4096 -> 175 / 8.8; 8192 -> 171 / 8.8. QPZK_COOP_MAX overrides.
+static u64 kCoopMaxPerms = 4096;
 // [leaf0, leaf0 + nleaves) restricts the work to a range of whole cap subtrees (multi-GPU shard); the
 // default is the whole tree.
 static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u32 log_n, u32 cap_height,
