@@ -27,24 +27,19 @@ typedef uint32_t u32;
 
 GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 
-// x = r0 + 2^32 r1 + 2^64 r2 + 2^96 r3  ->  (r1:r0) - r3 + r2*(2^32-1)   (any-u64 representative)
-// Carry-chain PTX, no compares or selects. NOTE on flags: CC.CF is the hardware carry, i.e. after a
-// sub chain it is NOT-borrow. `subc m,0,0` after a SUB chain therefore yields the borrow mask
-// (0 / 0xffffffff), but after an ADD chain it would yield the INVERTED carry mask - so add chains
-// read the carry with `addc c,0,0` (0/1), negate it into a mask and add that.
 // The fold  lo + r2*EPS - h  (mod p)  for lo any u64, r2 < 2^32, h <= 2^63: the Goldilocks reduction
 // 2^64 == EPS, 2^96 == -1 applied to x = lo + 2^64*r2 + 2^96*h. Returns some u64 representative.
 //
-// Written with a signed 128-bit intermediate ON PURPOSE: ptxas turns it into
-//   IMAD.WIDE.U32 m, P = r2 * 0xffffffff - h     (multiply-add with negated addend and carry-out)
-//   IADD3 / IADD3.X     t = lo + m               (second carry-out)
-//   IADD3.X k = 0 - 1 + P + P'                   (BOTH carries in one 3-input add: k in {-1, 0, 1})
-//   IMAD.WIDE.U32 r = k * 0xffffffff + t ; LEA.HI hi += k >> 31    (one correction by k*EPS)
-// i.e. 6 instructions, against 12 for the same fold written as PTX add.cc/subc chains (PTX only has
-// two-input adds with a single carry flag; SASS IADD3 has three inputs and two carries).
-// The single correction never wraps again: if k = 1 then t mod 2^64 <= 2^64 - 2^33, and if k = -1
-// then t mod 2^64 >= 2^64 - h.
-// Two spellings of the same fold. They differ only in which pipe pays for r2*EPS and k*EPS:
+// Written with a signed 128-bit intermediate ON PURPOSE. PTX only has two-input adds with a single carry
+// flag, so the same fold as add.cc/subc chains needs a mask-and-correct sequence per wrap: 12 SASS
+// instructions. From the __int128 expression ptxas emits three-input IADD3 with TWO carry-outs, sums both
+// carries into one k in {-1, 0, 1} (`IADD3.X k = 0 - 1 + P + P'`) and a single correction by k*EPS
+// follows: 6-7 instructions. The single correction never wraps again: if k = 1 then t mod 2^64 <=
+// 2^64 - 2^33, and if k = -1 then t mod 2^64 >= 2^64 - h.
+// (A note for anyone writing carry chains in PTX here: CC.CF is the hardware carry, so after a SUB chain
+// `subc m,0,0` yields the borrow mask, but after an ADD chain it yields the INVERTED carry mask.)
+//
+// Two spellings. They differ only in which pipe pays for r2*EPS and k*EPS:
 //  gl_fold_alu: (r2 << 32) - r2 and (k << 32) - k as adds. Default: Poseidon saturates the multiplier
 //               (FMA-heavy) pipe (ncu: 88 % with the multiplier spelling, ALU at 43 %).
 //  gl_fold_mul: two IMAD.WIDE. Measured on the NTT kernels, which saturate the ALU pipe instead
