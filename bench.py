@@ -320,7 +320,11 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     S = max(1, args.streams)
-    ctxs = [qpzk.Context(local_rank) for _ in range(S)]
+    # every proving thread spins on a host core while its stream works: keep threads x ranks within the cores
+    cores = os.cpu_count() or 1
+    if not args.blocking_sync:
+        S = max(1, min(S, cores // max(1, world)))
+    ctxs = [qpzk.Context(local_rank, blocking_sync=args.blocking_sync) for _ in range(S)]
     ctx0 = ctxs[0]
 
     # one synthetic wormhole-shaped circuit + witness per stream
@@ -586,6 +590,8 @@ def main():
     ap.add_argument("--streams", type=int, default=6, help="proofs in flight per GPU (measured: 1: 118, 2: 151, 4: 166, 6: 172, 8: 173 proofs/s)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--blocking-sync", action="store_true",
+                    help="contexts wait on blocking-sync events instead of spinning (QPZK_CTX_BLOCKING_SYNC)")
     ap.add_argument("--no-aggregator", action="store_true", help="skip the aggregation-node proof (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

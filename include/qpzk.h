@@ -60,6 +60,9 @@ enum {
 };
 
 /* ---- context ---- */
+/* flags: QPZK_CTX_BLOCKING_SYNC - waits for the device sleep on a blocking-sync event instead of spinning a
+ * host core (use when proving threads x processes exceed the host cores, e.g. many rayon workers). */
+#define QPZK_CTX_BLOCKING_SYNC 1u
 int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out);
 void qpzk_ctx_destroy(qpzk_ctx* ctx);
 const char* qpzk_last_error(void);

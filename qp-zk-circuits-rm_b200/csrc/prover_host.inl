@@ -318,7 +318,7 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
     for (size_t i = 0; i < np; i++) aux[np + i] = cm.coset_weights[i];
     QP(dev_alloc(c, aux.size() * 8, &q->coset_aux_dev));
     CU(cudaMemcpyAsync(q->coset_aux_dev, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
     d.coset_aux = q->coset_aux_dev;
   }
   QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
@@ -468,7 +468,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   if (want_trace) {
     q->tr_zs_pp.resize((size_t)nzs * n);
     CU(cudaMemcpyAsync(q->tr_zs_pp.data(), zs_vals.p, (size_t)nzs * n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
   }
 
   // ---- (6,7) quotient ----
@@ -519,7 +519,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   if (want_trace) {
     q->tr_quotient.resize((size_t)nch * qlde);
     CU(cudaMemcpyAsync(q->tr_quotient.data(), qcoeffs.p, (size_t)nch * qlde * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
   }
   u64 zeta[2] = {ch.get(), 0};
   zeta[1] = ch.get();
@@ -551,7 +551,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   CU(cudaGetLastError());
   std::vector<u64> opens((size_t)(total_polys + nch) * 2);
   CU(cudaMemcpyAsync(opens.data(), open_dev.p, opens.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   // observe order: constants, sigmas, wires, zs, partial_products, quotient (= oracle order) then zs_next
   ch.observe_n(opens.data(), opens.size());
   toc();  // stage 3: openings
@@ -595,7 +595,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   if (want_trace) {
     std::vector<u64> soa(2 * n);
     CU(cudaMemcpyAsync(soa.data(), fpoly.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
     q->tr_final_poly.resize(2 * n);
     for (u64 m = 0; m < n; m++) {
       q->tr_final_poly[2 * m] = soa[m];
@@ -649,7 +649,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     if (rc2 != QPZK_OK) { free_trees(); return rc2; }
     std::vector<u64> fc(4ull << h);
     cudaMemcpyAsync(fc.data(), cap_ptr(t.levels, t.log_n, h), fc.size() * 8, cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
+    ctx_wait(c);
     ch.observe_n(fc.data(), fc.size());
     fri_caps.push_back(fc);
     u64 b0 = ch.get(), b1 = ch.get();
@@ -668,7 +668,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   std::vector<u64> final_soa(2 * cur_n), final_poly(2 * cur_n);
   cudaMemcpyAsync(final_soa.data(), coeffs_cur, cur_n * 8, cudaMemcpyDeviceToHost, c->stream);
   cudaMemcpyAsync(final_soa.data() + cur_n, coeffs_cur + cur_n, cur_n * 8, cudaMemcpyDeviceToHost, c->stream);
-  cudaStreamSynchronize(c->stream);
+  ctx_wait(c);
   for (u64 m = 0; m < cur_n; m++) {
     final_poly[2 * m] = final_soa[m];
     final_poly[2 * m + 1] = final_soa[cur_n + m];
@@ -699,7 +699,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
                                                                  (unsigned long long*)best.p);
       c->launches++;
       cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, c->stream);
-      cudaStreamSynchronize(c->stream);
+      ctx_wait(c);
       start += batch;
       if (start >= (1ull << 40)) { free_trees(); return fail(QPZK_ERR_CUDA, "proof of work failed"); }
     }
@@ -746,7 +746,7 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     step_open[s].resize(per * nq);
     cudaMemcpyAsync(step_open[s].data(), ob->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream);
   }
-  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaError_t e = ctx_wait(c);
   for (auto* kb : keep) delete kb;
   free_trees();
   if (e != cudaSuccess) return fail(QPZK_ERR_CUDA, cudaGetErrorString(e));
@@ -820,7 +820,7 @@ int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, const uint64_t* public_in
   std::vector<uint8_t> bytes;
   int rc = prove_impl(q, wires, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, flags, &bytes);
   if (rc != QPZK_OK) {
-    cudaStreamSynchronize(q->ctx->stream);
+    ctx_wait(q->ctx);
     return rc;
   }
   *proof_len = bytes.size();

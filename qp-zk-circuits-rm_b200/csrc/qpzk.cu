@@ -56,6 +56,8 @@ struct TabKey {
 struct qpzk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool blocking_sync = false;      // QPZK_CTX_BLOCKING_SYNC: sleep instead of spinning while the device works
+  cudaEvent_t sync_ev = nullptr;
   cudaEvent_t ev[QPZK_NUM_STAGES + 1];
   float stage_ms[QPZK_NUM_STAGES] = {0};
   uint64_t launches = 0;
@@ -83,6 +85,16 @@ struct qpzk_tree {
 };
 
 // ------------------------------------------------------------------------------------------
+// Wait for the context's stream. cudaStreamSynchronize spins on a host core, which is the lowest
+// latency but oversubscribes the host once contexts x processes exceed the cores (measured: 8 ranks x 6
+// proving threads on 32 cores lost 10 % of throughput); a context created with
+// QPZK_CTX_BLOCKING_SYNC waits on a blocking-sync event instead.
+static cudaError_t ctx_wait(qpzk_ctx* c) {
+  if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
+  cudaError_t e = cudaEventRecord(c->sync_ev, c->stream);
+  return e != cudaSuccess ? e : cudaEventSynchronize(c->sync_ev);
+}
+
 static int dev_alloc(qpzk_ctx* c, size_t bytes, u64** out) {
   void* p = nullptr;
   CU(cudaMallocAsync(&p, bytes ? bytes : 8, c->stream));
@@ -324,7 +336,6 @@ extern "C" {
 const char* qpzk_last_error(void) { return g_err.c_str(); }
 
 int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
-  (void)flags;
   if (!out) return fail(QPZK_ERR_BAD_ARG, "out is NULL");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -337,6 +348,8 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->blocking_sync = (flags & QPZK_CTX_BLOCKING_SYNC) != 0;
+  CU(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   // keep freed blocks in the pool: commits allocate and release hundreds of MB per call
   cudaMemPool_t pool;
@@ -379,7 +392,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
     CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   }
   QP(dev_alloc(c, 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   *out = c;
   return QPZK_OK;
 }
@@ -387,7 +400,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
 void qpzk_ctx_destroy(qpzk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  ctx_wait(c);
   for (auto& kv : c->root_tabs) {
     dev_free(c, kv.second.first);
     dev_free(c, kv.second.second);
@@ -398,15 +411,16 @@ void qpzk_ctx_destroy(qpzk_ctx* c) {
     dev_free(c, kv.second.second);
   }
   dev_free(c, c->scratch_path);
-  cudaStreamSynchronize(c->stream);
+  ctx_wait(c);
   for (auto& e : c->ev) cudaEventDestroy(e);
+  cudaEventDestroy(c->sync_ev);
   cudaStreamDestroy(c->stream);
   delete c;
 }
 
 int qpzk_ctx_sync(qpzk_ctx* c) {
   if (!c) return fail(QPZK_ERR_BAD_ARG, "ctx is NULL");
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 void* qpzk_ctx_stream(qpzk_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -447,12 +461,12 @@ void qpzk_dev_free(qpzk_ctx* c, void* p) {
 }
 int qpzk_memcpy_h2d(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 int qpzk_memcpy_d2h(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -469,7 +483,7 @@ int qpzk_poseidon_permute(qpzk_ctx* c, uint64_t* states, uint64_t n) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(states, d, n * 96, cudaMemcpyDeviceToHost, c->stream));
   dev_free(c, d);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -488,7 +502,7 @@ int qpzk_hash_no_pad(qpzk_ctx* c, const uint64_t* inputs, uint64_t n, uint32_t l
   CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
   dev_free(c, din);
   dev_free(c, dout);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -506,7 +520,7 @@ int qpzk_two_to_one(qpzk_ctx* c, const uint64_t* pairs, uint64_t n, uint64_t* ou
   CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
   dev_free(c, din);
   dev_free(c, dout);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -542,7 +556,7 @@ int qpzk_merkle_new(qpzk_ctx* c, const uint64_t* leaves, uint64_t nleaves, uint3
   CU(cudaMemcpyAsync(dl, leaves, nleaves * leaf_len * 8, cudaMemcpyHostToDevice, c->stream));
   QP(build_tree(c, dl, leaf_len, 1, leaf_len, log_n, cap_height, t->levels, nullptr));
   dev_free(c, dl);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   *out = t;
   return QPZK_OK;
 }
@@ -552,7 +566,7 @@ int qpzk_tree_cap(const qpzk_tree* t, uint64_t* out) {
   CU(cudaSetDevice(t->ctx->device));
   CU(cudaMemcpyAsync(out, cap_ptr(t->levels, t->log_n, t->cap_height), ((size_t)32) << t->cap_height,
                      cudaMemcpyDeviceToHost, t->ctx->stream));
-  CU(cudaStreamSynchronize(t->ctx->stream));
+  CU(ctx_wait(t->ctx));
   return QPZK_OK;
 }
 
@@ -565,7 +579,7 @@ static int prove_from_levels(qpzk_ctx* c, const u64* levels, u32 log_n, u32 cap_
   c->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(siblings, c->scratch_path, (size_t)L * 32, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -586,7 +600,7 @@ static int export_digests(qpzk_ctx* c, const u64* levels, u32 log_n, u32 cap_hei
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, d, total * 32, cudaMemcpyDeviceToHost, c->stream));
   dev_free(c, d);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -685,7 +699,7 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
   dev_free(c, staging);
   dev_free(c, salt_staging);
   staging = salt_staging = nullptr;
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
   c->stage_ms[QPZK_STAGE_D2H] = 0;
   *out = b;
@@ -726,7 +740,7 @@ int qpzk_batch_set_cap(qpzk_batch* b, const uint64_t* cap) {
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(const_cast<u64*>(cap_ptr(b->levels, b->log_N(), b->cap_height)), cap, ((size_t)32) << b->cap_height,
                      cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
@@ -738,7 +752,7 @@ int qpzk_batch_cap(const qpzk_batch* b, uint64_t* out) {
   CU(cudaMemcpyAsync(out, cap_ptr(b->levels, b->log_N(), b->cap_height), ((size_t)32) << b->cap_height,
                      cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[1], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   cudaEventElapsedTime(&c->stage_ms[QPZK_STAGE_D2H], c->ev[0], c->ev[1]);
   return QPZK_OK;
 }
@@ -750,7 +764,7 @@ int qpzk_batch_coeffs(const qpzk_batch* b, uint64_t* out) {
   CU(cudaSetDevice(b->ctx->device));
   CU(cudaMemcpyAsync(out, b->coeffs, ((size_t)b->ncols << b->degree_bits) * 8, cudaMemcpyDeviceToHost,
                      b->ctx->stream));
-  CU(cudaStreamSynchronize(b->ctx->stream));
+  CU(ctx_wait(b->ctx));
   return QPZK_OK;
 }
 int qpzk_batch_get_lde_rows(const qpzk_batch* b, const uint32_t* idx, uint32_t nidx, uint32_t step,
@@ -772,7 +786,7 @@ int qpzk_batch_get_lde_rows(const qpzk_batch* b, const uint32_t* idx, uint32_t n
   CU(cudaMemcpyAsync(out, dout, (size_t)nidx * b->ncols * 8, cudaMemcpyDeviceToHost, c->stream));
   dev_free(c, didx);
   dev_free(c, dout);
-  CU(cudaStreamSynchronize(c->stream));
+  CU(ctx_wait(c));
   return QPZK_OK;
 }
 int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out, uint64_t* siblings_out) {
@@ -787,7 +801,7 @@ int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaf_out, row, (size_t)b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
   }
   if (siblings_out) return prove_from_levels(c, b->levels, b->log_N(), b->cap_height, leaf_index, siblings_out);
   return QPZK_OK;
@@ -806,7 +820,7 @@ int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests) 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaves, rows, (size_t)N * b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
     dev_free(c, rows);
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
   }
   if (digests) return export_digests(c, b->levels, b->log_N(), b->cap_height, digests);
   return QPZK_OK;
@@ -839,7 +853,7 @@ int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
       k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep, 17u, 15u, 41u, 16u);
     c->launches++;
     CU(cudaEventRecord(c->ev[1], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(ctx_wait(c));
     float ms;
     CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     if (rep > 0 && ms < best) best = ms;

@@ -118,10 +118,10 @@ def _ptr(a):
 class Context:
     """One CUDA stream + caches (twiddle tables, coset pre-multipliers) on one device."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, blocking_sync=False):
         L = load_library()
         h = _vp()
-        _check(L.qpzk_ctx_create(device, 0, ctypes.byref(h)))
+        _check(L.qpzk_ctx_create(device, 1 if blocking_sync else 0, ctypes.byref(h)))
         self._h = h
         self.device = device
 
