@@ -15,9 +15,12 @@ using namespace qpzk;
 #ifndef MINB
 #define MINB 6
 #endif
+#ifndef BLK
+#define BLK 128
+#endif
 
 // leaf-hash shaped: `reps` sponge permutations per thread, absorbing 8 fresh words each time
-__global__ void __launch_bounds__(128, MINB) k_exp(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int reps) {
+__global__ void __launch_bounds__(BLK, MINB) k_exp(const u64* __restrict__ in, u64* __restrict__ out, u64 n, int reps) {
   u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   u64 s[12];
@@ -101,7 +104,7 @@ int main(int argc, char** argv) {
   float best = 1e30f;
   for (int it = 0; it < 6; it++) {
     cudaEventRecord(e0);
-    k_exp<<<(unsigned)(n / 128), 128>>>(din, dout, n, reps);
+    k_exp<<<(unsigned)(n / BLK), BLK>>>(din, dout, n, reps);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
