@@ -76,3 +76,67 @@ def test_gpu_recursion_proof_matches_oracle(k, zk):
     assert rc != 0
     gc.free()
     ctx.close()
+
+
+# ---- what the gates MEAN (independent of wire order): the rows the builder fills, and the constraints accept,
+# compute the functions an in-circuit FRI verifier needs them for ----
+def _ext(w, r, i):
+    return (int(w[i, r]), int(w[i + 1, r]))
+
+
+def _emul(x, y):
+    P = orc.P
+    return ((x[0] * y[0] + 7 * x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+
+
+def _einv(x):
+    P = orc.P
+    d = (x[0] * x[0] - 7 * x[1] * x[1]) % P
+    di = pow(d, P - 2, P)
+    return (x[0] * di % P, (-x[1]) * di % P)
+
+
+def test_gate_semantics():
+    P = orc.P
+    circ = minibuilder.build_recursion(8, zk=False, seed=77)
+    w, gate = circ["wires"], circ["gate"]
+    # CosetInterpolation: evaluation_value == the degree-<16 interpolant of (shift*g^i, value_i) at evaluation_point
+    r = int(np.where(gate == synth.R_COSET)[0][0])
+    shift = int(w[0, r])
+    g = orc.root_of_unity(4)
+    xs = [shift * pow(g, i, P) % P for i in range(16)]
+    vals = [_ext(w, r, 1 + 2 * i) for i in range(16)]
+    x = _ext(w, r, 33)
+    acc = (0, 0)
+    for i in range(16):   # Lagrange, in F_p^2
+        num, den = (1, 0), 1
+        for j in range(16):
+            if j != i:
+                num = _emul(num, ((x[0] - xs[j]) % P, x[1]))
+                den = den * (xs[i] - xs[j]) % P
+        term = _emul(vals[i], num)
+        di = pow(den, P - 2, P)
+        acc = ((acc[0] + term[0] * di) % P, (acc[1] + term[1] * di) % P)
+    assert acc == _ext(w, r, 35)
+    # Reducing: output == old_acc*alpha^n + sum coeff_i * alpha^(n-1-i)   (Horner)
+    r = int(np.where(gate == synth.R_REDUCING)[0][0])
+    alpha, acc = _ext(w, r, 2), _ext(w, r, 4)
+    for i in range(43):
+        acc = _emul(acc, alpha)
+        acc = ((acc[0] + int(w[6 + i, r])) % P, acc[1])
+    assert acc == _ext(w, r, 0)
+    # Exponentiation: output == base ^ (little-endian power bits)
+    r = int(np.where(gate == synth.R_EXPONENTIATION)[0][0])
+    e = sum(int(w[1 + i, r]) << i for i in range(66))
+    assert pow(int(w[0, r]), e, P) == int(w[67, r])
+    # RandomAccess: claimed_element == list[access_index] for every copy
+    r = int(np.where(gate == synth.R_RANDOM_ACCESS)[0][0])
+    for cp in range(4):
+        assert int(w[18 * cp + 1, r]) == int(w[18 * cp + 2 + int(w[18 * cp, r]), r])
+    # MulExtension / ArithmeticExtension: field arithmetic in F_p^2
+    r = int(np.where(gate == synth.R_MUL_EXT)[0][0])
+    c0 = int(circ["constants_sigmas"][5, r])
+    m = _emul(_ext(w, r, 0), _ext(w, r, 2))
+    assert (m[0] * c0 % P, m[1] * c0 % P) == _ext(w, r, 4)
+    # and F_p^2 really is a field with X^2 = 7: x * x^-1 == 1
+    assert _emul(x, _einv(x)) == (1, 0)
