@@ -157,19 +157,40 @@ __global__ void k_partial_products(const u64* __restrict__ chunk_q, const u64* _
 // H9  quotient evaluation
 // ---------------------------------------------------------------------------------------------
 // Running sum_t alpha^t * term_t for every challenge, 160-bit lazily reduced accumulators.
+// Reduction of the constraint terms with powers of alpha (`reduce_with_powers_multi`): term t of the list
+// contributes alpha_c^t * term to challenge c. The powers come from a per-proof table apw[c][t]
+// (uniform address across the warp), and terms are multiply-accumulated into column accumulators
+// with ONE fold at the end; a gate's constraints go to a gate-local accumulator that is folded, scaled
+// by the gate's filter and added to the total when the gate is done - one multiplication by the filter
+// per gate instead of one per constraint, and no running alpha-power products.
+#define QPZK_APW_STRIDE 256
 struct AlphaAcc {
-  Acc160 acc[2];
-  u64 pw[2];  // alpha^t (times the current gate's filter while inside a gate)
-  u64 alpha[2];
+  Acc160 acc[2];   // current target: the total outside gates, the gate-local sum inside
+  Acc160 tot[2];
+  const u64* apw;  // [2][QPZK_APW_STRIDE]
+  u32 t;           // index of the next term
   u32 nch;
 };
 GL_DEV void aa_emit(AlphaAcc& a, u64 term) {
 #pragma unroll
   for (int c = 0; c < 2; c++)
-    if (c < (int)a.nch) {
-      acc_mac(a.acc[c], a.pw[c], term);
-      a.pw[c] = gl_mul(a.pw[c], a.alpha[c]);
-    }
+    if (c < (int)a.nch) acc_mac(a.acc[c], __ldg(a.apw + c * QPZK_APW_STRIDE + a.t), term);
+  a.t++;
+}
+GL_DEV void aa_gate_begin(AlphaAcc& a, u32 base) {
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    a.tot[c] = a.acc[c];
+    acc_init(a.acc[c]);
+  }
+  a.t = base;
+}
+GL_DEV void aa_gate_end(AlphaAcc& a, u64 filter) {
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    if (c < (int)a.nch) acc_mac(a.tot[c], acc_reduce(a.acc[c]), filter);
+    a.acc[c] = a.tot[c];
+  }
 }
 
 struct WireRow {  // column-major LDE accessor for one leaf position
@@ -397,6 +418,14 @@ GL_DEV void recursion_gate_eval(u32 id, u32 p1, u32 p2, u32 p3, const u64* __res
   }
 }
 
+// Per-circuit table for L_0 on the quotient domain: out[i] = 1 / (n * (x_i - 1)), x_i = g * w^i.
+__global__ void k_build_l0_den_inv(u64* __restrict__ out, RootTab tab, u32 degree_bits, u32 lb) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((u64)1 << lb)) return;
+  u64 x = gl_mul(GL_GEN, root_pow(tab, i));
+  out[i] = gl_canon(gl_inv(gl_mul(((u64)1 << degree_bits) % GL_P, gl_sub(x, 1))));
+}
+
 // One thread per LDE leaf position. out[ch][i] (natural index i) = vanishing(x_i) / Z_H(x_i).
 // RECURSION = false is the wormhole / voting gate set; the recursion gates are compiled only into the
 // <true> instantiation so that they cost the common case neither registers nor instruction cache.
@@ -405,7 +434,9 @@ __global__ void __launch_bounds__(128)
 k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, const u64* __restrict__ zs_lde,
            u64 cs_stride, u64 wires_stride, u64 zs_stride, u32 step_bits, const u64* __restrict__ k_is,
            CircuitDesc d, Challenges ch, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
-           const u64* __restrict__ zh_inv, RootTab tab /* size degree_bits + qdb */, u64* __restrict__ out) {
+           const u64* __restrict__ zh_inv, const u64* __restrict__ apw /* alpha powers [2][QPZK_APW_STRIDE] */,
+           const u64* __restrict__ l0_den_inv /* [2^lb]: 1 / (n (x_i - 1)) */, RootTab tab /* size degree_bits + qdb */,
+           u64* __restrict__ out) {
   const u32 lb = d.degree_bits + d.quotient_degree_bits;  // quotient domain bits
   const u64 lde = (u64)1 << lb;
   u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;     // position in the bit-reversed quotient domain
@@ -424,15 +455,12 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
 
   AlphaAcc a;
   a.nch = nch;
-  for (int c = 0; c < 2; c++) {
-    acc_init(a.acc[c]);
-    a.pw[c] = 1;
-    a.alpha[c] = c < (int)nch ? ch.alpha[c] : 0;
-  }
-  // L_0(x) (Z_i(x) - 1),  L_0(x) = Z_H(x) / (n (x - 1))
+  a.apw = apw;
+  a.t = 0;
+  for (int c = 0; c < 2; c++) acc_init(a.acc[c]);
+  // L_0(x) (Z_i(x) - 1),  L_0(x) = Z_H(x) / (n (x - 1)); the denominators are a per-circuit table
   {
-    u64 nn = ((u64)1 << d.degree_bits) % GL_P;
-    u64 l0 = gl_mul(zhx, gl_inv(gl_mul(nn, gl_sub(x, 1))));
+    u64 l0 = gl_mul(zhx, l0_den_inv[i]);
     for (u32 c = 0; c < nch; c++) aa_emit(a, gl_mul(l0, gl_sub(zs[c], 1)));
   }
   // partial-product checks
@@ -454,18 +482,16 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
     }
   }
   // gate constraints: slot j gets sum_g filter_g * c_{g,j}; each gate restarts at alpha^base
-  u64 base_pw[2];
-  for (int c = 0; c < 2; c++) base_pw[c] = a.pw[c];
-  const u64* gc_dummy = nullptr;
-  (void)gc_dummy;
+  const u32 base_t = a.t;
   for (u32 g = 0; g < d.num_gates; g++) {
+    if (d.gate_id[g] == G_NOOP) continue;
     const u32 si = d.gate_selector[g];
     const u64 s = cs[si];
     u64 filter = 1;
     for (u32 j = d.group_lo[si]; j < d.group_hi[si]; j++)
       if (j != g) filter = gl_mul(filter, gl_sub((u64)j, s));
     if (d.num_selectors > 1) filter = gl_mul(filter, gl_sub((u64)0xFFFFFFFFu, s));
-    for (int c = 0; c < 2; c++) a.pw[c] = gl_mul(base_pw[c], filter);
+    aa_gate_begin(a, base_t);
     switch (d.gate_id[g]) {
       case G_NOOP:
         break;
@@ -504,6 +530,7 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
                               cs[d.num_selectors], cs[d.num_selectors + 1], a);
         break;
     }
+    aa_gate_end(a, filter);
   }
   const u64 zi = zh_inv[i & (((u64)1 << d.quotient_degree_bits) - 1)];
   for (u32 c = 0; c < nch; c++) out[(u64)c * lde + i] = gl_canon(gl_mul(acc_reduce(a.acc[c]), zi));

@@ -243,6 +243,7 @@ struct qpzk_circuit {
   u64 digest[4];
   u64* k_is_dev = nullptr;
   u64* coset_aux_dev = nullptr;
+  u64* l0_den_inv_dev = nullptr;   // [2^(degree_bits + qdb)], see k_build_l0_den_inv
   u64* cs_values = nullptr;  // [num_constants + num_routed][n] values on the subgroup (for Z)
   qpzk_batch* cs_batch = nullptr;
   std::vector<u64> cs_cap;
@@ -334,6 +335,21 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
   }
   q->cs_cap.resize(4ull << cm.cap_height);
   QP(qpzk_batch_cap(q->cs_batch, q->cs_cap.data()));
+  {
+    const u32 qlb = (u32)cm.degree_bits + qdb;
+    if (cm.num_challenges * (1 + cm.num_partial_products + 1) + cm.num_gate_constraints > QPZK_APW_STRIDE) {
+      qpzk_circuit_free(q);
+      return fail(QPZK_ERR_UNSUPPORTED, "too many constraint terms for the alpha-power table");
+    }
+    RootTab tab_q;
+    QP(get_root_tab(c, (int)qlb, false, &tab_q));
+    QP(dev_alloc(c, sizeof(u64) << qlb, &q->l0_den_inv_dev));
+    k_build_l0_den_inv<<<(unsigned)(((1ull << qlb) + 127) / 128), 128, 0, c->stream>>>(q->l0_den_inv_dev, tab_q,
+                                                                                    (u32)cm.degree_bits, qlb);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(ctx_wait(c));
+  }
   *out = q;
   return QPZK_OK;
 }
@@ -358,6 +374,7 @@ void qpzk_circuit_free(qpzk_circuit* q) {
   cudaSetDevice(q->ctx->device);
   dev_free(q->ctx, q->k_is_dev);
   dev_free(q->ctx, q->coset_aux_dev);
+  dev_free(q->ctx, q->l0_den_inv_dev);
   dev_free(q->ctx, q->cs_values);
   qpzk_batch_free(q->cs_batch);
   delete q;
@@ -484,7 +501,16 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     }
   }
   DevBuf small(c), qvals(c), qcoeffs(c);
-  QP(small.alloc((4 + 2 * (1u << qdb)) * 8));
+  std::vector<u64> apw(2 * QPZK_APW_STRIDE, 0);   // alpha_c^t for the reduction of the constraint terms
+  for (u32 ci = 0; ci < nch; ci++) {
+    u64 pwr = 1;
+    for (u32 t = 0; t < QPZK_APW_STRIDE; t++) {
+      apw[ci * QPZK_APW_STRIDE + t] = pwr;
+      pwr = glh::mul(pwr, chal.alpha[ci]);
+    }
+  }
+  QP(small.alloc((4 + 2 * (1u << qdb) + 2 * QPZK_APW_STRIDE) * 8));
+  CU(cudaMemcpyAsync(small.p + 4 + 2 * (1u << qdb), apw.data(), apw.size() * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(small.p, pi_hash, 32, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(small.p + 4, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(small.p + 4 + zh.size(), zh_inv.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -495,11 +521,11 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   if (cm.recursion)
     k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
         q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), tab_q, qvals.p);
+        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
   else
     k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
         q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), tab_q, qvals.p);
+        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
   c->launches++;
   CU(cudaGetLastError());
   // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)
