@@ -356,8 +356,9 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
   CU(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thresh = ~0ull;
   CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-  // Poseidon tables -> __constant__ (same values for every context; the copy is idempotent)
+  // Poseidon tables -> __constant__, once per device (kernels of other contexts may be reading them)
   static std::mutex mu;
+  static bool device_ready[64] = {false};
   {
     std::lock_guard<std::mutex> lk(mu);
     static PoseidonTablesHost* T = nullptr;
@@ -365,31 +366,35 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
       T = new PoseidonTablesHost();
       build_poseidon_tables(T);
     }
-    CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
-    CU(cudaMemcpyToSymbol(g_rc, T->rc, sizeof T->rc));
-    CU(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
-    CU(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
-    CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
-    CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
-    CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
-    u32 circ[12];
-    for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
-    u32 diag0 = (u32)kMdsDiag0;
-    CU(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
-    CU(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
+    if (device < 64 && !device_ready[device]) {
+      CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
+      CU(cudaMemcpyToSymbol(g_rc, T->rc, sizeof T->rc));
+      CU(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
+      CU(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
+      CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
+      CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
+      CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
+      u32 circ[12];
+      for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
+      u32 diag0 = (u32)kMdsDiag0;
+      CU(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
+      CU(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
 #if PV_MDS_F64
-    double circ_d[12];
-    for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
-    CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
+      double circ_d[12];
+      for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
+      CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
 #endif
-    // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
-    const int kMaxSmem = 72 * 1024;
-    CU(cudaFuncSetAttribute(k_ntt_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_ntt_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
+      const int kMaxSmem = 72 * 1024;
+      CU(cudaFuncSetAttribute(k_ntt_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaDeviceSynchronize());
+      device_ready[device] = true;
+    }
   }
   QP(dev_alloc(c, 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
   CU(ctx_wait(c));
