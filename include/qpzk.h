@@ -163,6 +163,10 @@ int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out
 /* Full materialisation (compatibility / debugging): `merkle_tree.leaves` row-major
  * [N][ncols+salt_cols] and `merkle_tree.digests` in plonky2's layout. Either may be NULL. */
 int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests);
+/* `OpeningSet::new` for one oracle (qp-plonky2 plonk/proof.rs, reached from prove() at
+ * /root/reference/wormhole/prover/src/lib.rs:233-237): every committed polynomial evaluated at an
+ * extension-field point; out = [ncols][2]. */
+int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point /* [2] */, uint64_t* out);
 uint32_t qpzk_batch_ncols(const qpzk_batch* b);
 uint32_t qpzk_batch_width(const qpzk_batch* b); /* ncols + salt_cols */
 uint32_t qpzk_batch_degree_bits(const qpzk_batch* b);
@@ -207,6 +211,13 @@ size_t qpzk_prove_trace(const qpzk_circuit* c, int which, uint64_t* out);
  * commit, [2] quotient + commit, [3] openings, [4] FRI combine, [5] FRI commit phase,
  * [6] proof of work, [7] queries. */
 int qpzk_prove_stage_ms(const qpzk_circuit* c, float* out16);
+
+/* `fri_proof_of_work` (qp-plonky2 fri/prover.rs): the SMALLEST witness w such that permuting the
+ * duplex-sponge state with w written at `input_pos` (the challenger's input buffer length) yields an
+ * output word 7 with at least `min_leading_zeros` leading zero bits. The reference returns whichever
+ * witness a rayon worker finds first; any valid witness verifies. */
+int qpzk_fri_pow(qpzk_ctx* ctx, const uint64_t* sponge_state /* [12] */, uint32_t input_pos,
+                 uint32_t min_leading_zeros, uint64_t* witness_out);
 
 /* ---- measurement helper: dependency-free integer multiply-add throughput (the Poseidon
  * roofline denominator). kind 0: 32-bit mad.lo.u32, kind 1: mad.wide.u32.

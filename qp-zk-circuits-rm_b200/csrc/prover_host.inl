@@ -264,7 +264,62 @@ struct DevBuf {  // scoped stream-ordered allocation
 
 }  // namespace qpzk
 
+namespace qpzk {
+// fri_proof_of_work: the smallest w such that the permutation of the sponge state with w written at
+// `pos` has >= min_lz leading zero bits in output word 7. Candidate windows grow from the expected
+// witness size (2^min_lz) upwards: a window much larger than that only burns permutations behind
+// the witness before the early exit can see it.
+static int grind_pow(qpzk_ctx* c, const PowState& ps, u32 pos, u32 min_lz, u64* witness) {
+  DevBuf best(c);
+  QP(best.alloc(8));
+  unsigned long long init = ~0ull;
+  CU(cudaMemcpyAsync(best.p, &init, 8, cudaMemcpyHostToDevice, c->stream));
+  u64 batch = 1ull << (min_lz < 12 ? 12 : (min_lz > 20 ? 20 : min_lz));
+  u64 start = 0;
+  unsigned long long found = ~0ull;
+  for (int round = 0; found == ~0ull; round++) {
+    if (round >= 2 && batch < (1ull << 22)) batch <<= 1;
+    k_pow_grind<<<(unsigned)(batch / 128), 128, 0, c->stream>>>(ps, pos, min_lz, start, batch,
+                                                               (unsigned long long*)best.p);
+    c->launches++;
+    CU(cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    start += batch;
+    if (start >= (1ull << 40)) return fail(QPZK_ERR_CUDA, "proof of work failed");
+  }
+  *witness = found;
+  return QPZK_OK;
+}
+}  // namespace qpzk
+
 extern "C" {
+
+int qpzk_fri_pow(qpzk_ctx* c, const uint64_t* sponge_state, uint32_t input_pos, uint32_t min_leading_zeros,
+                 uint64_t* witness_out) {
+  if (!c || !sponge_state || !witness_out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (input_pos >= 12 || min_leading_zeros > 40) return fail(QPZK_ERR_BAD_ARG, "bad position or difficulty");
+  CU(cudaSetDevice(c->device));
+  PowState ps;
+  memcpy(ps.s, sponge_state, sizeof ps.s);
+  return grind_pow(c, ps, input_pos, min_leading_zeros, witness_out);
+}
+
+int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point, uint64_t* out) {
+  if (!b || !point || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  const u64 n = 1ull << b->degree_bits;
+  DevBuf zpow(c), res(c);
+  QP(zpow.alloc(n * 16));
+  QP(res.alloc((size_t)b->ncols * 16));
+  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(gl2{point[0], point[1]}, n, zpow.p);
+  k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, res.p);
+  c->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, res.p, (size_t)b->ncols * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
 
 int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len, const uint64_t* digest4,
                         const uint64_t* constants_sigmas, qpzk_circuit** out) {
@@ -710,26 +765,8 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     memcpy(ps.s, ch.state, sizeof ps.s);
     u32 pos = (u32)ch.in.size();
     for (u32 i = 0; i < pos; i++) ps.s[i] = ch.in[i];
-    DevBuf best(c);
-    if (best.alloc(8) != QPZK_OK) { free_trees(); return QPZK_ERR_OOM; }
-    unsigned long long init = ~0ull;
-    cudaMemcpyAsync(best.p, &init, 8, cudaMemcpyHostToDevice, c->stream);
-    // candidate windows grow from the expected witness size (2^pow_bits) upwards: a window much larger
-    // than that only burns permutations behind the witness before the early exit can see it
-    u64 batch = 1ull << (cm.pow_bits < 12 ? 12 : (cm.pow_bits > 20 ? 20 : cm.pow_bits));
-    u64 start = 0;
-    unsigned long long found = ~0ull;
-    for (int round = 0; found == ~0ull; round++) {
-      if (round >= 2 && batch < (1ull << 22)) batch <<= 1;
-      k_pow_grind<<<(unsigned)(batch / 128), 128, 0, c->stream>>>(ps, pos, cm.pow_bits, start, batch,
-                                                                 (unsigned long long*)best.p);
-      c->launches++;
-      cudaMemcpyAsync(&found, best.p, 8, cudaMemcpyDeviceToHost, c->stream);
-      ctx_wait(c);
-      start += batch;
-      if (start >= (1ull << 40)) { free_trees(); return fail(QPZK_ERR_CUDA, "proof of work failed"); }
-    }
-    pow_witness = found;
+    int prc = grind_pow(c, ps, pos, cm.pow_bits, &pow_witness);
+    if (prc != QPZK_OK) { free_trees(); return prc; }
   }
   ch.observe(pow_witness);
   u64 pow_resp = ch.get();

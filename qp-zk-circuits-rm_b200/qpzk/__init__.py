@@ -79,6 +79,8 @@ def load_library():
         "qpzk_batch_get_lde_rows": (i, [_vp, _u32p, u32, u32, _u64p]),
         "qpzk_batch_open": (i, [_vp, u64, _u64p, _u64p]),
         "qpzk_batch_export": (i, [_vp, _u64p, _u64p]),
+        "qpzk_batch_eval_ext": (i, [_vp, _u64p, _u64p]),
+        "qpzk_fri_pow": (i, [_vp, _u64p, u32, u32, ctypes.POINTER(u64)]),
         "qpzk_batch_ncols": (u32, [_vp]),
         "qpzk_batch_width": (u32, [_vp]),
         "qpzk_batch_degree_bits": (u32, [_vp]),
@@ -172,6 +174,13 @@ class Context:
     def d2h(self, host_array, dev_ptr):
         _check(load_library().qpzk_memcpy_d2h(self._h, host_array.ctypes.data_as(_vp), _vp(dev_ptr),
                                               host_array.nbytes))
+
+    def fri_pow(self, sponge_state, input_pos, min_leading_zeros):
+        """`fri_proof_of_work`: smallest valid witness for the given duplex-sponge state."""
+        st = _arr(sponge_state)
+        out = ctypes.c_uint64()
+        _check(load_library().qpzk_fri_pow(self._h, _ptr(st), input_pos, min_leading_zeros, ctypes.byref(out)))
+        return out.value
 
     # -- PoseidonHash --
     def poseidon_permute(self, states):
@@ -364,6 +373,13 @@ class PolynomialBatch:
         _check(load_library().qpzk_batch_get_lde_rows(self._h, idx.ctypes.data_as(_u32p), idx.size, step,
                                                       _ptr(out)))
         return out[0] if np.ndim(index) == 0 else out
+
+    def eval_ext(self, point):
+        """Every committed polynomial at an extension point (a, b): [ncols][2] (`OpeningSet::new`)."""
+        pt = _arr(point)
+        out = np.zeros((self.ncols, 2), np.uint64)
+        _check(load_library().qpzk_batch_eval_ext(self._h, _ptr(pt), _ptr(out)))
+        return out
 
     def open(self, leaf_index):
         """(merkle_tree.leaves[leaf_index], merkle_tree.prove(leaf_index).siblings)"""

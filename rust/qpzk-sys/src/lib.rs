@@ -57,6 +57,8 @@ extern "C" {
     pub fn qpzk_batch_get_lde_rows(b: *const qpzk_batch, idx: *const u32, nidx: u32, step: u32, out_: *mut u64) -> c_int;
     pub fn qpzk_batch_open(b: *const qpzk_batch, leaf_index: u64, leaf_out: *mut u64, siblings_out: *mut u64) -> c_int;
     pub fn qpzk_batch_export(b: *const qpzk_batch, leaves: *mut u64, digests: *mut u64) -> c_int;
+    pub fn qpzk_batch_eval_ext(b: *const qpzk_batch, point: *const u64, out_: *mut u64) -> c_int;
+    pub fn qpzk_fri_pow(ctx: *mut qpzk_ctx, sponge_state: *const u64, input_pos: u32, min_leading_zeros: u32, witness_out: *mut u64) -> c_int;
     pub fn qpzk_batch_ncols(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_width(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_degree_bits(b: *const qpzk_batch) -> u32;

@@ -251,3 +251,46 @@ def test_every_degree_matches_oracle(ctx, k):
     assert np.array_equal(b.polynomials, want["coeffs"])
     assert np.array_equal(b.cap, want["cap"])
     b.free()
+
+
+def test_batch_eval_ext_is_horner_in_the_extension(ctx):
+    """`OpeningSet::new` for one oracle: p(zeta) for every committed polynomial, zeta in F_p^2 (X^2 = 7)."""
+    import qpzk
+    rng = np.random.default_rng(31)
+    k, ncols = 9, 7
+    vals = rand_felts(rng, (ncols, 1 << k))
+    b = qpzk.PolynomialBatch.from_values(ctx, vals, 3, 4)
+    coeffs = b.polynomials
+    z = (int(rng.integers(0, P, dtype=np.uint64)), int(rng.integers(0, P, dtype=np.uint64)))
+    got = b.eval_ext(np.array(z, np.uint64))
+    for c in range(ncols):
+        a0, a1 = 0, 0
+        for coef in coeffs[c][::-1]:      # (a0 + a1 X) * (z0 + z1 X) + coef
+            a0, a1 = (a0 * z[0] + 7 * a1 * z[1] + int(coef)) % P, (a0 * z[1] + a1 * z[0]) % P
+        assert (int(got[c, 0]), int(got[c, 1])) == (a0, a1)
+    b.free()
+
+
+@pytest.mark.parametrize("bits,pos", [(8, 3), (16, 0), (16, 5)])
+def test_fri_pow_returns_the_smallest_valid_witness(ctx, bits, pos):
+    """`fri_proof_of_work`: permuting the state with the witness at `pos` gives >= `bits` leading zeros in
+    output word 7; no smaller witness does (the reference takes whichever a rayon worker finds first)."""
+    rng = np.random.default_rng(40 + bits + pos)
+    state = rand_felts(rng, 12)
+    w = ctx.fri_pow(state, pos, bits)
+
+    def lz(cand):
+        s = state.copy()
+        s[pos] = np.uint64(cand)
+        v = int(orc.poseidon(s)[7])
+        return 64 - v.bit_length()
+
+    assert lz(w) >= bits
+    if bits <= 8:                          # exhaustive minimality check is cheap only for easy targets
+        assert all(lz(c) < bits for c in range(w))
+    else:
+        # minimality through the GPU itself: every smaller candidate, permuted in one batch
+        cands = np.tile(state, (w, 1))
+        cands[:, pos] = np.arange(w, dtype=np.uint64)
+        out7 = ctx.poseidon_permute(cands)[:, 7]
+        assert not (out7 < np.uint64(1 << (64 - bits))).any()
