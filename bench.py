@@ -479,6 +479,19 @@ def run_gpu(args, rank, local_rank, world):
                       "note": "gate definitions restated from upstream plonky2, not pinned by a reference fixture"}
         for q in acircs:
             q.free()
+        # a flat 16-ary aggregation node is ~2^16 rows: single-proof latency at that degree
+        bk = 16
+        bc = synth.build_recursion(bk, zk=True, seed=10, provider=synth.GpuProvider(ctx0))
+        bcirc = qpzk.Circuit(ctx0, bc["common"], bc["digest"], bc["constants_sigmas"])
+        blat = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            bproof = bcirc.prove(bc["wires"], bc["public_inputs"], bc["salts"])
+            if i:
+                blat.append((time.perf_counter() - t0) * 1e3)
+        aggregator["flat_node_2^%d_rows" % bk] = {"latency_ms_median": float(np.median(blat)), "proof_bytes": len(bproof),
+                                                  "stage_ms": bcirc.stage_ms()}
+        bcirc.free()
 
     sharded = None
     if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:

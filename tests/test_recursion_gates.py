@@ -53,7 +53,7 @@ def test_every_gate_type_is_constrained():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k,zk", [(7, False), (9, True), (12, False)])
+@pytest.mark.parametrize("k,zk", [(7, False), (9, True), (12, False), (15, True)])
 def test_gpu_recursion_proof_matches_oracle(k, zk):
     import qpzk
     ctx = qpzk.Context(0)
