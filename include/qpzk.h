@@ -204,6 +204,19 @@ int qpzk_prove(qpzk_circuit* c, const uint64_t* wires, const uint64_t* public_in
                uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
                const uint64_t* salts_quotient, uint32_t flags, uint8_t* proof_out, size_t proof_cap,
                size_t* proof_len);
+/* Per-stage hooks for a fork that keeps plonky2's own `prove()` loop and transcript (integration depth (b),
+ * INTEGRATION.md): the same device code qpzk_prove runs.
+ * qpzk_zs_partial_products = `all_wires_permutation_partial_products` + the running product (qp-plonky2
+ *   plonk/prover.rs): wires host [num_wires][n]; out [nch*(1+npp)][n] = Z_0..Z_{nch-1} followed by each
+ *   challenge's num_partial_products columns (the layout of the second committed oracle).
+ * qpzk_quotient = `compute_quotient_polys` (plonk/prover.rs + vanishing_poly.rs + gates/*): from the wires
+ *   and Z|partial-product batches committed on the circuit's context; out_chunks [nch*qdf][n] quotient
+ *   chunk coefficients, ready for `from_coeffs`. pi_hash = hash_no_pad(public_inputs). */
+int qpzk_zs_partial_products(qpzk_circuit* c, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas,
+                             uint64_t* out);
+int qpzk_quotient(qpzk_circuit* c, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch,
+                  const uint64_t* pi_hash /* [4] */, const uint64_t* betas, const uint64_t* gammas,
+                  const uint64_t* alphas, uint64_t* out_chunks);
 /* Parity hook (flags bit 0): which = 0 challenges, 1 zs|partial-product values [.][n],
  * 2 quotient chunk coefficients [.][n], 3 FRI input polynomial [n][2]. Returns u64 count. */
 size_t qpzk_prove_trace(const qpzk_circuit* c, int which, uint64_t* out);

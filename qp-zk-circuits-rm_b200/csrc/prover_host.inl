@@ -457,6 +457,89 @@ int qpzk_prove_stage_ms(const qpzk_circuit* q, float* out16) {
 namespace qpzk {
 
 // Proof of one witness. wires_host: [num_wires][n]. Salts: NULL or host [4][N] per blinded oracle.
+// ---- H8: Z and partial products on the subgroup: zs_vals [nch*(1+npp)][n] = Z_0..Z_{nch-1}, then the
+// partial products of each challenge (all_wires_permutation_partial_products + the running product) ----
+static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, const Challenges& chal, DevBuf* zs_vals) {
+  qpzk_ctx* c = q->ctx;
+  const CircuitDesc& d = q->desc;
+  const u32 k = d.degree_bits, nch = d.num_challenges, npp = d.num_partial_products;
+  const u64 n = 1ull << k;
+  RootTab tab_n;
+  QP(get_root_tab(c, (int)k, false, &tab_n));
+  const u32 nchunks = npp + 1, nzs = nch * (1 + npp);
+  DevBuf chunk_q(c), row_prod(c);
+  QP(chunk_q.alloc((size_t)nch * nchunks * n * 8));
+  QP(row_prod.alloc((size_t)nch * n * 8));
+  QP(zs_vals->alloc((size_t)nzs * n * 8));
+  k_zs_chunk_quotients<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(
+      wires_dev, q->cs_values, q->k_is_dev, d, chal, tab_n, chunk_q.p, row_prod.p);
+  k_prefix_product<<<nch, 1024, 0, c->stream>>>(row_prod.p, zs_vals->p, n);
+  k_partial_products<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(chunk_q.p, zs_vals->p, nch, npp, n,
+                                                                                   zs_vals->p + (size_t)nch * n);
+  c->launches += 3;
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+
+// ---- H9: compute_quotient_polys: vanishing(x)/Z_H(x) on the quotient coset from the three committed
+// oracles, coset IFFT, coefficients [nch][qdf*n] (= nch*qdf chunks of n) ----
+static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash,
+                                   const Challenges& chal, DevBuf* qcoeffs) {
+  qpzk_ctx* c = q->ctx;
+  const CommonHost& cm = q->common;
+  const CircuitDesc& d = q->desc;
+  const u32 k = d.degree_bits, r = d.rate_bits, nch = d.num_challenges, qdb = d.quotient_degree_bits;
+  const u64 n = 1ull << k, N = n << r;
+  const u32 qlb = k + qdb;
+  const u64 qlde = 1ull << qlb;
+  std::vector<u64> zh(1u << qdb), zh_inv(1u << qdb);
+  {
+    u64 gn = glh::pow(GL_GEN, n), wq = glh::root_of_unity(qdb);
+    for (u32 i = 0; i < (1u << qdb); i++) {
+      zh[i] = glh::sub(glh::mul(gn, glh::pow(wq, i)), 1);
+      zh_inv[i] = glh::inv(zh[i]);
+    }
+  }
+  DevBuf small(c), qvals(c);
+  std::vector<u64> apw(2 * QPZK_APW_STRIDE, 0);   // alpha_c^t for the reduction of the constraint terms
+  for (u32 ci = 0; ci < nch; ci++) {
+    u64 pwr = 1;
+    for (u32 t = 0; t < QPZK_APW_STRIDE; t++) {
+      apw[ci * QPZK_APW_STRIDE + t] = pwr;
+      pwr = glh::mul(pwr, chal.alpha[ci]);
+    }
+  }
+  QP(small.alloc((4 + 2 * (1u << qdb) + 2 * QPZK_APW_STRIDE) * 8));
+  CU(cudaMemcpyAsync(small.p + 4 + 2 * (1u << qdb), apw.data(), apw.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(small.p, pi_hash, 32, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(small.p + 4, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(small.p + 4 + zh.size(), zh_inv.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  QP(qvals.alloc((size_t)nch * qlde * 8));
+  QP(qcoeffs->alloc((size_t)nch * qlde * 8));
+  RootTab tab_q;
+  QP(get_root_tab(c, (int)qlb, false, &tab_q));
+  if (cm.recursion)
+    k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
+        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
+  else
+    k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
+        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
+  c->launches++;
+  CU(cudaGetLastError());
+  // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)
+  QP(launch_ifft(c, qvals.p, qlde, qcoeffs->p, qlde, nch, (int)qlb));
+  RootTab tab_ginv;
+  QP(get_pow_tab(c, glh::inv(GL_GEN), (int)qlb, &tab_ginv));
+  k_scale_by_powers<<<dim3((unsigned)((qlde + 255) / 256), nch), 256, 0, c->stream>>>(qcoeffs->p, qlde, tab_ginv);
+  c->launches++;
+  CU(cudaGetLastError());
+  // the small staging vectors above are pageable host memory: the copies must have left before they die
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
+
 static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u32 npi, const u64* salt_w,
                       const u64* salt_z, const u64* salt_q, u32 flags, std::vector<uint8_t>* proof) {
   qpzk_ctx* c = q->ctx;
@@ -515,20 +598,9 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 
   // ---- (4,5) Z + partial products, commit ----
   tic();
-  RootTab tab_n;
-  QP(get_root_tab(c, (int)k, false, &tab_n));
-  const u32 nchunks = npp + 1, nzs = nch * (1 + npp);
-  DevBuf chunk_q(c), row_prod(c), zs_vals(c);
-  QP(chunk_q.alloc((size_t)nch * nchunks * n * 8));
-  QP(row_prod.alloc((size_t)nch * n * 8));
-  QP(zs_vals.alloc((size_t)nzs * n * 8));
-  k_zs_chunk_quotients<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(
-      wires_dev, q->cs_values, q->k_is_dev, d, chal, tab_n, chunk_q.p, row_prod.p);
-  k_prefix_product<<<nch, 1024, 0, c->stream>>>(row_prod.p, zs_vals.p, n);
-  k_partial_products<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(chunk_q.p, zs_vals.p, nch, npp, n,
-                                                                                   zs_vals.p + (size_t)nch * n);
-  c->launches += 3;
-  CU(cudaGetLastError());
+  const u32 nzs = nch * (1 + npp);
+  DevBuf zs_vals(c);
+  QP(compute_zs_partial_products(q, wires_dev, chal, &zs_vals));
   qpzk_batch* zs_b = nullptr;
   QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, !on_device, salt_cols, &zs_b));
   std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> zs_guard(zs_b, qpzk_batch_free);
@@ -547,49 +619,8 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   tic();
   const u32 qlb = k + qdb;
   const u64 qlde = 1ull << qlb;
-  std::vector<u64> zh(1u << qdb), zh_inv(1u << qdb);
-  {
-    u64 gn = glh::pow(GL_GEN, n), wq = glh::root_of_unity(qdb);
-    for (u32 i = 0; i < (1u << qdb); i++) {
-      zh[i] = glh::sub(glh::mul(gn, glh::pow(wq, i)), 1);
-      zh_inv[i] = glh::inv(zh[i]);
-    }
-  }
-  DevBuf small(c), qvals(c), qcoeffs(c);
-  std::vector<u64> apw(2 * QPZK_APW_STRIDE, 0);   // alpha_c^t for the reduction of the constraint terms
-  for (u32 ci = 0; ci < nch; ci++) {
-    u64 pwr = 1;
-    for (u32 t = 0; t < QPZK_APW_STRIDE; t++) {
-      apw[ci * QPZK_APW_STRIDE + t] = pwr;
-      pwr = glh::mul(pwr, chal.alpha[ci]);
-    }
-  }
-  QP(small.alloc((4 + 2 * (1u << qdb) + 2 * QPZK_APW_STRIDE) * 8));
-  CU(cudaMemcpyAsync(small.p + 4 + 2 * (1u << qdb), apw.data(), apw.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p, pi_hash, 32, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p + 4, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p + 4 + zh.size(), zh_inv.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  QP(qvals.alloc((size_t)nch * qlde * 8));
-  QP(qcoeffs.alloc((size_t)nch * qlde * 8));
-  RootTab tab_q;
-  QP(get_root_tab(c, (int)qlb, false, &tab_q));
-  if (cm.recursion)
-    k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
-        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
-  else
-    k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
-        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
-  c->launches++;
-  CU(cudaGetLastError());
-  // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)
-  QP(launch_ifft(c, qvals.p, qlde, qcoeffs.p, qlde, nch, (int)qlb));
-  RootTab tab_ginv;
-  QP(get_pow_tab(c, glh::inv(GL_GEN), (int)qlb, &tab_ginv));
-  k_scale_by_powers<<<dim3((unsigned)((qlde + 255) / 256), nch), 256, 0, c->stream>>>(qcoeffs.p, qlde, tab_ginv);
-  c->launches++;
-  CU(cudaGetLastError());
+  DevBuf qcoeffs(c);
+  QP(compute_quotient_chunks(q, wires_b, zs_b, pi_hash, chal, &qcoeffs));
   qpzk_batch* q_b = nullptr;
   QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, !on_device, salt_cols, &q_b));
   std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> q_guard(q_b, qpzk_batch_free);
@@ -873,6 +904,58 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 }  // namespace qpzk
 
 extern "C" {
+
+static int challenges_from(const qpzk_circuit* q, const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
+                           Challenges* chal) {
+  memset(chal, 0, sizeof *chal);
+  for (u32 i = 0; i < q->desc.num_challenges; i++) {
+    if (betas) chal->beta[i] = betas[i];
+    if (gammas) chal->gamma[i] = gammas[i];
+    if (alphas) chal->alpha[i] = alphas[i];
+  }
+  return QPZK_OK;
+}
+
+int qpzk_zs_partial_products(qpzk_circuit* q, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas,
+                             uint64_t* out) {
+  if (!q || !wires || !betas || !gammas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = q->ctx;
+  CU(cudaSetDevice(c->device));
+  const CircuitDesc& d = q->desc;
+  const u64 n = 1ull << d.degree_bits;
+  Challenges chal;
+  challenges_from(q, betas, gammas, nullptr, &chal);
+  DevBuf wd(c), zs(c);
+  QP(wd.alloc((size_t)d.num_wires * n * 8));
+  CU(cudaMemcpyAsync(wd.p, wires, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
+  QP(compute_zs_partial_products(q, wd.p, chal, &zs));
+  const size_t cnt = (size_t)d.num_challenges * (1 + d.num_partial_products) * n;
+  CU(cudaMemcpyAsync(out, zs.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
+
+int qpzk_quotient(qpzk_circuit* q, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch, const uint64_t* pi_hash,
+                  const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out_chunks) {
+  if (!q || !wires_batch || !zs_batch || !pi_hash || !betas || !gammas || !alphas || !out_chunks)
+    return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = q->ctx;
+  const CircuitDesc& d = q->desc;
+  if (wires_batch->ctx != c || zs_batch->ctx != c) return fail(QPZK_ERR_BAD_ARG, "batches belong to another context");
+  if (wires_batch->degree_bits != d.degree_bits || zs_batch->degree_bits != d.degree_bits ||
+      wires_batch->rate_bits != d.rate_bits || zs_batch->rate_bits != d.rate_bits || wires_batch->ncols != d.num_wires ||
+      zs_batch->ncols != d.num_challenges * (1 + d.num_partial_products))
+    return fail(QPZK_ERR_BAD_ARG, "batch shape does not match the circuit");
+  CU(cudaSetDevice(c->device));
+  Challenges chal;
+  challenges_from(q, betas, gammas, alphas, &chal);
+  DevBuf qc(c);
+  QP(compute_quotient_chunks(q, wires_batch, zs_batch, pi_hash, chal, &qc));
+  const size_t cnt = ((size_t)d.num_challenges << (d.degree_bits + d.quotient_degree_bits));
+  CU(cudaMemcpyAsync(out_chunks, qc.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
 
 int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, const uint64_t* public_inputs, uint32_t num_public_inputs,
                const uint64_t* salts_wires, const uint64_t* salts_zs, const uint64_t* salts_quotient, uint32_t flags,

@@ -92,6 +92,8 @@ def load_library():
         "qpzk_circuit_free": (None, [_vp]),
         "qpzk_prove": (i, [_vp, _vp, _u64p, u32, _vp, _vp, _vp, u32, ctypes.c_char_p, ctypes.c_size_t,
                            ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_zs_partial_products": (i, [_vp, _vp, _u64p, _u64p, _u64p]),
+        "qpzk_quotient": (i, [_vp, _vp, _vp, _u64p, _u64p, _u64p, _u64p, _u64p]),
         "qpzk_prove_trace": (ctypes.c_size_t, [_vp, i, _u64p]),
         "qpzk_prove_stage_ms": (i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     }
@@ -473,6 +475,21 @@ class Circuit:
         _check(L.qpzk_prove(self._h, _vp(wires_dev), _ptr(pi), pi.size, sp[0], sp[1], sp[2], 2, buf, cap,
                             ctypes.byref(ln)))
         return buf.raw[:ln.value]
+
+    def zs_partial_products(self, wires, betas, gammas, nch=2, npp=9):
+        """H8 as a stand-alone stage: [nch*(1+npp)][n]."""
+        w, b, g = _arr(wires), _arr(betas), _arr(gammas)
+        out = np.zeros((nch * (1 + npp), self.n), np.uint64)
+        _check(load_library().qpzk_zs_partial_products(self._h, w.ctypes.data_as(_vp), _ptr(b), _ptr(g), _ptr(out)))
+        return out
+
+    def quotient(self, wires_batch, zs_batch, pi_hash, betas, gammas, alphas, nch=2, qdf=8):
+        """H9 as a stand-alone stage: quotient chunk coefficients [nch*qdf][n]."""
+        ph, b, g, a = _arr(pi_hash), _arr(betas), _arr(gammas), _arr(alphas)
+        out = np.zeros((nch * qdf, self.n), np.uint64)
+        _check(load_library().qpzk_quotient(self._h, wires_batch._h, zs_batch._h, _ptr(ph), _ptr(b), _ptr(g), _ptr(a),
+                                            _ptr(out)))
+        return out
 
     def trace(self, which):
         L = load_library()

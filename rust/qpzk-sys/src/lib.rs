@@ -68,6 +68,8 @@ extern "C" {
     pub fn qpzk_circuit_verifier_only(c: *const qpzk_circuit, out_: *mut u8, cap: usize) -> usize;
     pub fn qpzk_circuit_free(c: *mut qpzk_circuit);
     pub fn qpzk_prove(c: *mut qpzk_circuit, wires: *const u64, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+    pub fn qpzk_zs_partial_products(c: *mut qpzk_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out_: *mut u64) -> c_int;
+    pub fn qpzk_quotient(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, pi_hash: *const u64, betas: *const u64, gammas: *const u64, alphas: *const u64, out_chunks: *mut u64) -> c_int;
     pub fn qpzk_prove_trace(c: *const qpzk_circuit, which: c_int, out_: *mut u64) -> usize;
     pub fn qpzk_prove_stage_ms(c: *const qpzk_circuit, out16: *mut f32) -> c_int;
     pub fn qpzk_measure_imad_peak(ctx: *mut qpzk_ctx, kind: c_int, out_ops_per_s: *mut f64) -> c_int;

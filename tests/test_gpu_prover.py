@@ -84,3 +84,43 @@ def test_unsupported_gate_set_is_refused(ctx):
     bad = common_bytes(6, False, [4], gates=[(9, None), (3, 2), (12, None), (2, 63), (0, 20), (27, None)])
     with pytest.raises(qpzk.QpzkError):
         qpzk.Circuit(ctx, bad, np.zeros(4, np.uint64), np.zeros((84, 64), np.uint64))
+
+
+@pytest.mark.parametrize("k,zk", [(8, False), (12, True)])
+def test_stage_hooks_match_the_oracle_trace(ctx, k, zk):
+    """qpzk_zs_partial_products / qpzk_quotient / qpzk_batch_eval_ext called one by one - the way a qp-plonky2
+    fork that keeps its own prove() loop would - with the challenges of the oracle's transcript: each
+    stage must reproduce the oracle prover's intermediate values exactly."""
+    import qpzk
+    circ = minibuilder.build(k, zk=zk, seed=50 + k)
+    n = 1 << k
+    oc = orc.Circuit(circ["common"], circ["digest"], circ["constants_sigmas"], threads=8)
+    oc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
+    tr = oc.trace(rounds=len(circ["arities"]))
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    salts = circ["salts"] or [None, None, None]
+    # H8
+    zs = gc.zs_partial_products(circ["wires"], tr["betas"], tr["gammas"])
+    assert np.array_equal(zs, tr["zs_pp"])
+    # commits (H2-H7), then H9 on the committed batches
+    wb = qpzk.PolynomialBatch.from_values(ctx, circ["wires"], 3, 4, salts=salts[0])
+    zb = qpzk.PolynomialBatch.from_values(ctx, zs, 3, 4, salts=salts[1])
+    pih = orc.hash_no_pad(circ["public_inputs"])
+    chunks = gc.quotient(wb, zb, pih, tr["betas"], tr["gammas"], tr["alphas"])
+    assert np.array_equal(chunks, tr["quotient_chunks"])
+    # H10: openings of the quotient oracle at zeta
+    qb = qpzk.PolynomialBatch.from_coeffs(ctx, chunks, 3, 4, salts=salts[2])
+    ev = qb.eval_ext(tr["zeta"])
+    z = (int(tr["zeta"][0]), int(tr["zeta"][1]))
+    P = orc.P
+    for c in (0, 15):
+        a0, a1 = 0, 0
+        for coef in chunks[c][::-1]:
+            a0, a1 = (a0 * z[0] + 7 * a1 * z[1] + int(coef)) % P, (a0 * z[1] + a1 * z[0]) % P
+        assert (int(ev[c, 0]), int(ev[c, 1])) == (a0, a1)
+    # shape checks are enforced
+    with pytest.raises(qpzk.QpzkError):
+        gc.quotient(zb, wb, pih, tr["betas"], tr["gammas"], tr["alphas"])
+    for x in (wb, zb, qb):
+        x.free()
+    gc.free()
