@@ -217,6 +217,26 @@ int qpzk_zs_partial_products(qpzk_circuit* c, const uint64_t* wires, const uint6
 int qpzk_quotient(qpzk_circuit* c, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch,
                   const uint64_t* pi_hash /* [4] */, const uint64_t* betas, const uint64_t* gammas,
                   const uint64_t* alphas, uint64_t* out_chunks);
+/* The FRI prover as a resumable object (`PolynomialBatch::prove_openings`, `fri_committed_trees`,
+ * `fri_prover_query_rounds`; qp-plonky2 fri/oracle.rs, fri/prover.rs); the transcript stays with the caller:
+ *   qpzk_fri_begin(circuit, wires, zs|pp, quotient batches, zeta, alpha)      batch-combine at zeta / g*zeta
+ *   repeat qpzk_fri_num_rounds times:
+ *     qpzk_fri_commit_round -> cap [2^cap_height][4]   (caller observes it and squeezes beta)
+ *     qpzk_fri_fold(beta)
+ *   qpzk_fri_final_poly -> [len][2] extension coefficients   (caller observes, grinds with qpzk_fri_pow)
+ *   qpzk_fri_query(x_index) -> for each of the 4 oracles (constants|sigmas, wires, zs|pp, quotient): the
+ *     salted row then its Merkle path ([L][4]); then for each reduction round: 2^arity_bits extension
+ *     evaluations then the path. Lengths follow from the circuit; *len_words reports the total. */
+typedef struct qpzk_fri qpzk_fri;
+int qpzk_fri_begin(qpzk_circuit* c, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch,
+                   const qpzk_batch* quotient_batch, const uint64_t* zeta /* [2] */, const uint64_t* alpha /* [2] */,
+                   qpzk_fri** out);
+uint32_t qpzk_fri_num_rounds(const qpzk_fri* f);
+int qpzk_fri_commit_round(qpzk_fri* f, uint64_t* cap_out);
+int qpzk_fri_fold(qpzk_fri* f, const uint64_t* beta /* [2] */);
+int qpzk_fri_final_poly(qpzk_fri* f, uint64_t* out, size_t cap_words, size_t* len_words);
+int qpzk_fri_query(qpzk_fri* f, uint64_t x_index, uint64_t* out, size_t cap_words, size_t* len_words);
+void qpzk_fri_free(qpzk_fri* f);
 /* Parity hook (flags bit 0): which = 0 challenges, 1 zs|partial-product values [.][n],
  * 2 quotient chunk coefficients [.][n], 3 FRI input polynomial [n][2]. Returns u64 count. */
 size_t qpzk_prove_trace(const qpzk_circuit* c, int which, uint64_t* out);

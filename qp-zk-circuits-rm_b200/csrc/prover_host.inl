@@ -457,6 +457,210 @@ int qpzk_prove_stage_ms(const qpzk_circuit* q, float* out16) {
 namespace qpzk {
 
 // Proof of one witness. wires_host: [num_wires][n]. Salts: NULL or host [4][N] per blinded oracle.
+// ---- H11-H14: the FRI prover as a resumable object (prove_openings, fri_committed_trees,
+// fri_prover_query_rounds of qp-plonky2 fri/oracle.rs, fri/prover.rs). The transcript stays with the
+// caller: begin -> [commit_round -> (observe cap, squeeze beta) -> fold]* -> final_poly -> queries. ----
+struct FriTree {
+  u64* leaves = nullptr;  // AoS [nleaves][2*arity]
+  u64* levels = nullptr;
+  u32 log_n = 0, arity_bits = 0;
+};
+}  // namespace qpzk
+
+struct qpzk_fri {
+  qpzk_circuit* q = nullptr;
+  qpzk_ctx* c = nullptr;
+  const qpzk_batch* oracles[4] = {nullptr, nullptr, nullptr, nullptr};
+  u64 *fpoly = nullptr, *fold_a = nullptr, *fold_b = nullptr, *vals = nullptr;  // device
+  u64* coeffs_cur = nullptr;  // SoA [2][cur_n]
+  u64 cur_n = 0, shift = GL_GEN;
+  u32 cur_k = 0;
+  bool flip = false;
+  size_t round = 0;
+  std::vector<qpzk::FriTree> trees;
+  ~qpzk_fri() {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& t : trees) {
+      dev_free(c, t.leaves);
+      dev_free(c, t.levels);
+    }
+    dev_free(c, fpoly);
+    dev_free(c, fold_a);
+    dev_free(c, fold_b);
+    dev_free(c, vals);
+  }
+};
+
+namespace qpzk {
+
+// prove_openings up to the polynomial that enters FRI: batch 0 = every polynomial of the four oracles
+// at zeta, batch 1 = the Z polynomials at g*zeta; final = q0 * alpha^(len batch 1) + q1 (no multiply-by-X).
+static int fri_begin(qpzk_circuit* q, qpzk_batch* const* oracles, const u64* zeta, const u64* alpha, qpzk_fri** out) {
+  qpzk_ctx* c = q->ctx;
+  const CircuitDesc& d = q->desc;
+  const u32 k = d.degree_bits, r = d.rate_bits, nch = d.num_challenges;
+  const u64 n = 1ull << k, N = n << r;
+  std::unique_ptr<qpzk_fri> F(new qpzk_fri());
+  F->q = q;
+  F->c = c;
+  u32 total_polys = 0;
+  for (int o = 0; o < 4; o++) {
+    F->oracles[o] = oracles[o];
+    total_polys += oracles[o]->ncols;
+  }
+  u64 wn = glh::root_of_unity(k);
+  u64 zeta_next[2] = {glh::mul(zeta[0], wn), glh::mul(zeta[1], wn)};
+  std::vector<u64> apow((size_t)total_polys * 2);
+  {
+    u64 a = 1, b = 0;
+    for (u32 j = 0; j < total_polys; j++) {
+      apow[2 * j] = a;
+      apow[2 * j + 1] = b;
+      u64 na = glh::add(glh::mul(a, alpha[0]), glh::mul(7, glh::mul(b, alpha[1])));
+      u64 nb = glh::add(glh::mul(a, alpha[1]), glh::mul(b, alpha[0]));
+      a = na;
+      b = nb;
+    }
+  }
+  DevBuf apow_dev(c), comp0(c), comp1(c), q0(c), q1(c);
+  QP(apow_dev.alloc(apow.size() * 8));
+  CU(cudaMemcpyAsync(apow_dev.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  QP(comp0.alloc(n * 16)); QP(comp1.alloc(n * 16)); QP(q0.alloc(n * 16)); QP(q1.alloc(n * 16));
+  QP(dev_alloc(c, n * 16, &F->fpoly));
+  QP(dev_alloc(c, n * 16 / 2 + 64, &F->fold_a));
+  QP(dev_alloc(c, n * 16 / 2 + 64, &F->fold_b));
+  QP(dev_alloc(c, (size_t)2 * N * 8, &F->vals));
+  PolyList pl0;
+  memset(&pl0, 0, sizeof pl0);
+  pl0.noracles = 4;
+  for (int o = 0; o < 4; o++) { pl0.base[o] = oracles[o]->coeffs; pl0.count[o] = oracles[o]->ncols; }
+  PolyList pl1;
+  memset(&pl1, 0, sizeof pl1);
+  pl1.noracles = 1; pl1.base[0] = oracles[2]->coeffs; pl1.count[0] = nch;
+  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl0, n, apow_dev.p, comp0.p);
+  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl1, n, apow_dev.p, comp1.p);
+  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp0.p, q0.p, n, gl2{zeta[0], zeta[1]});
+  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp1.p, q1.p, n, gl2{zeta_next[0], zeta_next[1]});
+  gl2 shift_s = gl2{apow[2 * nch], apow[2 * nch + 1]};
+  k_ext_axpy<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(q0.p, q1.p, shift_s, n, F->fpoly);
+  c->launches += 5;
+  CU(cudaGetLastError());
+  F->coeffs_cur = F->fpoly;
+  F->cur_n = n;
+  F->cur_k = k;
+  *out = F.release();
+  return QPZK_OK;
+}
+
+// One commit-phase round: LDE of the current coefficients on the coset shift*<w>, leaves of 2^arity_bits
+// extension evaluations, MerkleTree::new; the cap goes back to the caller's transcript.
+static int fri_commit_round(qpzk_fri* F, u64* cap_out) {
+  qpzk_ctx* c = F->c;
+  const CommonHost& cm = F->q->common;
+  const u32 r = F->q->desc.rate_bits, h = (u32)cm.cap_height;
+  if (F->round >= cm.arities.size() || F->trees.size() != F->round) return fail(QPZK_ERR_BAD_ARG, "FRI round out of order");
+  const u64 ab = cm.arities[F->round];
+  const u64 NV = F->cur_n << r;  // values in this round
+  QP(launch_lde_shift(c, F->coeffs_cur, F->cur_n, F->vals, NV, 2, (int)F->cur_k, (int)r, F->shift));
+  FriTree t;
+  t.arity_bits = (u32)ab;
+  t.log_n = F->cur_k + r - (u32)ab;
+  if (h > t.log_n) return fail(QPZK_ERR_UNSUPPORTED, "FRI tree smaller than the cap");
+  QP(dev_alloc(c, NV * 16, &t.leaves));
+  F->trees.push_back(t);  // owned by F from here on
+  QP(dev_alloc(c, (2ull << t.log_n) * 32, &F->trees.back().levels));
+  t = F->trees.back();
+  k_ext_interleave<<<(unsigned)((NV + 255) / 256), 256, 0, c->stream>>>(F->vals, NV, t.leaves);
+  c->launches++;
+  QP(build_tree(c, t.leaves, 2ull << ab, 1, 2u << ab, t.log_n, h, t.levels, nullptr));
+  CU(cudaMemcpyAsync(cap_out, cap_ptr(t.levels, t.log_n, h), (size_t)32 << h, cudaMemcpyDeviceToHost, c->stream));
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
+
+// Fold in coefficient space: chunks of 2^arity_bits coefficients combined with powers of beta.
+static int fri_fold(qpzk_fri* F, u64 b0, u64 b1) {
+  qpzk_ctx* c = F->c;
+  const CommonHost& cm = F->q->common;
+  if (F->round >= cm.arities.size() || F->trees.size() != F->round + 1) return fail(QPZK_ERR_BAD_ARG, "FRI fold out of order");
+  const u64 ab = cm.arities[F->round];
+  u64* dst = F->flip ? F->fold_b : F->fold_a;
+  F->flip = !F->flip;
+  u64 n_out = F->cur_n >> ab;
+  k_fri_fold<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(F->coeffs_cur, F->cur_n, (u32)ab, gl2{b0, b1}, dst);
+  c->launches++;
+  CU(cudaGetLastError());
+  F->coeffs_cur = dst;
+  F->cur_n = n_out;
+  F->cur_k -= (u32)ab;
+  for (u64 e = 0; e < ab; e++) F->shift = glh::mul(F->shift, F->shift);
+  F->round++;
+  return QPZK_OK;
+}
+
+// The polynomial left after the last fold, as interleaved extension coefficients [len][2].
+static int fri_final_poly(qpzk_fri* F, std::vector<u64>* out) {
+  qpzk_ctx* c = F->c;
+  if (F->round != F->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
+  const u64 m = F->cur_n;
+  std::vector<u64> soa(2 * m);
+  out->resize(2 * m);
+  CU(cudaMemcpyAsync(soa.data(), F->coeffs_cur, m * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(soa.data() + m, F->coeffs_cur + m, m * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(ctx_wait(c));
+  for (u64 i = 0; i < m; i++) {
+    (*out)[2 * i] = soa[i];
+    (*out)[2 * i + 1] = soa[m + i];
+  }
+  return QPZK_OK;
+}
+
+// fri_prover_query_rounds for nq indices at once. init_open[o] = nq x (salted row | path), step_open[s] =
+// nq x (2^arity ext evaluations | path).
+static int fri_queries(qpzk_fri* F, const u64* xidx, u32 nq, std::vector<std::vector<u64>>* init_open,
+                       std::vector<std::vector<u64>>* step_open) {
+  qpzk_ctx* c = F->c;
+  const CircuitDesc& d = F->q->desc;
+  const u32 h = (u32)F->q->common.cap_height, lb = d.degree_bits + d.rate_bits;
+  const u64 N = 1ull << lb;
+  const u32 L0 = lb - h;
+  DevBuf xdev(c);
+  QP(xdev.alloc((size_t)nq * 8));
+  CU(cudaMemcpyAsync(xdev.p, xidx, (size_t)nq * 8, cudaMemcpyHostToDevice, c->stream));
+  init_open->assign(4, {});
+  step_open->assign(F->trees.size(), {});
+  std::vector<std::unique_ptr<DevBuf>> keep;
+  for (int o = 0; o < 4; o++) {
+    u32 width = F->oracles[o]->width();
+    size_t per = width + 4ull * L0;
+    keep.emplace_back(new DevBuf(c));
+    QP(keep.back()->alloc(per * nq * 8));
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(F->oracles[o]->lde, 1, N, width, F->oracles[o]->levels, lb, h, xdev.p, 0,
+                                                 keep.back()->p);
+    c->launches++;
+    (*init_open)[o].resize(per * nq);
+    CU(cudaMemcpyAsync((*init_open)[o].data(), keep.back()->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  u32 sh = 0;
+  for (size_t s = 0; s < F->trees.size(); s++) {
+    const FriTree& t = F->trees[s];
+    sh += t.arity_bits;
+    u32 width = 2u << t.arity_bits, L = t.log_n - h;
+    size_t per = width + 4ull * L;
+    keep.emplace_back(new DevBuf(c));
+    QP(keep.back()->alloc(per * nq * 8));
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(t.leaves, width, 1, width, t.levels, t.log_n, h, xdev.p, sh,
+                                                 keep.back()->p);
+    c->launches++;
+    (*step_open)[s].resize(per * nq);
+    CU(cudaMemcpyAsync((*step_open)[s].data(), keep.back()->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaGetLastError());
+  CU(ctx_wait(c));
+  return QPZK_OK;
+}
+
 // ---- H8: Z and partial products on the subgroup: zs_vals [nch*(1+npp)][n] = Z_0..Z_{nch-1}, then the
 // partial products of each challenge (all_wires_permutation_partial_products + the running product) ----
 static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, const Challenges& chal, DevBuf* zs_vals) {
@@ -672,41 +876,12 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 
   // ---- (9) FRI: batch combine ----
   tic();
-  std::vector<u64> apow((size_t)total_polys * 2);
-  {
-    u64 a = 1, b = 0;
-    for (u32 j = 0; j < total_polys; j++) {
-      apow[2 * j] = a;
-      apow[2 * j + 1] = b;
-      u64 na = glh::add(glh::mul(a, alpha[0]), glh::mul(7, glh::mul(b, alpha[1])));
-      u64 nb = glh::add(glh::mul(a, alpha[1]), glh::mul(b, alpha[0]));
-      a = na;
-      b = nb;
-    }
-  }
-  DevBuf apow_dev(c), comp0(c), comp1(c), q0(c), q1(c), fpoly(c);
-  QP(apow_dev.alloc(apow.size() * 8));
-  CU(cudaMemcpyAsync(apow_dev.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  QP(comp0.alloc(n * 16)); QP(comp1.alloc(n * 16)); QP(q0.alloc(n * 16)); QP(q1.alloc(n * 16)); QP(fpoly.alloc(n * 16));
-  PolyList pl0;
-  memset(&pl0, 0, sizeof pl0);
-  pl0.noracles = 4;
-  for (int o = 0; o < 4; o++) { pl0.base[o] = oracles[o]->coeffs; pl0.count[o] = oracles[o]->ncols; }
-  PolyList pl1;
-  memset(&pl1, 0, sizeof pl1);
-  pl1.noracles = 1; pl1.base[0] = zs_b->coeffs; pl1.count[0] = nch;
-  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl0, n, apow_dev.p, comp0.p);
-  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl1, n, apow_dev.p, comp1.p);
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp0.p, q0.p, n, gl2{zeta[0], zeta[1]});
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp1.p, q1.p, n, gl2{zeta_next[0], zeta_next[1]});
-  // final = q0 * alpha^(len batch 1) + q1
-  gl2 shift_s = gl2{apow[2 * nch], apow[2 * nch + 1]};
-  k_ext_axpy<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(q0.p, q1.p, shift_s, n, fpoly.p);
-  c->launches += 5;
-  CU(cudaGetLastError());
+  qpzk_fri* F = nullptr;
+  QP(fri_begin(q, oracles, zeta, alpha, &F));
+  std::unique_ptr<qpzk_fri> fri_guard(F);
   if (want_trace) {
     std::vector<u64> soa(2 * n);
-    CU(cudaMemcpyAsync(soa.data(), fpoly.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(soa.data(), F->fpoly, n * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(ctx_wait(c));
     q->tr_final_poly.resize(2 * n);
     for (u64 m = 0; m < n; m++) {
@@ -718,73 +893,20 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 
   // ---- (9) FRI: commit phase ----
   tic();
-  struct FriTree {
-    u64* leaves = nullptr;  // AoS [nleaves][2*arity]
-    u64* levels = nullptr;
-    u32 log_n = 0, arity_bits = 0;
-  };
-  std::vector<FriTree> trees;
-  auto free_trees = [&]() {
-    for (auto& t : trees) {
-      dev_free(c, t.leaves);
-      dev_free(c, t.levels);
-    }
-  };
   std::vector<std::vector<u64>> fri_caps;
   std::vector<u64> fri_betas;
-  u64 cur_n = n;
-  u32 cur_k = k;
-  u64 shift = GL_GEN;
-  u64* coeffs_cur = fpoly.p;  // SoA [2][cur_n]
-  DevBuf fold_a(c), fold_b(c), vals(c);
-  QP(fold_a.alloc(n * 16 / 2 + 64));
-  QP(fold_b.alloc(n * 16 / 2 + 64));
-  QP(vals.alloc((size_t)2 * N * 8));
-  bool flip = false;
-  for (u64 ab : cm.arities) {
-    const u64 NV = cur_n << r;  // values in this round
-    int rc2 = launch_lde_shift(c, coeffs_cur, cur_n, vals.p, NV, 2, (int)cur_k, (int)r, shift);
-    if (rc2 != QPZK_OK) { free_trees(); return rc2; }
-    FriTree t;
-    t.arity_bits = (u32)ab;
-    t.log_n = cur_k + r - (u32)ab;
-    if (h > t.log_n) { free_trees(); return fail(QPZK_ERR_UNSUPPORTED, "FRI tree smaller than the cap"); }
-    if (dev_alloc(c, NV * 16, &t.leaves) != QPZK_OK || dev_alloc(c, (2ull << t.log_n) * 32, &t.levels) != QPZK_OK) {
-      dev_free(c, t.leaves);
-      free_trees();
-      return QPZK_ERR_OOM;
-    }
-    k_ext_interleave<<<(unsigned)((NV + 255) / 256), 256, 0, c->stream>>>(vals.p, NV, t.leaves);
-    c->launches++;
-    trees.push_back(t);
-    rc2 = build_tree(c, t.leaves, 2ull << ab, 1, 2u << ab, t.log_n, h, t.levels, nullptr);
-    if (rc2 != QPZK_OK) { free_trees(); return rc2; }
+  for (size_t round = 0; round < cm.arities.size(); round++) {
     std::vector<u64> fc(4ull << h);
-    cudaMemcpyAsync(fc.data(), cap_ptr(t.levels, t.log_n, h), fc.size() * 8, cudaMemcpyDeviceToHost, c->stream);
-    ctx_wait(c);
+    QP(fri_commit_round(F, fc.data()));
     ch.observe_n(fc.data(), fc.size());
     fri_caps.push_back(fc);
     u64 b0 = ch.get(), b1 = ch.get();
     fri_betas.push_back(b0);
     fri_betas.push_back(b1);
-    u64* dst = flip ? fold_b.p : fold_a.p;
-    flip = !flip;
-    u64 n_out = cur_n >> ab;
-    k_fri_fold<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(coeffs_cur, cur_n, (u32)ab, gl2{b0, b1}, dst);
-    c->launches++;
-    coeffs_cur = dst;
-    cur_n = n_out;
-    cur_k -= (u32)ab;
-    for (u64 e = 0; e < ab; e++) shift = glh::mul(shift, shift);
+    QP(fri_fold(F, b0, b1));
   }
-  std::vector<u64> final_soa(2 * cur_n), final_poly(2 * cur_n);
-  cudaMemcpyAsync(final_soa.data(), coeffs_cur, cur_n * 8, cudaMemcpyDeviceToHost, c->stream);
-  cudaMemcpyAsync(final_soa.data() + cur_n, coeffs_cur + cur_n, cur_n * 8, cudaMemcpyDeviceToHost, c->stream);
-  ctx_wait(c);
-  for (u64 m = 0; m < cur_n; m++) {
-    final_poly[2 * m] = final_soa[m];
-    final_poly[2 * m + 1] = final_soa[cur_n + m];
-  }
+  std::vector<u64> final_poly;
+  QP(fri_final_poly(F, &final_poly));
   ch.observe_n(final_poly.data(), final_poly.size());
   toc();  // stage 5: FRI commit phase
 
@@ -796,12 +918,11 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     memcpy(ps.s, ch.state, sizeof ps.s);
     u32 pos = (u32)ch.in.size();
     for (u32 i = 0; i < pos; i++) ps.s[i] = ch.in[i];
-    int prc = grind_pow(c, ps, pos, cm.pow_bits, &pow_witness);
-    if (prc != QPZK_OK) { free_trees(); return prc; }
+    QP(grind_pow(c, ps, pos, cm.pow_bits, &pow_witness));
   }
   ch.observe(pow_witness);
   u64 pow_resp = ch.get();
-  if ((pow_resp >> (64 - cm.pow_bits)) != 0 && cm.pow_bits) { free_trees(); return fail(QPZK_ERR_CUDA, "pow response mismatch"); }
+  if ((pow_resp >> (64 - cm.pow_bits)) != 0 && cm.pow_bits) return fail(QPZK_ERR_CUDA, "pow response mismatch");
   toc();  // stage 6: PoW
 
   // ---- (9) query rounds ----
@@ -809,41 +930,9 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   const u32 nq = (u32)cm.num_queries;
   std::vector<u64> xidx(nq);
   for (u32 i = 0; i < nq; i++) xidx[i] = ch.get() & (N - 1);
-  DevBuf xdev(c);
-  if (xdev.alloc(nq * 8) != QPZK_OK) { free_trees(); return QPZK_ERR_OOM; }
-  cudaMemcpyAsync(xdev.p, xidx.data(), nq * 8, cudaMemcpyHostToDevice, c->stream);
-  std::vector<std::vector<u64>> init_open(4), step_open(trees.size());
+  std::vector<std::vector<u64>> init_open, step_open;
   const u32 L0 = lb - h;
-  std::vector<DevBuf*> keep;
-  for (int o = 0; o < 4; o++) {
-    u32 width = oracles[o]->width();
-    size_t per = width + 4ull * L0;
-    DevBuf* ob = new DevBuf(c);
-    keep.push_back(ob);
-    if (ob->alloc(per * nq * 8) != QPZK_OK) { for (auto* kb : keep) delete kb; free_trees(); return QPZK_ERR_OOM; }
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(oracles[o]->lde, 1, N, width, oracles[o]->levels, lb, h, xdev.p, 0, ob->p);
-    c->launches++;
-    init_open[o].resize(per * nq);
-    cudaMemcpyAsync(init_open[o].data(), ob->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream);
-  }
-  u32 sh = 0;
-  for (size_t s = 0; s < trees.size(); s++) {
-    sh += trees[s].arity_bits;
-    u32 width = 2u << trees[s].arity_bits, L = trees[s].log_n - h;
-    size_t per = width + 4ull * L;
-    DevBuf* ob = new DevBuf(c);
-    keep.push_back(ob);
-    if (ob->alloc(per * nq * 8) != QPZK_OK) { for (auto* kb : keep) delete kb; free_trees(); return QPZK_ERR_OOM; }
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(trees[s].leaves, width, 1, width, trees[s].levels, trees[s].log_n, h,
-                                                 xdev.p, sh, ob->p);
-    c->launches++;
-    step_open[s].resize(per * nq);
-    cudaMemcpyAsync(step_open[s].data(), ob->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream);
-  }
-  cudaError_t e = ctx_wait(c);
-  for (auto* kb : keep) delete kb;
-  free_trees();
-  if (e != cudaSuccess) return fail(QPZK_ERR_CUDA, cudaGetErrorString(e));
+  QP(fri_queries(F, xidx.data(), nq, &init_open, &step_open));
   toc();  // stage 7: queries
 
   // ---- (10) ProofWithPublicInputs::to_bytes ----
@@ -956,6 +1045,68 @@ int qpzk_quotient(qpzk_circuit* q, const qpzk_batch* wires_batch, const qpzk_bat
   CU(ctx_wait(c));
   return QPZK_OK;
 }
+
+int qpzk_fri_begin(qpzk_circuit* q, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch,
+                   const qpzk_batch* quotient_batch, const uint64_t* zeta, const uint64_t* alpha, qpzk_fri** out) {
+  if (!q || !wires_batch || !zs_batch || !quotient_batch || !zeta || !alpha || !out)
+    return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_ctx* c = q->ctx;
+  const CircuitDesc& d = q->desc;
+  qpzk_batch* oracles[4] = {q->cs_batch, const_cast<qpzk_batch*>(wires_batch), const_cast<qpzk_batch*>(zs_batch),
+                            const_cast<qpzk_batch*>(quotient_batch)};
+  const u32 want[4] = {d.num_constants + d.num_routed, d.num_wires, d.num_challenges * (1 + d.num_partial_products),
+                       d.num_challenges * d.qdf};
+  for (int o = 0; o < 4; o++)
+    if (oracles[o]->ctx != c || oracles[o]->degree_bits != d.degree_bits || oracles[o]->rate_bits != d.rate_bits ||
+        oracles[o]->ncols != want[o] || oracles[o]->cap_height != q->common.cap_height)
+      return fail(QPZK_ERR_BAD_ARG, "oracle shape does not match the circuit");
+  CU(cudaSetDevice(c->device));
+  return fri_begin(q, oracles, zeta, alpha, out);
+}
+uint32_t qpzk_fri_num_rounds(const qpzk_fri* f) { return f ? (uint32_t)f->q->common.arities.size() : 0; }
+int qpzk_fri_commit_round(qpzk_fri* f, uint64_t* cap_out) {
+  if (!f || !cap_out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(f->c->device));
+  return fri_commit_round(f, cap_out);
+}
+int qpzk_fri_fold(qpzk_fri* f, const uint64_t* beta) {
+  if (!f || !beta) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(f->c->device));
+  return fri_fold(f, beta[0], beta[1]);
+}
+int qpzk_fri_final_poly(qpzk_fri* f, uint64_t* out, size_t cap_words, size_t* len_words) {
+  if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(f->c->device));
+  std::vector<u64> v;
+  QP(fri_final_poly(f, &v));
+  *len_words = v.size();
+  if (out) {
+    if (v.size() > cap_words) return fail(QPZK_ERR_BAD_ARG, "buffer too small");
+    memcpy(out, v.data(), v.size() * 8);
+  }
+  return QPZK_OK;
+}
+int qpzk_fri_query(qpzk_fri* f, uint64_t x_index, uint64_t* out, size_t cap_words, size_t* len_words) {
+  if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  const CircuitDesc& d = f->q->desc;
+  if (x_index >> (d.degree_bits + d.rate_bits)) return fail(QPZK_ERR_BAD_ARG, "x_index out of range");
+  if (f->round != f->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
+  CU(cudaSetDevice(f->c->device));
+  std::vector<std::vector<u64>> init_open, step_open;
+  QP(fri_queries(f, &x_index, 1, &init_open, &step_open));
+  size_t total = 0;
+  for (auto& v : init_open) total += v.size();
+  for (auto& v : step_open) total += v.size();
+  *len_words = total;
+  if (out) {
+    if (total > cap_words) return fail(QPZK_ERR_BAD_ARG, "buffer too small");
+    size_t off = 0;
+    for (auto& v : init_open) { memcpy(out + off, v.data(), v.size() * 8); off += v.size(); }
+    for (auto& v : step_open) { memcpy(out + off, v.data(), v.size() * 8); off += v.size(); }
+  }
+  return QPZK_OK;
+}
+void qpzk_fri_free(qpzk_fri* f) { delete f; }
 
 int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, const uint64_t* public_inputs, uint32_t num_public_inputs,
                const uint64_t* salts_wires, const uint64_t* salts_zs, const uint64_t* salts_quotient, uint32_t flags,

@@ -94,6 +94,13 @@ def load_library():
                            ctypes.POINTER(ctypes.c_size_t)]),
         "qpzk_zs_partial_products": (i, [_vp, _vp, _u64p, _u64p, _u64p]),
         "qpzk_quotient": (i, [_vp, _vp, _vp, _u64p, _u64p, _u64p, _u64p, _u64p]),
+        "qpzk_fri_begin": (i, [_vp, _vp, _vp, _vp, _u64p, _u64p, ctypes.POINTER(_vp)]),
+        "qpzk_fri_num_rounds": (u32, [_vp]),
+        "qpzk_fri_commit_round": (i, [_vp, _u64p]),
+        "qpzk_fri_fold": (i, [_vp, _u64p]),
+        "qpzk_fri_final_poly": (i, [_vp, _u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_fri_query": (i, [_vp, u64, _u64p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_fri_free": (None, [_vp]),
         "qpzk_prove_trace": (ctypes.c_size_t, [_vp, i, _u64p]),
         "qpzk_prove_stage_ms": (i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     }
@@ -403,6 +410,51 @@ class PolynomialBatch:
     def free(self):
         if getattr(self, "_h", None):
             load_library().qpzk_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Fri:
+    """The FRI prover driven step by step (the caller owns the transcript): see include/qpzk.h."""
+
+    def __init__(self, circuit, wires_batch, zs_batch, quotient_batch, zeta, alpha, cap_height=4):
+        z, a = _arr(zeta), _arr(alpha)
+        h = _vp()
+        _check(load_library().qpzk_fri_begin(circuit._h, wires_batch._h, zs_batch._h, quotient_batch._h, _ptr(z), _ptr(a),
+                                             ctypes.byref(h)))
+        self._h, self.cap_height = h, cap_height
+        self.num_rounds = int(load_library().qpzk_fri_num_rounds(h))
+
+    def commit_round(self):
+        cap = np.zeros((1 << self.cap_height, 4), np.uint64)
+        _check(load_library().qpzk_fri_commit_round(self._h, _ptr(cap)))
+        return cap
+
+    def fold(self, beta):
+        b = _arr(beta)
+        _check(load_library().qpzk_fri_fold(self._h, _ptr(b)))
+
+    def _sized(self, fn, *args):
+        ln = ctypes.c_size_t(0)
+        _check(fn(self._h, *args, None, 0, ctypes.byref(ln)))
+        out = np.zeros(max(ln.value, 1), np.uint64)
+        _check(fn(self._h, *args, _ptr(out), out.size, ctypes.byref(ln)))
+        return out[:ln.value]
+
+    def final_poly(self):
+        return self._sized(load_library().qpzk_fri_final_poly).reshape(-1, 2)
+
+    def query(self, x_index):
+        return self._sized(load_library().qpzk_fri_query, int(x_index))
+
+    def free(self):
+        if getattr(self, "_h", None):
+            load_library().qpzk_fri_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -22,6 +22,7 @@ pub const QPZK_CTX_BLOCKING_SYNC: u32 = 1;
 #[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_tree { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_circuit { _p: [u8; 0] }
+#[repr(C)] pub struct qpzk_fri { _p: [u8; 0] }
 
 extern "C" {
     pub fn qpzk_ctx_create(device: c_int, flags: u32, out_: *mut *mut qpzk_ctx) -> c_int;
@@ -70,6 +71,13 @@ extern "C" {
     pub fn qpzk_prove(c: *mut qpzk_circuit, wires: *const u64, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn qpzk_zs_partial_products(c: *mut qpzk_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out_: *mut u64) -> c_int;
     pub fn qpzk_quotient(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, pi_hash: *const u64, betas: *const u64, gammas: *const u64, alphas: *const u64, out_chunks: *mut u64) -> c_int;
+    pub fn qpzk_fri_begin(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, quotient_batch: *const qpzk_batch, zeta: *const u64, alpha: *const u64, out_: *mut *mut qpzk_fri) -> c_int;
+    pub fn qpzk_fri_num_rounds(f: *const qpzk_fri) -> u32;
+    pub fn qpzk_fri_commit_round(f: *mut qpzk_fri, cap_out: *mut u64) -> c_int;
+    pub fn qpzk_fri_fold(f: *mut qpzk_fri, beta: *const u64) -> c_int;
+    pub fn qpzk_fri_final_poly(f: *mut qpzk_fri, out_: *mut u64, cap_words: usize, len_words: *mut usize) -> c_int;
+    pub fn qpzk_fri_query(f: *mut qpzk_fri, x_index: u64, out_: *mut u64, cap_words: usize, len_words: *mut usize) -> c_int;
+    pub fn qpzk_fri_free(f: *mut qpzk_fri);
     pub fn qpzk_prove_trace(c: *const qpzk_circuit, which: c_int, out_: *mut u64) -> usize;
     pub fn qpzk_prove_stage_ms(c: *const qpzk_circuit, out16: *mut f32) -> c_int;
     pub fn qpzk_measure_imad_peak(ctx: *mut qpzk_ctx, kind: c_int, out_ops_per_s: *mut f64) -> c_int;

@@ -124,3 +124,65 @@ def test_stage_hooks_match_the_oracle_trace(ctx, k, zk):
     for x in (wb, zb, qb):
         x.free()
     gc.free()
+
+
+@pytest.mark.parametrize("k,zk", [(9, False), (13, True)])
+def test_fri_object_reproduces_the_oracle_proof(ctx, k, zk):
+    """The FRI prover driven step by step through the C ABI (begin / commit_round / fold / final_poly / pow /
+    query) with the oracle transcript's challenges: commit-phase caps, final polynomial, proof-of-work
+    witness and every query opening must be the ones inside the oracle prover's proof bytes."""
+    import qpzk
+    from helpers import parse_proof
+    circ = minibuilder.build(k, zk=zk, seed=70 + k)
+    n, salt = 1 << k, 4 if zk else 0
+    oc = orc.Circuit(circ["common"], circ["digest"], circ["constants_sigmas"], threads=8)
+    proof = oc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
+    tr = oc.trace(rounds=len(circ["arities"]))
+    rc, chal = orc.verify(circ["common"], oc.verifier_only_bytes(), proof)
+    assert rc == 0
+    steps = []
+    lg = k + 3
+    for a in circ["arities"]:
+        lg -= a
+        steps.append(lg - 4)
+    final_len = 1 << (k - sum(circ["arities"]))
+    pr = parse_proof(proof, rows=[84, 135 + salt, 20 + salt, 16 + salt], path_len=k + 3 - 4, fri_steps=steps,
+                     final_len=final_len)
+    salts = circ["salts"] or [None, None, None]
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    wb = qpzk.PolynomialBatch.from_values(ctx, circ["wires"], 3, 4, salts=salts[0])
+    zb = qpzk.PolynomialBatch.from_values(ctx, tr["zs_pp"], 3, 4, salts=salts[1])
+    qb = qpzk.PolynomialBatch.from_coeffs(ctx, tr["quotient_chunks"], 3, 4, salts=salts[2])
+    assert np.array_equal(wb.cap, pr["caps"][0]) and np.array_equal(zb.cap, pr["caps"][1])
+    assert np.array_equal(qb.cap, pr["caps"][2])
+    f = qpzk.Fri(gc, wb, zb, qb, tr["zeta"], tr["fri_alpha"])
+    assert f.num_rounds == len(circ["arities"])
+    betas = tr["fri_betas"].reshape(-1, 2)
+    for rnd in range(f.num_rounds):
+        assert np.array_equal(f.commit_round(), pr["fri_caps"][rnd])
+        f.fold(betas[rnd])
+    assert np.array_equal(f.final_poly(), pr["final_poly"])
+    # every query round of the proof, opened one index at a time
+    widths = [84, 135 + salt, 20 + salt, 16 + salt]
+    L0 = k + 3 - 4
+    for qi, x in enumerate(int(v) for v in chal["query_indices"][:28]):
+        out = f.query(x)
+        off = 0
+        for o in range(4):
+            assert np.array_equal(out[off:off + widths[o]], pr["queries"][qi]["rows"][o])
+            off += widths[o]
+            assert np.array_equal(out[off:off + 4 * L0].reshape(L0, 4), pr["queries"][qi]["paths"][o])
+            off += 4 * L0
+        for s_, st in enumerate(steps):
+            assert np.array_equal(out[off:off + 32], pr["queries"][qi]["evals"][s_])
+            off += 32
+            assert np.array_equal(out[off:off + 4 * st].reshape(st, 4), pr["queries"][qi]["fri_paths"][s_])
+            off += 4 * st
+        assert off == out.size
+    # calling the steps out of order is refused
+    with pytest.raises(qpzk.QpzkError):
+        f.fold(betas[0])
+    f.free()
+    for x in (wb, zb, qb):
+        x.free()
+    gc.free()
