@@ -85,3 +85,21 @@ def test_dummy_proof_paths_on_gpu(ctx, ref_fixture, name, first):
         indices.append(hits[0])
     assert indices[0] == first
     _check_proof(ctx, pr, [None] + pr["caps"], indices, 2)
+
+
+def test_storage_proof_hash_chain_on_gpu(ctx):
+    """P3 of SURVEY 8(c) through the CUDA sponge: the 7 trie nodes of the reference's storage proof
+    (/root/reference/wormhole/tests/test-helpers/src/lib.rs:68-80), each zero-padded to 188 felts (24
+    permutations), hashed in one GPU batch; node i+1's digest must appear inside node i, node 0 must hash to
+    DEFAULT_ROOT_HASH (what /root/reference/wormhole/circuit/src/storage_proof/mod.rs:169-243 constrains)."""
+    from test_oracle_poseidon import (ROOT_HASH, STORAGE_INDICES, STORAGE_PROOF, bytes4_to_felts, digest_to_felts)
+    rows = []
+    for node_hex in STORAGE_PROOF:
+        f = bytes4_to_felts(bytes.fromhex(node_hex))
+        rows.append(f + [0] * (188 - len(f)))
+    digests = ctx.hash_no_pad(np.array(rows, np.uint64))
+    prev = digest_to_felts(bytes.fromhex(ROOT_HASH))
+    for padded, idx, h in zip(rows, STORAGE_INDICES, digests):
+        assert [int(x) for x in h] == prev
+        j = idx // 8
+        prev = [padded[j + 2 * k] + (padded[j + 2 * k + 1] << 32) for k in range(4)]
