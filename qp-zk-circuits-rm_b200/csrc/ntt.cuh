@@ -54,6 +54,17 @@ __global__ void k_build_coset_pm(u64* pm, u64 shift0, u64 wN, int k, int r) {
   pm[i] = gl_canon(gl_pow(shift, m));
 }
 
+// Twiddle matrix M[k1][j] = root^(j*k1), k1 < 2^a, j < 2^(k-a), stored at (k1 << (k-a)) + j: the factors
+// between the first 2^a-point stage of a 2^k-point DIF and the rest (pass A's inter-pass twiddle with
+// a = log n1; the first radix-16 stage of a long single-CTA transform with a = 4). One coalesced load per
+// element instead of two table lookups and a multiplication.
+__global__ void k_build_tw_matrix(u64* out, RootTab tab, int k, int a) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((u64)1 << k)) return;
+  u64 k1 = i >> (k - a), j = i & (((u64)1 << (k - a)) - 1);
+  out[i] = gl_canon(root_pow(tab, j * k1));
+}
+
 // ---- register-resident radix-16 butterflies -------------------------------------------------------
 // plonky2's power-of-two roots of unity are powers of TWO in Goldilocks up to order 64:
 // POWER_OF_TWO_GENERATOR^(2^26) = 8, so w_16 = 2^12, w_8 = 2^24, w_4 = 2^48 (2^96 = -1, 2^192 = 1).
@@ -128,13 +139,25 @@ struct TileSt {
 struct NoPre {
   GL_DEV void operator()() const {}
 };
+// Inter-stage twiddle w_m^(e_lo * k1) of a stage over blocks of length m inside a 2^lg-point transform:
+//  TwTable  : from a table tw[e] = w_L^e (shared memory), index (e_lo * k1) << sh, sh = log(L / m)
+//  TwMatrix : from a global matrix t[(k1 << q_log) + e_lo] (k_build_tw_matrix), consecutive threads read
+//             consecutive words
+struct TwTable {
+  const u64* tw; int sh;
+  GL_DEV u64 operator()(u32 e_lo, u32 k1) const { return tw[(e_lo * k1) << sh]; }
+};
+struct TwMatrix {
+  const u64* t; u32 q_log;
+  GL_DEV u64 operator()(u32 e_lo, u32 k1) const { return t[((u64)k1 << q_log) + e_lo]; }
+};
 
 // One stage: 2^LOGR-point DFTs over the elements base + i*q of every block of length m = 2^m_log,
-// then the inter-stage twiddle w_m^(e_lo * k1); output k1 goes to sub-block rev(k1) (DIF order).
-// tw[e] = w_len^e for e < len. `pre` runs after the first item's loads have been issued and before any
-// twiddle is read (a first stage uses it to fill the twiddle table and __syncthreads()).
-template <int LOGR, bool INTERLEAVED, bool INV, class LD, class ST, class PRE>
-GL_DEV void dif_stage(const u64* tw, int lg, int m_log, u32 cnt_log, LD ld, ST st, PRE pre) {
+// then the inter-stage twiddle w_m^(e_lo * k1) = tw(e_lo, k1); output k1 goes to sub-block rev(k1) (DIF
+// order). `pre` runs after the first item's loads have been issued and before any shared-memory twiddle
+// is read (a first stage uses it to fill the twiddle table and __syncthreads()).
+template <int LOGR, bool INTERLEAVED, bool INV, class TW, class LD, class ST, class PRE>
+GL_DEV void dif_stage(TW tw, int lg, int m_log, u32 cnt_log, LD ld, ST st, PRE pre) {
   constexpr int R = 1 << LOGR;
   const u32 q_log = m_log - LOGR, q = 1u << q_log;
   const u32 per_c_log = lg - LOGR;
@@ -165,7 +188,7 @@ GL_DEV void dif_stage(const u64* tw, int lg, int m_log, u32 cnt_log, LD ld, ST s
     for (int p = 0; p < R; p++) {
       const u32 k1 = __brev((u32)p) >> (32 - LOGR);
       u64 v = x[p];
-      if (p != 0 && q > 1) v = gl_mul(v, tw[(e_lo * k1) << (lg - m_log)]);
+      if (p != 0 && q > 1) v = gl_mul(v, tw(e_lo, k1));
       st(c, base + ((u32)p << q_log), v);
     }
     id += blockDim.x;
@@ -178,8 +201,13 @@ GL_DEV void dif_stage(const u64* tw, int lg, int m_log, u32 cnt_log, LD ld, ST s
 // Full tile DIF of `cnt` transforms of length 2^lg: first stage reads through `ld0` (after which
 // `pre` runs once), stages in between use the shared-memory tile, the last stage writes through `stN`.
 // Afterwards position p of every transform holds X[rev_lg(p)].
+// Twiddles: tw1 == nullptr: tw[e] = w_len^e, e < len, in shared memory serves every stage.
+//           tw1 != nullptr (lg > 4): the first radix-16 stage reads the global matrix tw1[16][len/16] and
+//           tw[e] = w_(len/16)^e, e < len/16, serves the rest - a 2^14-point tile then needs 8 KB of
+//           twiddles next to its 136 KB of data instead of another 128 KB.
 template <bool INTERLEAVED, bool INV, class LD0, class STN, class PRE>
-GL_DEV void tile_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch, LD0 ld0, STN stN, PRE pre) {
+GL_DEV void tile_dif(u64* sm, const u64* tw, const u64* tw1, int lg, u32 cnt_log, u32 pitch, LD0 ld0, STN stN,
+                     PRE pre) {
   TileLd<INTERLEAVED> tl{sm, cnt_log, pitch};
   TileSt<INTERLEAVED> ts{sm, cnt_log, pitch};
   if (lg == 0) {  // nothing to transform: copy through
@@ -188,8 +216,9 @@ GL_DEV void tile_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch, LD0
     __syncthreads();
     return;
   }
-  const int first = lg >= 4 ? 4 : lg;
-#define QPZK_STAGE(LOGR, LD, ST, PRE_) dif_stage<LOGR, INTERLEAVED, INV>(tw, lg, m_log, cnt_log, LD, ST, PRE_)
+  const int sub = tw1 ? 4 : 0;
+#define QPZK_STAGE(LOGR, LD, ST, PRE_) \
+  dif_stage<LOGR, INTERLEAVED, INV>(TwTable{tw, lg - m_log - sub}, lg, m_log, cnt_log, LD, ST, PRE_)
   int m_log = lg;
   if (lg <= 4) {  // single stage: global in, `stN` out
     if (lg == 4) QPZK_STAGE(4, ld0, stN, pre);
@@ -198,8 +227,11 @@ GL_DEV void tile_dif(u64* sm, const u64* tw, int lg, u32 cnt_log, u32 pitch, LD0
     if (lg == 1) QPZK_STAGE(1, ld0, stN, pre);
     return;
   }
-  QPZK_STAGE(4, ld0, ts, pre);
-  m_log -= first;
+  if (tw1)
+    dif_stage<4, INTERLEAVED, INV>(TwMatrix{tw1, (u32)(lg - 4)}, lg, m_log, cnt_log, ld0, ts, pre);
+  else
+    QPZK_STAGE(4, ld0, ts, pre);
+  m_log -= 4;
   while (m_log > 4) {
     QPZK_STAGE(4, tl, ts, NoPre());
     m_log -= 4;
@@ -220,11 +252,15 @@ struct TwFill {
   }
 };
 
-// ---- single-CTA transform for n <= 2^12 ----
+// ---- single-CTA transform for n <= 2^14 ----
 // grid (ncols, ncosets). src column c at src + c*src_stride (natural order).
 // Output column c, coset t at dst + c*dst_stride + brev(t, r)*n:
 //   NATURAL_OUT = false : DIF order (position = bit-reversed index)  [LDE flavour]
 //   NATURAL_OUT = true  : natural order                              [IFFT flavour]
+// tw1 == nullptr: n <= 2^12, the whole twiddle table sits in shared memory. Otherwise (n = 2^13, 2^14; the
+// wormhole proof sizes) the first stage takes its twiddles from the global matrix tw1[16][n/16] and the
+// tile (68 / 136 KB) plus n/16 twiddles fill the SM's shared memory: one read of the coefficients, one
+// write of the evaluations, nothing in between touches HBM.
 struct SmallLd {  // natural-order input column, optional coset pre-multiplier
   const u64* s; const u64* pmt;
   GL_DEV u64 operator()(u32, u32 j) const {
@@ -233,10 +269,11 @@ struct SmallLd {  // natural-order input column, optional coset pre-multiplier
     return v;
   }
 };
-template <bool NATURAL_OUT>
-__global__ void __launch_bounds__(256)
+template <bool NATURAL_OUT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
-            const u64* __restrict__ pm, RootTab tab, int k, int r, u64 scale, u32 blk0) {
+            const u64* __restrict__ pm, RootTab tab, const u64* __restrict__ tw1, int k, int r, u64 scale,
+            u32 blk0) {
   extern __shared__ u64 smem[];
   const u32 n = 1u << k;
   const u32 pitch = tile_pitch(n);
@@ -246,7 +283,8 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
   const u32 col = blockIdx.x, blk = blk0 + blockIdx.y, t = brev(blk, r);
   SmallLd ld{src + (u64)col * src_stride, pm ? pm + ((u64)t << k) : nullptr};
   // the natural-order flavour is the inverse transform
-  tile_dif<false, NATURAL_OUT>(x, tw, k, 0, pitch, ld, TileSt<false>{x, 0, pitch}, TwFill{tw, tab, n, 0});
+  tile_dif<false, NATURAL_OUT>(x, tw, tw1, k, 0, pitch, ld, TileSt<false>{x, 0, pitch},
+                               TwFill{tw, tab, tw1 ? n >> 4 : n, tw1 ? 4 : 0});
   u64* d = dst + (u64)col * dst_stride + ((u64)blk << k);
   for (u32 q = threadIdx.x; q < n; q += blockDim.x) {
     u64 v = x[tile_pos<false>(0, NATURAL_OUT ? brev(q, k) : q, 0, pitch)];
@@ -270,17 +308,18 @@ struct PassALd {  // element j1 of column j2_base + c of the [n1][n2] view, opti
 };
 template <bool ROW_BITREV>
 struct PassASt {  // DIF position p = frequency k1 = rev_a(p): inter-pass twiddle w_n^(j2*k1), row p or k1
-  u64* d; RootTab tab; int a, b; u32 j2_base;
+  u64* d; const u64* twm; int a, b; u32 j2_base;  // twm[k1][j2] = w_n^(j2*k1) (k_build_tw_matrix)
   GL_DEV void operator()(u32 c, u32 p, u64 v) const {
     u32 k1 = brev(p, a), j2 = j2_base + c;
-    v = gl_mul(v, root_pow(tab, (u64)j2 * k1));
+    v = gl_mul(v, twm[((u64)k1 << b) + j2]);
     d[((u64)(ROW_BITREV ? p : k1) << b) + j2] = v;  // non-canonical is fine: pass B canonicalises
   }
 };
 template <bool ROW_BITREV>
 __global__ void __launch_bounds__(256)
 k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
-             const u64* __restrict__ pm, RootTab tab, int k, int a, int r, u32 cols_log, u32 blk0) {
+             const u64* __restrict__ pm, RootTab tab, const u64* __restrict__ twm, int k, int a, int r,
+             u32 cols_log, u32 blk0) {
   const u32 cols = 1u << cols_log;
   extern __shared__ u64 smem[];
   const int b = k - a;
@@ -290,9 +329,9 @@ k_ntt_pass_a(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst,
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z, t = brev(blk, r);
   const u32 j2_base = blockIdx.x * cols;
   PassALd ld{src + (u64)col * src_stride, pm ? pm + ((u64)t << k) : nullptr, b, j2_base};
-  PassASt<ROW_BITREV> st{dst + (u64)col * dst_stride + ((u64)blk << k), tab, a, b, j2_base};
+  PassASt<ROW_BITREV> st{dst + (u64)col * dst_stride + ((u64)blk << k), twm, a, b, j2_base};
   // ROW_BITREV = forward (LDE), otherwise inverse
-  tile_dif<true, !ROW_BITREV>(x, tw, a, cols_log, 0, ld, st, TwFill{tw, tab, n1, b});
+  tile_dif<true, !ROW_BITREV>(x, tw, nullptr, a, cols_log, 0, ld, st, TwFill{tw, tab, n1, b});
 }
 
 // ---- pass B (LDE flavour): n2-point DIF along contiguous rows, in place, DIF output order ----
@@ -313,7 +352,7 @@ k_ntt_pass_b_rows(u64* __restrict__ data, u64 stride, RootTab tab, int k, int a,
   const u32 col = blockIdx.y, blk = blk0 + blockIdx.z;
   u64* d = data + (u64)col * stride + ((u64)blk << k) + (u64)blockIdx.x * rows_per_cta * n2;
   const u32 total = rows_per_cta * n2;
-  tile_dif<false, false>(x, tw, b, rows_log, pitch, RowsLd{d, b}, TileSt<false>{x, rows_log, pitch},
+  tile_dif<false, false>(x, tw, nullptr, b, rows_log, pitch, RowsLd{d, b}, TileSt<false>{x, rows_log, pitch},
                          TwFill{tw, tab, n2, a});
   for (u32 idx = threadIdx.x; idx < total; idx += blockDim.x)
     d[idx] = gl_canon(x[tile_pos<false>(idx >> b, idx & (n2 - 1), 0, pitch)]);
@@ -333,7 +372,7 @@ k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restr
   const u32 col = blockIdx.y;
   const u32 k1_base = blockIdx.x * rc;
   const u64* s = tmp + (u64)col * tmp_stride + ((u64)k1_base << b);
-  tile_dif<false, true>(x, tw, b, rc_log, pitch, RowsLd{s, b}, TileSt<false>{x, rc_log, pitch},
+  tile_dif<false, true>(x, tw, nullptr, b, rc_log, pitch, RowsLd{s, b}, TileSt<false>{x, rc_log, pitch},
                         TwFill{tw, tab, n2, a});
   u64* d = dst + (u64)col * dst_stride;
   for (u32 idx = threadIdx.x; idx < rc * n2; idx += blockDim.x) {

@@ -65,6 +65,7 @@ struct qpzk_ctx {
   std::map<TabKey, std::pair<u64*, u64*>> root_tabs;   // (lo, hi)
   std::map<std::tuple<int, int, u64>, u64*> coset_pm;    // (k, r, shift) -> pm[2^r][2^k]
   std::map<std::pair<u64, int>, std::pair<u64*, u64*>> pow_tabs;  // (base, k) -> two-level base^e table
+  std::map<std::tuple<int, int, bool>, u64*> tw_mats;    // (k, a, inverse) -> twiddle matrix [2^a][2^(k-a)]
   u64* scratch_path = nullptr;                           // small device scratch for openings
 };
 
@@ -150,6 +151,26 @@ static int get_pow_tab(qpzk_ctx* c, u64 base, int k, RootTab* out) {
   return QPZK_OK;
 }
 
+// M[k1][j] = root^(j*k1) (k_build_tw_matrix): the twiddles between the first 2^a-point stage of a
+// 2^k-point transform and the rest.
+static int get_tw_matrix(qpzk_ctx* c, int k, int a, bool inverse, const u64** out) {
+  auto key = std::make_tuple(k, a, inverse);
+  auto it = c->tw_mats.find(key);
+  if (it == c->tw_mats.end()) {
+    RootTab tab;
+    QP(get_root_tab(c, k, inverse, &tab));
+    u64* m;
+    u64 cnt = (u64)1 << k;
+    QP(dev_alloc(c, cnt * sizeof(u64), &m));
+    k_build_tw_matrix<<<(unsigned)((cnt + 255) / 256), 256, 0, c->stream>>>(m, tab, k, a);
+    c->launches++;
+    CU(cudaGetLastError());
+    it = c->tw_mats.emplace(key, m).first;
+  }
+  *out = it->second;
+  return QPZK_OK;
+}
+
 static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
   auto key = std::make_tuple(k, r, shift);
   auto it = c->coset_pm.find(key);
@@ -169,8 +190,34 @@ static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
 
 // Batched n-point transforms. flavour LDE: src natural -> dst DIF order per coset (ncosets = 2^r,
 // coset pre-multipliers applied). flavour IFFT: src natural values -> dst natural coefficients.
-static const int kSmallMaxLog = 12;
+// Up to 2^14 points (every wormhole / voting / aggregation-node proof) one CTA transforms a whole
+// (column, coset) in shared memory; above that, two passes.
+static const int kSmallMaxLog = 14;
+static const int kSmallTableLog = 12;  // up to here the full twiddle table fits next to the tile
+static const int kSmallSmemBytes = 148 * 1024;
 
+// (Tried and dropped: running the two passes of a long transform per group of columns small enough for
+// pass A's output to stay in the 126 MB L2 until pass B overwrites it in place. The kernels are
+// integer-issue-bound, not HBM-bound, so the saved DRAM round trip bought nothing and the extra launch
+// boundaries cost 11 % (48 MB groups) to 47 % (16 MB groups) of the LDE time at 2^16 x 135.)
+
+template <bool NATURAL_OUT>
+static int launch_small(qpzk_ctx* c, const u64* src, u64 src_stride, u64* dst, u64 dst_stride, const u64* pm,
+                        RootTab tab, u32 ncols, u32 ncosets, int k, int r, u64 scale, u32 blk0) {
+  const u64* tw1 = nullptr;
+  if (k > kSmallTableLog) QP(get_tw_matrix(c, k, 4, NATURAL_OUT, &tw1));
+  u32 n = 1u << k;
+  size_t smem = ((size_t)tile_pitch(n) + (tw1 ? n >> 4 : n)) * 8;
+  if (k == 14)  // one CTA per SM: 512 threads keep 16 warps resident
+    k_ntt_small<NATURAL_OUT, 512><<<dim3(ncols, ncosets), 512, smem, c->stream>>>(src, src_stride, dst, dst_stride, pm,
+                                                                                  tab, tw1, k, r, scale, blk0);
+  else
+    k_ntt_small<NATURAL_OUT, 256><<<dim3(ncols, ncosets), 256, smem, c->stream>>>(src, src_stride, dst, dst_stride, pm,
+                                                                                  tab, tw1, k, r, scale, blk0);
+  c->launches++;
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
 
 // blk0 / nblk: which of the 2^r leaf blocks (n bit-reversed leaves each, block b = coset rev_r(b)) to
 // evaluate; the full commit passes (0, 2^r), a multi-GPU shard its own range.
@@ -183,29 +230,25 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
   const u64* pm;
   QP(get_coset_pm(c, k, r, shift, &pm));
   u32 ncosets = nblk;
-  if (k <= kSmallMaxLog) {
-    size_t smem = ((size_t)tile_pitch(1u << k) + ((size_t)1 << k)) * 8;
-    k_ntt_small<false><<<dim3(ncols, ncosets), 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride,
-                                                                       pm, tab, k, r, 1, blk0);
-    c->launches++;
-  } else {
-    if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
-    int a = (k + 1) / 2;
-    if (a > 8) a = 8;
-    int b = k - a;
-    u32 cols_log = 4, cols = 16;
-    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
-    k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
-        coeffs, src_stride, lde, dst_stride, pm, tab, k, a, r, cols_log, blk0);
-    int rows_log = 12 - b;  // kTileElems / n2
-    if (rows_log < 0) rows_log = 0;
-    if (rows_log > a) rows_log = a;
-    u32 rows = 1u << rows_log;
-    size_t smem_b = ((size_t)rows * tile_pitch(1u << b) + (1u << b)) * 8;
-    k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k,
-                                                                                         a, r, (u32)rows_log, blk0);
-    c->launches += 2;
-  }
+  if (k <= kSmallMaxLog) return launch_small<false>(c, coeffs, src_stride, lde, dst_stride, pm, tab, ncols, ncosets, k, r, 1, blk0);
+  if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
+  int a = (k + 1) / 2;
+  if (a > 8) a = 8;
+  int b = k - a;
+  const u64* twm;
+  QP(get_tw_matrix(c, k, a, false, &twm));
+  u32 cols_log = 4, cols = 16;
+  size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
+  int rows_log = 12 - b;  // kTileElems / n2
+  if (rows_log < 0) rows_log = 0;
+  if (rows_log > a) rows_log = a;
+  u32 rows = 1u << rows_log;
+  size_t smem_b = ((size_t)rows * tile_pitch(1u << b) + (1u << b)) * 8;
+  k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
+      coeffs, src_stride, lde, dst_stride, pm, tab, twm, k, a, r, cols_log, blk0);
+  k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k, a, r,
+                                                                                       (u32)rows_log, blk0);
+  c->launches += 2;
   CU(cudaGetLastError());
   return QPZK_OK;
 }
@@ -221,28 +264,24 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   RootTab tab;
   QP(get_root_tab(c, k, true, &tab));
   u64 ninv = glh::inv(((u64)1 << k) % GL_P);
-  if (k <= kSmallMaxLog) {
-    size_t smem = ((size_t)tile_pitch(1u << k) + ((size_t)1 << k)) * 8;
-    k_ntt_small<true><<<dim3(ncols, 1), 256, smem, c->stream>>>(values, src_stride, coeffs, dst_stride, nullptr,
-                                                                tab, k, 0, ninv, 0);
-    c->launches++;
-  } else {
-    if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 20 not supported");
-    int a = (k + 1) / 2, b = k - a;
-    // tiles of 4096 elements: [2^a][cols] in pass A, [rc][2^b] in pass B
-    u32 cols_log = a <= 8 ? 4 : 12 - a, cols = 1u << cols_log;
-    u32 rc_log = b <= 8 ? 4 : 12 - b, rc = 1u << rc_log;
-    u64* tmp;
-    QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
-    size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
-    k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
-        values, src_stride, tmp, (u64)1 << k, nullptr, tab, k, a, 0, cols_log, 0);
-    size_t smem_b = ((size_t)rc * tile_pitch(1u << b) + (1u << b)) * 8;
-    k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs,
-                                                                                    dst_stride, tab, k, a, rc_log, ninv);
-    c->launches += 2;
-    dev_free(c, tmp);
-  }
+  if (k <= kSmallMaxLog) return launch_small<true>(c, values, src_stride, coeffs, dst_stride, nullptr, tab, ncols, 1, k, 0, ninv, 0);
+  if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 20 not supported");
+  int a = (k + 1) / 2, b = k - a;
+  const u64* twm;
+  QP(get_tw_matrix(c, k, a, true, &twm));
+  // tiles of 4096 elements: [2^a][cols] in pass A, [rc][2^b] in pass B
+  u32 cols_log = a <= 8 ? 4 : 12 - a, cols = 1u << cols_log;
+  u32 rc_log = b <= 8 ? 4 : 12 - b, rc = 1u << rc_log;
+  u64* tmp;
+  QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
+  size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
+  size_t smem_b = ((size_t)rc * tile_pitch(1u << b) + (1u << b)) * 8;
+  k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
+      values, src_stride, tmp, (u64)1 << k, nullptr, tab, twm, k, a, 0, cols_log, 0);
+  k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs, dst_stride,
+                                                                                  tab, k, a, rc_log, ninv);
+  c->launches += 2;
+  dev_free(c, tmp);
   CU(cudaGetLastError());
   return QPZK_OK;
 }
@@ -386,8 +425,10 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
 #endif
       // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
       const int kMaxSmem = 72 * 1024;
-      CU(cudaFuncSetAttribute(k_ntt_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      CU(cudaFuncSetAttribute(k_ntt_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+      CU(cudaFuncSetAttribute(k_ntt_small<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+      CU(cudaFuncSetAttribute(k_ntt_small<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+      CU(cudaFuncSetAttribute(k_ntt_small<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+      CU(cudaFuncSetAttribute(k_ntt_small<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
       CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
       CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
       CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -411,6 +452,7 @@ void qpzk_ctx_destroy(qpzk_ctx* c) {
     dev_free(c, kv.second.second);
   }
   for (auto& kv : c->coset_pm) dev_free(c, kv.second);
+  for (auto& kv : c->tw_mats) dev_free(c, kv.second);
   for (auto& kv : c->pow_tabs) {
     dev_free(c, kv.second.first);
     dev_free(c, kv.second.second);
