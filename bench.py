@@ -320,11 +320,13 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     S = max(1, args.streams)
-    # every proving thread spins on a host core while its stream works: keep threads x ranks within the cores
-    cores = os.cpu_count() or 1
-    if not args.blocking_sync:
-        S = max(1, min(S, cores // max(1, world)))
-    ctxs = [qpzk.Context(local_rank, blocking_sync=args.blocking_sync) for _ in range(S)]
+    # a spinning proving thread occupies a host core while its stream works: once threads x ranks exceed the
+    # cores the threads poll and yield instead
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    sync = args.sync
+    if sync == "auto":
+        sync = "spin" if S * max(1, world) <= cores else "yield"
+    ctxs = [qpzk.Context(local_rank, blocking_sync=sync == "blocking", yield_sync=sync == "yield") for _ in range(S)]
     ctx0 = ctxs[0]
 
     # one synthetic wormhole-shaped circuit + witness per stream
@@ -535,7 +537,7 @@ def run_gpu(args, rank, local_rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "degree_bits": PROOF_K, "zero_knowledge": PROOF_ZK,
-                       "streams_per_gpu": S,
+                       "streams_per_gpu": S, "host_wait": sync, "host_cores": cores,
                        "l2": "each proof streams ~0.3 GB of LDE/digest buffers through HBM (> 126 MB L2); "
                              "the commit microbench rotates 4 distinct 70.8 MB traces",
                        "parallelism": "independent proofs, %d stream(s) per GPU, no collective" % S},
@@ -603,8 +605,10 @@ def main():
     ap.add_argument("--streams", type=int, default=6, help="proofs in flight per GPU (measured: 1: 118, 2: 151, 4: 166, 6: 172, 8: 173 proofs/s)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--blocking-sync", action="store_true",
-                    help="contexts wait on blocking-sync events instead of spinning (QPZK_CTX_BLOCKING_SYNC)")
+    ap.add_argument("--sync", default="auto", choices=["auto", "spin", "yield", "blocking"],
+                    help="how a proving thread waits for its stream: spin on a core, poll + sched_yield "
+                         "(QPZK_CTX_YIELD_SYNC) or sleep on a blocking-sync event (QPZK_CTX_BLOCKING_SYNC); "
+                         "auto = spin while streams x ranks fit the host cores, else yield")
     ap.add_argument("--no-aggregator", action="store_true", help="skip the aggregation-node proof (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -618,7 +622,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--streams", str(args.streams)]
+               "--streams", str(args.streams), "--sync", args.sync]
+        cmd += ["--no-cpu"] * args.no_cpu + ["--no-aggregator"] * args.no_aggregator
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
 

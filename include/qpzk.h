@@ -60,9 +60,14 @@ enum {
 };
 
 /* ---- context ---- */
-/* flags: QPZK_CTX_BLOCKING_SYNC - waits for the device sleep on a blocking-sync event instead of spinning a
- * host core (use when proving threads x processes exceed the host cores, e.g. many rayon workers). */
+/* flags: how a call waits for its stream (the Fiat-Shamir transcript stays on the host, so one proof waits
+ * about a dozen times). Default: spin on a host core - lowest latency, right when proving threads <= cores.
+ * QPZK_CTX_BLOCKING_SYNC - sleep on a blocking-sync event (interrupt wake-up, tens of microseconds each).
+ * QPZK_CTX_YIELD_SYNC    - poll the event and sched_yield() between polls: spinning latency while cores are
+ *                          free, and proving threads x processes may exceed the host cores (many rayon
+ *                          workers, 8 ranks x 6 proofs in flight on 32 cores) without starving each other. */
 #define QPZK_CTX_BLOCKING_SYNC 1u
+#define QPZK_CTX_YIELD_SYNC 2u
 int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out);
 void qpzk_ctx_destroy(qpzk_ctx* ctx);
 const char* qpzk_last_error(void);

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sched.h>
 #include <map>
 #include <memory>
 #include <tuple>
@@ -57,6 +58,7 @@ struct qpzk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool blocking_sync = false;      // QPZK_CTX_BLOCKING_SYNC: sleep instead of spinning while the device works
+  bool yield_sync = false;         // QPZK_CTX_YIELD_SYNC: poll + sched_yield()
   cudaEvent_t sync_ev = nullptr;
   cudaEvent_t ev[QPZK_NUM_STAGES + 1];
   float stage_ms[QPZK_NUM_STAGES] = {0};
@@ -91,9 +93,12 @@ struct qpzk_tree {
 // proving threads on 32 cores lost 10 % of throughput); a context created with
 // QPZK_CTX_BLOCKING_SYNC waits on a blocking-sync event instead.
 static cudaError_t ctx_wait(qpzk_ctx* c) {
-  if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
+  if (!c->blocking_sync && !c->yield_sync) return cudaStreamSynchronize(c->stream);
   cudaError_t e = cudaEventRecord(c->sync_ev, c->stream);
-  return e != cudaSuccess ? e : cudaEventSynchronize(c->sync_ev);
+  if (e != cudaSuccess) return e;
+  if (c->blocking_sync) return cudaEventSynchronize(c->sync_ev);
+  while ((e = cudaEventQuery(c->sync_ev)) == cudaErrorNotReady) sched_yield();
+  return e;
 }
 
 static int dev_alloc(qpzk_ctx* c, size_t bytes, u64** out) {
@@ -388,6 +393,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->blocking_sync = (flags & QPZK_CTX_BLOCKING_SYNC) != 0;
+  c->yield_sync = !c->blocking_sync && (flags & QPZK_CTX_YIELD_SYNC) != 0;
   CU(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   for (auto& e : c->ev) CU(cudaEventCreate(&e));
   // keep freed blocks in the pool: commits allocate and release hundreds of MB per call

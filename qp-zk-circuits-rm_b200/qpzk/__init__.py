@@ -129,10 +129,11 @@ def _ptr(a):
 class Context:
     """One CUDA stream + caches (twiddle tables, coset pre-multipliers) on one device."""
 
-    def __init__(self, device=0, blocking_sync=False):
+    def __init__(self, device=0, blocking_sync=False, yield_sync=False):
+        """blocking_sync / yield_sync: QPZK_CTX_BLOCKING_SYNC / QPZK_CTX_YIELD_SYNC (include/qpzk.h)."""
         L = load_library()
         h = _vp()
-        _check(L.qpzk_ctx_create(device, 1 if blocking_sync else 0, ctypes.byref(h)))
+        _check(L.qpzk_ctx_create(device, 1 if blocking_sync else (2 if yield_sync else 0), ctypes.byref(h)))
         self._h = h
         self.device = device
 

@@ -17,6 +17,7 @@ pub const QPZK_ERR_NOT_DIVISIBLE: c_int = -4;
 pub const QPZK_ERR_UNSUPPORTED: c_int = -5;
 pub const QPZK_SALT_SIZE: usize = 4;
 pub const QPZK_CTX_BLOCKING_SYNC: u32 = 1;
+pub const QPZK_CTX_YIELD_SYNC: u32 = 2;
 
 #[repr(C)] pub struct qpzk_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }
