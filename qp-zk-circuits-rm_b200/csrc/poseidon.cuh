@@ -37,7 +37,7 @@ GL_DEV u64 sbox7(u64 x) {
   return gl_mul(x3, x4);
 }
 
-// MDS lane recombination: al + ah*2^32 with al, ah < 2^42, folded to 64 bits.
+// MDS lane recombination: al + ah*2^32 with al = l1:l0, ah = h1:h0 < 2^42, folded to 64 bits.
 //   value = l0 + (l1 + h0)*2^32 + (h1 + carry)*2^64,  2^64 == EPS; the multiply-add by EPS can carry once.
 GL_DEV u64 mds_combine(u32 l0, u32 l1, u32 h0, u32 h1) {
   asm("{\n\t.reg .u32 c;\n\t"
@@ -106,37 +106,49 @@ GL_DEV void mad_wide(u32& lo, u32& hi, u32 a, u32 b) {
 #define PV_MDS_F64 1
 #endif
 // MDS on the FP64 pipe. The integer multiplier (FMA-heavy) pipe is the one Poseidon saturates, while
-// the DFMA pipe of the B200 (64 per clock per SM) idles. The circulant has entries < 2^6, so the state
-// is cut into three limbs of 22/22/20 bits, each plane's 12x12 product runs as exact integer arithmetic
-// in doubles (|sum| < 2^31 << 2^53), and the three 31-bit plane sums are stitched back with shifts
-// and one fold. int <-> double through the 2^52 bias (one DADD each way), no conversion instructions.
+// the DFMA pipe of the B200 (64 per clock per SM) idles. The circulant has entries < 2^6 (row sum 264), so
+// the 12x12 product runs on the two 32-bit HALVES of the state as exact integer arithmetic in doubles:
+// every sum is < 264 * 2^32 < 2^41 << 2^53. int -> double through the 2^52 bias (the half is the low
+// mantissa word, one DADD removes the bias), double -> int by adding the bias back and reading the
+// mantissa: low word + 20 bits of the high word. No conversion instructions, no limb shifting or masking
+// on the way in, 288 DFMA per layer. (The first version cut the state into three 22-bit limbs so that each
+// sum fitted one 32-bit word: 432 DFMA, 72 conversions and a three-way stitch per layer.)
 __constant__ double c_mds_circ_d[12];
+#ifndef PV_RC_FOLD
+#define PV_RC_FOLD 1
+#endif
+// With PV_RC_FOLD the layer also adds the constants of the round that follows it (poseidon_next_rc_f64):
+// they enter as the accumulators' initial values, which costs nothing, and the 64-bit modular additions at
+// the head of the next round disappear.
+__constant__ double c_mds_next_rc_d[8][2][12];
 GL_DEV double u32_to_f64(u32 v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
-GL_DEV u32 f64_to_u32(double d) { return (u32)__double2loint(d + 4503599627370496.0); }
-GL_DEV void mds_layer_f64(u64 (&s)[12]) {
-  u32 S[3][12];
+GL_DEV void f64_to_u52(double d, u32& lo, u32& hi) {
+  const double t = d + 4503599627370496.0;
+  lo = (u32)__double2loint(t);
+  hi = (u32)__double2hiint(t) & 0xFFFFFu;
+}
+GL_DEV void mds_layer_f64(u64 (&s)[12], int layer) {
+  u32 S[2][2][12];  // [half][word][lane]: sum over the low / high halves, each < 2^41 (+ 2^32 of constants)
 #pragma unroll
-  for (int k = 0; k < 3; k++) {
+  for (int k = 0; k < 2; k++) {
     double d[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      u32 limb = k == 0 ? (u32)s[i] & 0x3FFFFFu : (k == 1 ? (u32)(s[i] >> 22) & 0x3FFFFFu : (u32)(s[i] >> 44));
-      d[i] = u32_to_f64(limb);
-    }
+    for (int i = 0; i < 12; i++) d[i] = u32_to_f64(k == 0 ? (u32)s[i] : (u32)(s[i] >> 32));
 #pragma unroll
     for (int r = 0; r < 12; r++) {
+#if PV_RC_FOLD
+      double acc = c_mds_next_rc_d[layer][k][r];
+      if (r == 0) acc = fma(d[0], 8.0, acc);
+#else
       double acc = r == 0 ? d[0] * 8.0 : 0.0;
+#endif
 #pragma unroll
       for (int i = 0; i < 12; i++) acc = fma(d[(i + r) % 12], c_mds_circ_d[i], acc);
-      S[k][r] = f64_to_u32(acc);
+      f64_to_u52(acc, S[k][0][r], S[k][1][r]);
     }
   }
 #pragma unroll
-  for (int r = 0; r < 12; r++) {
-    // T = S0 + S1*2^22 + S2*2^44 < 2^76: low 64 bits + top*2^64, 2^64 == EPS
-    unsigned __int128 t = (unsigned __int128)S[0][r] + ((unsigned __int128)S[1][r] << 22) + ((unsigned __int128)S[2][r] << 44);
-    s[r] = gl_fold((u64)t, (u32)(u64)(t >> 64), 0);
-  }
+  for (int r = 0; r < 12; r++) s[r] = mds_combine(S[0][0][r], S[0][1][r], S[1][0][r], S[1][1][r]);
 }
 // MDS on the integer multiplier: 32-bit halves, IMAD.WIDE accumulate, one fold per lane. Used where the
 // FP64 variant's extra registers hurt (the quotient kernel's PoseidonGate evaluation).
@@ -162,43 +174,63 @@ GL_DEV void mds_layer_int(u64 (&s)[12]) {
     s[r] = mds_combine(al0, al1, ah0, ah1);
   }
 }
-GL_DEV void mds_layer(u64 (&s)[12]) {
-#if PV_MDS_F64
-  mds_layer_f64(s);
+// Full round: add constants (unless the previous MDS layer already did), x^7 on every lane, MDS.
+// Code size matters more than the last instruction here: ncu showed the fully unrolled permutation
+// (90 KB of SASS) stalled ~50% on instruction fetch, the 32 KB L1.5 I-cache thrashing with 24 warps
+// per SM spread over the kernel. The 12 s-boxes are therefore issued as PV_SBOX_TRIPS trips over
+// 12 / PV_SBOX_TRIPS lanes with the state ROTATED per trip (indices stay compile-time, 24 MOVs per trip).
+#ifndef PV_SBOX_TRIPS
+#define PV_SBOX_TRIPS 1
+#endif
+template <bool ADD_RC>
+GL_DEV void sbox_layer(u64 (&s)[12], const u64* __restrict__ rc) {
+  constexpr int LANES = 12 / PV_SBOX_TRIPS;
+#pragma unroll 1
+  for (int g = 0; g < PV_SBOX_TRIPS; g++) {
+    u64 t[LANES];
+#pragma unroll
+    for (int j = 0; j < LANES; j++) t[j] = sbox7(ADD_RC ? gl_add_c(s[j], rc[LANES * g + j]) : s[j]);
+#pragma unroll
+    for (int i = 0; i < 12 - LANES; i++) s[i] = s[i + LANES];
+#pragma unroll
+    for (int j = 0; j < LANES; j++) s[12 - LANES + j] = t[j];
+  }
+}
+// layer = index of the full round among the 8 (selects the constants the FP64 MDS adds for the next round)
+GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc, int layer) {
+#if PV_MDS_F64 && PV_RC_FOLD
+  if (layer == 0 || layer == 4) {  // the rounds not preceded by an FP64 MDS layer
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[i]);
+  }
+  sbox_layer<false>(s, rc);
+  mds_layer_f64(s, layer);
+#elif PV_MDS_F64
+  sbox_layer<true>(s, rc);
+  mds_layer_f64(s, layer);
 #else
+  sbox_layer<true>(s, rc);
   mds_layer_int(s);
 #endif
 }
 
-// Full round: add constants, x^7 on every lane, MDS.
-// Code size matters more than the last instruction here: ncu showed the fully unrolled permutation
-// (90 KB of SASS) stalled ~50% on instruction fetch, the 32 KB L1.5 I-cache thrashing with 24 warps
-// per SM spread over the kernel. The 12 s-boxes are therefore issued as 3 trips over 4 lanes with
-// the state ROTATED by 4 registers per trip (indices stay compile-time, 24 MOVs per trip).
-GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc) {
-#pragma unroll 1
-  for (int g = 0; g < 3; g++) {
-    u64 t0 = sbox7(gl_add_c(s[0], rc[4 * g + 0]));
-    u64 t1 = sbox7(gl_add_c(s[1], rc[4 * g + 1]));
-    u64 t2 = sbox7(gl_add_c(s[2], rc[4 * g + 2]));
-    u64 t3 = sbox7(gl_add_c(s[3], rc[4 * g + 3]));
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-    s[8] = t0;
-    s[9] = t1;
-    s[10] = t2;
-    s[11] = t3;
-  }
-  mds_layer(s);
-}
-
+#ifndef PV_INIT_UNROLL
+#define PV_INIT_UNROLL 1
+#endif
+#ifndef PV_PARTIAL_UNROLL
+#define PV_PARTIAL_UNROLL 1
+#endif
+#define PV_PRAGMA_(x) _Pragma(#x)
+#define PV_UNROLL(n) PV_PRAGMA_(unroll n)
 GL_DEV void partial_rounds(u64 (&s)[12]) {
+#if !(PV_MDS_F64 && PV_RC_FOLD)  // otherwise the MDS layer of the 4th full round added them
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
+#endif
   {  // mds_partial_layer_init: out[c] = sum_r in[r] * init[r-1][c-1], c = 1..11.
      // One trip per output lane; results are shifted through o[] so every index is static.
     u64 o[11];
-#pragma unroll 1
+PV_UNROLL(PV_INIT_UNROLL)
     for (int c = 0; c < 11; c++) {
       Acc160 a;
       acc_init(a);
@@ -211,7 +243,7 @@ GL_DEV void partial_rounds(u64 (&s)[12]) {
 #pragma unroll
     for (int i = 1; i < 12; i++) s[i] = o[i - 1];
   }
-#pragma unroll 1
+PV_UNROLL(PV_PARTIAL_UNROLL)
   for (int r = 0; r < 22; r++) {
     u64 s0 = sbox7(s[0]);
     s0 = gl_add_c(s0, c_fast_rc[r]);  // entry 21 is zero
@@ -232,7 +264,7 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * (26 * half + r));
+    for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * (26 * half + r), 4 * half + r);
     if (half == 0) partial_rounds(s);
   }
 }

@@ -193,4 +193,19 @@ static inline void build_poseidon_tables(PoseidonTablesHost* T) {
   }
 }
 
+// Constants added by the FP64 MDS layer of full round j (0..7, both halves) on behalf of the round that
+// follows it, as the 32-bit halves of each word in doubles: [j][half][lane]. Layers 0-2 and 4-6 carry the
+// next full round's constants, layer 3 the first constants of the partial rounds, layer 7 zeros.
+static inline void poseidon_next_rc_f64(const PoseidonTablesHost& T, double (*out)[2][12]) {
+  for (int j = 0; j < 8; j++)
+    for (int i = 0; i < 12; i++) {
+      u64 c = 0;
+      if (j < 3) c = T.rc[12 * (j + 1) + i];
+      else if (j == 3) c = T.fast_first[i];
+      else if (j < 7) c = T.rc[12 * (26 + (j - 4) + 1) + i];
+      out[j][0][i] = (double)(uint32_t)c;
+      out[j][1][i] = (double)(uint32_t)(c >> 32);
+    }
+}
+
 }  // namespace qpzk

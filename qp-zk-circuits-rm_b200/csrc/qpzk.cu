@@ -428,6 +428,9 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
       double circ_d[12];
       for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
       CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
+      static double next_rc[8][2][12];
+      poseidon_next_rc_f64(*T, next_rc);
+      CU(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
 #endif
       // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
       const int kMaxSmem = 72 * 1024;

@@ -84,6 +84,9 @@ int main(int argc, char** argv) {
     double cd[12];
     for (int i = 0; i < 12; i++) cd[i] = (double)kMdsCirc[i];
     CK(cudaMemcpyToSymbol(c_mds_circ_d, cd, sizeof cd));
+    static double next_rc[8][2][12];
+    poseidon_next_rc_f64(*T, next_rc);
+    CK(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
   }
 #endif
   const u64 n = 1 << 19;
