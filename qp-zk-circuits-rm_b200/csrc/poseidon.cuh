@@ -225,44 +225,49 @@ GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc, int layer) {
 #endif
 #define PV_PRAGMA_(x) _Pragma(#x)
 #define PV_UNROLL(n) PV_PRAGMA_(unroll n)
+// mds_partial_layer_init of the sparse partial-round form: out[c] = sum_r in[r] * init[r-1][c-1] for
+// c = 1..11 (11x11, 64-bit entries), one trip per output lane. Also used by the quotient kernel's
+// PoseidonGate. Every caller runs 128-thread blocks.
+GL_DEV void partial_init_layer(u64 (&s)[12]) {
+#if PV_INIT_SMEM
+  // Outputs are parked in shared memory (one column per thread, conflict-free) until all 11 are done: a
+  // store per trip and 11 loads at the end, instead of shifting an 11-word register file every trip
+  // (220 moves per permutation plus the spills they caused).
+  __shared__ u64 sh_o[11][128];
+#pragma unroll 1
+  for (int c = 0; c < 11; c++) {
+    Acc160 a;
+    acc_init(a);
+#pragma unroll
+    for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
+    sh_o[c][threadIdx.x] = acc_reduce(a);
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) s[i] = sh_o[i - 1][threadIdx.x];
+#else
+  // Results are shifted through o[] so every index is static.
+  u64 o[11];
+  PV_UNROLL(PV_INIT_UNROLL)
+  for (int c = 0; c < 11; c++) {
+    Acc160 a;
+    acc_init(a);
+#pragma unroll
+    for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
+#pragma unroll
+    for (int i = 0; i < 10; i++) o[i] = o[i + 1];
+    o[10] = acc_reduce(a);
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) s[i] = o[i - 1];
+#endif
+}
+
 GL_DEV void partial_rounds(u64 (&s)[12]) {
 #if !(PV_MDS_F64 && PV_RC_FOLD)  // otherwise the MDS layer of the 4th full round added them
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
 #endif
-  {  // mds_partial_layer_init: out[c] = sum_r in[r] * init[r-1][c-1], c = 1..11. One trip per output lane.
-#if PV_INIT_SMEM
-    // Outputs are parked in shared memory (one column per thread, conflict-free) until all 11 are done: a
-    // store per trip and 11 loads at the end, instead of shifting an 11-word register file every trip
-    // (220 moves per permutation plus the spills they caused). Every caller runs 128-thread blocks.
-    __shared__ u64 sh_o[11][128];
-#pragma unroll 1
-    for (int c = 0; c < 11; c++) {
-      Acc160 a;
-      acc_init(a);
-#pragma unroll
-      for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
-      sh_o[c][threadIdx.x] = acc_reduce(a);
-    }
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = sh_o[i - 1][threadIdx.x];
-#else
-    // Results are shifted through o[] so every index is static.
-    u64 o[11];
-PV_UNROLL(PV_INIT_UNROLL)
-    for (int c = 0; c < 11; c++) {
-      Acc160 a;
-      acc_init(a);
-#pragma unroll
-      for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
-#pragma unroll
-      for (int i = 0; i < 10; i++) o[i] = o[i + 1];
-      o[10] = acc_reduce(a);
-    }
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = o[i - 1];
-#endif
-  }
+  partial_init_layer(s);
 PV_UNROLL(PV_PARTIAL_UNROLL)
   for (int r = 0; r < 22; r++) {
     u64 s0 = sbox7(s[0]);

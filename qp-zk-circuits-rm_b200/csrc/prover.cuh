@@ -232,25 +232,11 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer_int(s);
+    mds_layer_f64(s, 7);  // layer 7: no constants folded in
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
-  {
-    u64 o[11];
-#pragma unroll 1
-    for (int c = 0; c < 11; c++) {
-      Acc160 acc;
-      acc_init(acc);
-#pragma unroll
-      for (int r = 1; r < 12; r++) acc_mac(acc, s[r], c_fast_init[(r - 1) * 11 + c]);
-#pragma unroll
-      for (int i = 0; i < 10; i++) o[i] = o[i + 1];
-      o[10] = acc_reduce(acc);
-    }
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = o[i - 1];
-  }
+  partial_init_layer(s);
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
     u64 in = w[65 + r];
@@ -281,7 +267,7 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer_int(s);
+    mds_layer_f64(s, 7);  // layer 7: no constants folded in
   }
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {
