@@ -200,10 +200,18 @@ struct WireRow {  // column-major LDE accessor for one leaf position
 };
 
 // PoseidonGate::eval_unfiltered (123 constraints) with the fast partial rounds; emits in order.
+// The s-box input wires (29..134) are consumed in index order, a few per round, each right before a long
+// dependent computation: fetched just in time they stalled the kernel on memory latency (ncu: 41 % of the
+// warp stall samples were long_scoreboard at 16 warps per SM). Every group of wires is therefore loaded
+// one group AHEAD - the next trip's four while the current four go through their s-boxes, the next partial
+// round's one during the current round.
 GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
   u64 swap = w[24];
   aa_emit(a, gl_mul(swap, gl_sub(swap, 1)));
   u64 s[12];
+  u64 nx[4];  // the next four s-box inputs, in flight
+#pragma unroll
+  for (int q = 0; q < 4; q++) nx[q] = w[29 + q];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     u64 lhs = w[i], rhs = w[i + 4], delta = w[25 + i];
@@ -213,18 +221,25 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
   }
 #pragma unroll
   for (int i = 8; i < 12; i++) s[i] = w[i];
+  u32 next = 33;  // index of the first wire not yet requested
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
 #pragma unroll 1
     for (int g = 0; g < 3; g++) {  // rotate-by-4 so indices stay static (see poseidon.cuh)
-      u64 t[4];
+      u64 t[4], in[4];
+      if (r != 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) in[q] = nx[q];
+#pragma unroll
+        for (int q = 0; q < 4; q++) nx[q] = w[next + q];  // wires 33..64, then 65..68 (only 65 is used)
+        next += 4;
+      }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         u64 v = gl_add_c(s[q], c_rc[12 * r + 4 * g + q]);
         if (r != 0) {
-          u64 in = w[29 + 12 * (r - 1) + 4 * g + q];
-          aa_emit(a, gl_sub(v, in));
-          v = in;
+          aa_emit(a, gl_sub(v, in[q]));
+          v = in[q];
         }
         t[q] = sbox7(v);
       }
@@ -237,9 +252,11 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
   partial_init_layer(s);
+  u64 in_next = nx[0];  // wire 65
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
-    u64 in = w[65 + r];
+    u64 in = in_next;
+    in_next = w[66 + r];  // the last trip requests wire 87, the first input of the second half
     aa_emit(a, gl_sub(s[0], in));
     u64 s0 = gl_add_c(sbox7(in), c_fast_rc[r]);
     Acc160 acc;
@@ -251,23 +268,33 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
     for (int i = 1; i < 12; i++) s[i] = gl_mad(s0, c_fast_v[r * 11 + i - 1], s[i]);
     s[0] = acc_reduce(acc);
   }
+  nx[0] = in_next;
+#pragma unroll
+  for (int q = 1; q < 4; q++) nx[q] = w[87 + q];
+  next = 91;
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
 #pragma unroll 1
     for (int g = 0; g < 3; g++) {
-      u64 t[4];
+      u64 t[4], in[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) in[q] = nx[q];
+      if (next < 135) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) nx[q] = w[next + q];
+        next += 4;
+      }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         u64 v = gl_add_c(s[q], c_rc[12 * (26 + r) + 4 * g + q]);
-        u64 in = w[87 + 12 * r + 4 * g + q];
-        aa_emit(a, gl_sub(v, in));
-        t[q] = sbox7(in);
+        aa_emit(a, gl_sub(v, in[q]));
+        t[q] = sbox7(in[q]);
       }
 #pragma unroll
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer_f64(s, 7);  // layer 7: no constants folded in
+    mds_layer_f64(s, 7);
   }
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {
@@ -416,7 +443,7 @@ __global__ void k_build_l0_den_inv(u64* __restrict__ out, RootTab tab, u32 degre
 // RECURSION = false is the wormhole / voting gate set; the recursion gates are compiled only into the
 // <true> instantiation so that they cost the common case neither registers nor instruction cache.
 template <bool RECURSION>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RECURSION ? 3 : 4)
 k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, const u64* __restrict__ zs_lde,
            u64 cs_stride, u64 wires_stride, u64 zs_stride, u32 step_bits, const u64* __restrict__ k_is,
            CircuitDesc d, Challenges ch, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
@@ -449,23 +476,59 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
     u64 l0 = gl_mul(zhx, l0_den_inv[i]);
     for (u32 c = 0; c < nch; c++) aa_emit(a, gl_mul(l0, gl_sub(zs[c], 1)));
   }
-  // partial-product checks
+  // partial-product checks: term (c, k) = prev * prod_j num_j - next * prod_j den_j over chunk k of qdf routed
+  // wires. Chunks outside, challenges inside: the chunk's wires, sigmas and k_is are requested as ONE batch
+  // before any arithmetic and serve both challenges (fetched one by one inside the product loop, every
+  // factor waited for its own loads: 38 % of the kernel's stall samples, 97 % of them long_scoreboard).
+  // The alpha-power table makes the emission order free, so each term goes straight to its slot.
   const u32 nchunks = npp + 1;
-  for (u32 c = 0; c < nch; c++) {
-    const u64 beta = ch.beta[c], gamma = ch.gamma[c];
-    const u64 bx = gl_mul(beta, x);
-    u64 prev = zs[c];
-    for (u32 k = 0; k < nchunks; k++) {
-      u64 num = 1, den = 1;
-      for (u32 j = k * d.qdf; j < (k + 1) * d.qdf && j < d.num_routed; j++) {
-        u64 wv = w[j];
-        num = gl_mul(num, gl_add(gl_mad(bx, k_is[j], wv), gamma));
-        den = gl_mul(den, gl_add(gl_mad(beta, cs[d.num_constants + j], wv), gamma));
-      }
-      u64 next = k + 1 < nchunks ? zs[nch + c * npp + k] : zsn[c];
-      aa_emit(a, gl_sub(gl_mul(prev, num), gl_mul(next, den)));
-      prev = next;
+  const u32 pp_base = a.t;
+  {
+    u64 bx[2], prev[2];
+    for (u32 c = 0; c < nch; c++) {
+      bx[c] = gl_mul(ch.beta[c], x);
+      prev[c] = zs[c];
     }
+    for (u32 k = 0; k < nchunks; k++) {
+      const u32 j0 = k * d.qdf;
+      u64 next[2];
+      for (u32 c = 0; c < nch; c++) next[c] = k + 1 < nchunks ? zs[nch + c * npp + k] : zsn[c];
+      if (d.qdf == 8 && j0 + 8 <= d.num_routed) {
+        u64 wv[8], sg[8], kk[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          wv[e] = w[j0 + e];
+          sg[e] = cs[d.num_constants + j0 + e];
+          kk[e] = __ldg(k_is + j0 + e);
+        }
+        for (u32 c = 0; c < nch; c++) {
+          const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+          u64 num = gl_add(gl_mad(bx[c], kk[0], wv[0]), gamma);
+          u64 den = gl_add(gl_mad(beta, sg[0], wv[0]), gamma);
+#pragma unroll
+          for (int e = 1; e < 8; e++) {
+            num = gl_mul(num, gl_add(gl_mad(bx[c], kk[e], wv[e]), gamma));
+            den = gl_mul(den, gl_add(gl_mad(beta, sg[e], wv[e]), gamma));
+          }
+          a.t = pp_base + c * nchunks + k;
+          aa_emit(a, gl_sub(gl_mul(prev[c], num), gl_mul(next[c], den)));
+        }
+      } else {  // other chunk sizes, ragged last chunk
+        for (u32 c = 0; c < nch; c++) {
+          const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+          u64 num = 1, den = 1;
+          for (u32 j = j0; j < j0 + d.qdf && j < d.num_routed; j++) {
+            u64 wv = w[j];
+            num = gl_mul(num, gl_add(gl_mad(bx[c], k_is[j], wv), gamma));
+            den = gl_mul(den, gl_add(gl_mad(beta, cs[d.num_constants + j], wv), gamma));
+          }
+          a.t = pp_base + c * nchunks + k;
+          aa_emit(a, gl_sub(gl_mul(prev[c], num), gl_mul(next[c], den)));
+        }
+      }
+      for (u32 c = 0; c < nch; c++) prev[c] = next[c];
+    }
+    a.t = pp_base + nch * nchunks;
   }
   // gate constraints: slot j gets sum_g filter_g * c_{g,j}; each gate restarts at alpha^base
   const u32 base_t = a.t;
