@@ -249,7 +249,7 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
   if (rows_log > a) rows_log = a;
   u32 rows = 1u << rows_log;
   size_t smem_b = ((size_t)rows * tile_pitch(1u << b) + (1u << b)) * 8;
-  k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncols, ncosets), 256, smem_a, c->stream>>>(
+  k_ntt_pass_a<true><<<dim3((1u << b) / cols, ncosets, ncols), 256, smem_a, c->stream>>>(
       coeffs, src_stride, lde, dst_stride, pm, tab, twm, k, a, r, cols_log, blk0);
   k_ntt_pass_b_rows<<<dim3((1u << a) / rows, ncols, ncosets), 256, smem_b, c->stream>>>(lde, dst_stride, tab, k, a, r,
                                                                                        (u32)rows_log, blk0);
@@ -281,7 +281,7 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   QP(dev_alloc(c, (size_t)ncols << (k + 3), &tmp));
   size_t smem_a = ((size_t)(1u << a) * cols + (1u << a)) * 8;
   size_t smem_b = ((size_t)rc * tile_pitch(1u << b) + (1u << b)) * 8;
-  k_ntt_pass_a<false><<<dim3((1u << b) / cols, ncols, 1), 256, smem_a, c->stream>>>(
+  k_ntt_pass_a<false><<<dim3((1u << b) / cols, 1, ncols), 256, smem_a, c->stream>>>(
       values, src_stride, tmp, (u64)1 << k, nullptr, tab, twm, k, a, 0, cols_log, 0);
   k_ntt_pass_b_transpose<<<dim3((1u << a) / rc, ncols), 256, smem_b, c->stream>>>(tmp, (u64)1 << k, coeffs, dst_stride,
                                                                                   tab, k, a, rc_log, ninv);
