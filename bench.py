@@ -46,9 +46,11 @@ WORKLOAD = ("wormhole single-proof generation, bench-data shape (2^14 x 135 wire
             "Noop/Constant/PublicInput/BaseSum63/Arithmetic20/Poseidon, FRI [4,4,4], salted), synthetic satisfying witness")
 
 
-NTT_DRAM_BYTES_PER_COMMIT = int((70.916096 + 70.898688 + 558.888192 + 566.393088 +
-                                 26.451968 + 25.257216 + 522.532096 + 505.859584) * 1e6)
-LEAF_HASH_DRAM_BYTES_PER_COMMIT = int((572.058624 + 46.661888) * 1e6)   # profiles/r1_poseidon_v3_ncu_full.txt
+# dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture per kernel
+# profiles/r1_ntt_v2_ncu_full.txt: k_ntt_pass_a<0>, k_ntt_pass_b_transpose, k_ntt_pass_a<1>, k_ntt_pass_b_rows
+NTT_DRAM_BYTES_PER_COMMIT = int((71.430912 + 28.294144 + 70.869504 + 25.209344 +
+                                 75.717888 + 509.248000 + 566.322176 + 506.380288) * 1e6)
+LEAF_HASH_DRAM_BYTES_PER_COMMIT = int((566.815232 + 17.787392) * 1e6)   # profiles/r1_leaf_hash_v5_twoplane_ncu_full.txt
 
 
 def algorithmic_counts(k=DEGREE_BITS, c=NCOLS, s=0, r=RATE_BITS, h=CAP_HEIGHT):
@@ -552,10 +554,10 @@ def run_gpu(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "kernel": "commit microbench: IFFT + coset-LDE NTT passes "
                                                    "(k_ntt_pass_a / k_ntt_pass_b_*)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the four NTT launches of one commit,
-                         # from the ncu --set full capture profiles/r1_ntt_fused_ncu_full.txt (two passes over
-                         # HBM: 3.7x the algorithmic bytes - the second pass re-reads and re-writes the LDE)
-                         "traffic": NTT_DRAM_BYTES_PER_COMMIT, "traffic_source": "profiles/r1_ntt_fused_ncu_full.txt",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the four NTT launches of one commit
+                         # (two passes over HBM: 2.9x the algorithmic bytes - the second pass re-reads and
+                         # re-writes the LDE; the kernels are integer-issue-bound, not HBM-bound)
+                         "traffic": NTT_DRAM_BYTES_PER_COMMIT, "traffic_source": "profiles/r1_ntt_v2_ncu_full.txt",
                          "peak_source": peak_src, "algorithmic_bytes": alg["ntt_bytes"],
                          "stage_ms": ntt_ms,
                          "note": "the north star's split: HBM roofline for the NTT/transpose stages (integer-issue-bound "
@@ -568,7 +570,8 @@ def run_gpu(args, rank, local_rank, world):
                              "peak_source": "measured here: IMAD.WIDE.U32 (32x32+64, the instruction the field "
                                             "multiply and the MDS layer issue) on 8 independent accumulator chains "
                                             "per thread, SASS-checked; 6612 such multiplies per permutation is the "
-                                            "algorithmic minimum (SURVEY 8(d))",
+                                            "algorithmic count of SURVEY 8(d) (its 2304 small-constant MDS "
+                                            "multiplies now execute as DFMA on the FP64 pipe)",
                              "peak_imad_32bit": imad_lo / 1e12, "permutations": alg["perms"],
                              "traffic": LEAF_HASH_DRAM_BYTES_PER_COMMIT,
                              "perms_per_s": alg["perms"] / (hash_ms * 1e-3), "stage_ms": hash_ms},
