@@ -24,6 +24,13 @@ __constant__ u64 c_fast_rc[22];
 __constant__ u64 c_fast_init[121];
 __constant__ u64 c_fast_w_hat[242];
 __constant__ u64 c_fast_v[242];
+// The sparse tables of the permutation kernels: the same derivation for the partial rounds that remain sparse
+// when the first PV_DENSE_PARTIAL of them run in the textbook form (equal to c_fast_* when that is 0; the
+// quotient kernel's PoseidonGate always evaluates the all-sparse form, whose s-box inputs are its wires).
+__constant__ u64 c_h_rc[22];
+__constant__ u64 c_h_init[121];
+__constant__ u64 c_h_w_hat[242];
+__constant__ u64 c_h_v[242];
 // Kept in constant memory (not literals) on purpose: with literal multipliers nvcc strength-reduces
 // every c*x into shift/add chains on the already saturated ALU pipe; as constant-bank operands they
 // stay single IMAD.WIDE instructions.
@@ -114,19 +121,30 @@ GL_DEV void mad_wide(u32& lo, u32& hi, u32 a, u32 b) {
 // on the way in, 288 DFMA per layer. (The first version cut the state into three 22-bit limbs so that each
 // sum fitted one 32-bit word: 432 DFMA, 72 conversions and a three-way stitch per layer.)
 __constant__ double c_mds_circ_d[12];
+__constant__ double c_mds_half_d[12];  // (c[i] + c[i+6]) / 2 for i < 6, then (c[i] - c[i+6]) / 2
 #ifndef PV_RC_FOLD
 #define PV_RC_FOLD 1
 #endif
 // With PV_RC_FOLD the layer also adds the constants of the round that follows it (poseidon_next_rc_f64):
 // they enter as the accumulators' initial values, which costs nothing, and the 64-bit modular additions at
 // the head of the next round disappear.
-__constant__ double c_mds_next_rc_d[8][2][12];
+__constant__ double c_mds_next_rc_d[30][2][12];
 GL_DEV double u32_to_f64(u32 v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 GL_DEV void f64_to_u52(double d, u32& lo, u32& hi) {
   const double t = d + 4503599627370496.0;
   lo = (u32)__double2loint(t);
   hi = (u32)__double2hiint(t) & 0xFFFFFu;
 }
+// The 12x12 circulant product itself is split once by z^12 - 1 = (z^6 - 1)(z^6 + 1): with s = x_lo + x_hi and
+// d = x_lo - x_hi (x_lo = x[0..5], x_hi = x[6..11]), U = cyclic_6(s, (c_lo + c_hi)/2) and V = negacyclic_6(d,
+// (c_lo - c_hi)/2) give y[r] = U[r] + V[r] and y[r+6] = U[r] - V[r]: 12 + 72 + 12 FP64 operations per plane
+// instead of 144. The halved constants are integers for this matrix ({15,14,40,17,18,24}, {2,1,1,-1,-16,4}),
+// intermediate values are signed integers below 2^41 in magnitude (constants: half-integers below 2^33), so
+// everything stays exact. The folded round constants enter through U and V: U starts from
+// (rc[r] + rc[r+6])/2, V from (rc[r] - rc[r+6])/2.
+#ifndef PV_MDS_SPLIT
+#define PV_MDS_SPLIT 1
+#endif
 GL_DEV void mds_layer_f64(u64 (&s)[12], int layer) {
   u32 S[2][2][12];  // [half][word][lane]: sum over the low / high halves, each < 2^41 (+ 2^32 of constants)
 #pragma unroll
@@ -134,6 +152,32 @@ GL_DEV void mds_layer_f64(u64 (&s)[12], int layer) {
     double d[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) d[i] = u32_to_f64(k == 0 ? (u32)s[i] : (u32)(s[i] >> 32));
+#if PV_MDS_SPLIT
+    double sm[6], df[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      sm[j] = d[j] + d[j + 6];
+      df[j] = d[j] - d[j + 6];
+    }
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#if PV_RC_FOLD
+      const double c0 = c_mds_next_rc_d[layer][k][r], c6 = c_mds_next_rc_d[layer][k][r + 6];  // (rc[r] +- rc[r+6]) / 2
+      double u = c0, v = c6;
+#else
+      double u = 0.0, v = 0.0;
+#endif
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        u = fma(sm[(i + r) % 6], c_mds_half_d[i], u);
+        v = fma(df[(i + r) % 6], i + r < 6 ? c_mds_half_d[6 + i] : -c_mds_half_d[6 + i], v);
+      }
+      double y0 = u + v, y6 = u - v;
+      if (r == 0) y0 = fma(d[0], 8.0, y0);
+      f64_to_u52(y0, S[k][0][r], S[k][1][r]);
+      f64_to_u52(y6, S[k][0][r + 6], S[k][1][r + 6]);
+    }
+#else
 #pragma unroll
     for (int r = 0; r < 12; r++) {
 #if PV_RC_FOLD
@@ -146,6 +190,7 @@ GL_DEV void mds_layer_f64(u64 (&s)[12], int layer) {
       for (int i = 0; i < 12; i++) acc = fma(d[(i + r) % 12], c_mds_circ_d[i], acc);
       f64_to_u52(acc, S[k][0][r], S[k][1][r]);
     }
+#endif
   }
 #pragma unroll
   for (int r = 0; r < 12; r++) s[r] = mds_combine(S[0][0][r], S[0][1][r], S[1][0][r], S[1][1][r]);
@@ -196,24 +241,6 @@ GL_DEV void sbox_layer(u64 (&s)[12], const u64* __restrict__ rc) {
     for (int j = 0; j < LANES; j++) s[12 - LANES + j] = t[j];
   }
 }
-// layer = index of the full round among the 8 (selects the constants the FP64 MDS adds for the next round)
-GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc, int layer) {
-#if PV_MDS_F64 && PV_RC_FOLD
-  if (layer == 0 || layer == 4) {  // the rounds not preceded by an FP64 MDS layer
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[i]);
-  }
-  sbox_layer<false>(s, rc);
-  mds_layer_f64(s, layer);
-#elif PV_MDS_F64
-  sbox_layer<true>(s, rc);
-  mds_layer_f64(s, layer);
-#else
-  sbox_layer<true>(s, rc);
-  mds_layer_int(s);
-#endif
-}
-
 #ifndef PV_INIT_UNROLL
 #define PV_INIT_UNROLL 1
 #endif
@@ -228,7 +255,9 @@ GL_DEV void full_round(u64 (&s)[12], const u64* __restrict__ rc, int layer) {
 // mds_partial_layer_init of the sparse partial-round form: out[c] = sum_r in[r] * init[r-1][c-1] for
 // c = 1..11 (11x11, 64-bit entries), one trip per output lane. Also used by the quotient kernel's
 // PoseidonGate. Every caller runs 128-thread blocks.
+template <bool HYBRID_TABLES>
 GL_DEV void partial_init_layer(u64 (&s)[12]) {
+  const u64* init = HYBRID_TABLES ? c_h_init : c_fast_init;
 #if PV_INIT_SMEM
   // Outputs are parked in shared memory (one column per thread, conflict-free) until all 11 are done: a
   // store per trip and 11 loads at the end, instead of shifting an 11-word register file every trip
@@ -239,7 +268,7 @@ GL_DEV void partial_init_layer(u64 (&s)[12]) {
     Acc160 a;
     acc_init(a);
 #pragma unroll
-    for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
+    for (int r = 1; r < 12; r++) acc_mac(a, s[r], init[(r - 1) * 11 + c]);
     sh_o[c][threadIdx.x] = acc_reduce(a);
   }
 #pragma unroll
@@ -252,7 +281,7 @@ GL_DEV void partial_init_layer(u64 (&s)[12]) {
     Acc160 a;
     acc_init(a);
 #pragma unroll
-    for (int r = 1; r < 12; r++) acc_mac(a, s[r], c_fast_init[(r - 1) * 11 + c]);
+    for (int r = 1; r < 12; r++) acc_mac(a, s[r], init[(r - 1) * 11 + c]);
 #pragma unroll
     for (int i = 0; i < 10; i++) o[i] = o[i + 1];
     o[10] = acc_reduce(a);
@@ -262,36 +291,72 @@ GL_DEV void partial_init_layer(u64 (&s)[12]) {
 #endif
 }
 
-GL_DEV void partial_rounds(u64 (&s)[12]) {
-#if !(PV_MDS_F64 && PV_RC_FOLD)  // otherwise the MDS layer of the 4th full round added them
+// The partial rounds that run in the sparse form (the last 22 - PV_DENSE_PARTIAL of them): initial layer, then
+// per round one s-box, one 12-term dot product with a single fold, 11 fused multiply-adds.
+#ifndef PV_DENSE_PARTIAL
+#define PV_DENSE_PARTIAL 0
+#endif
+GL_DEV void sparse_partial_rounds(u64 (&s)[12]) {
+#if !(PV_MDS_F64 && PV_RC_FOLD)  // otherwise the MDS layer before them added the first constants
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
 #endif
-  partial_init_layer(s);
+  partial_init_layer<true>(s);
 PV_UNROLL(PV_PARTIAL_UNROLL)
-  for (int r = 0; r < 22; r++) {
+  for (int r = 0; r < 22 - PV_DENSE_PARTIAL; r++) {
     u64 s0 = sbox7(s[0]);
-    s0 = gl_add_c(s0, c_fast_rc[r]);  // entry 21 is zero
+    s0 = gl_add_c(s0, c_h_rc[r]);  // the last entry is zero
     Acc160 a;
     acc_init(a);
     acc_mac(a, s0, 25);  // MDS[0][0] = 17 + 8
 #pragma unroll
-    for (int i = 1; i < 12; i++) acc_mac(a, s[i], c_fast_w_hat[r * 11 + i - 1]);
+    for (int i = 1; i < 12; i++) acc_mac(a, s[i], c_h_w_hat[r * 11 + i - 1]);
 #pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = gl_mad(s0, c_fast_v[r * 11 + i - 1], s[i]);
+    for (int i = 1; i < 12; i++) s[i] = gl_mad(s0, c_h_v[r * 11 + i - 1], s[i]);
     s[0] = acc_reduce(a);
   }
 }
 
 // In-place permutation; inputs may be any u64 representatives, outputs likewise (not canonical).
-// Both halves of full rounds share one copy of the round body (see the I-cache note above).
+// One copy of the round body (s-boxes + MDS) serves the first four full rounds, the PV_DENSE_PARTIAL dense
+// partial rounds (s-box on lane 0 only) and the last four full rounds (see the I-cache note above).
+//
+// Why dense partial rounds at all: a sparse partial round is 23 multiplications by 64-bit constants = 92
+// IMAD.WIDE on the multiplier pipe, the pipe the whole permutation is bound by; the textbook round is one
+// s-box and the small-entry MDS, which runs as 288 DFMA on the otherwise idle FP64 pipe (and adds the next
+// round's constants for free). Moving some of the 22 rounds over balances the two pipes.
 GL_DEV void poseidon_permute(u64 (&s)[12]) {
+#if PV_MDS_F64 && PV_RC_FOLD
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    const u64* rc = c_rc + 12 * 26 * half;  // the rounds not preceded by an FP64 MDS layer add their constants
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[i]);
+    const int nrounds = half ? 4 : 4 + PV_DENSE_PARTIAL, layer0 = half ? 4 + PV_DENSE_PARTIAL : 0;
+#pragma unroll 1
+    for (int r = 0; r < nrounds; r++) {
+      if (r < 4) sbox_layer<false>(s, rc);
+      else s[0] = sbox7(s[0]);
+      mds_layer_f64(s, layer0 + r);
+    }
+    if (half == 0) sparse_partial_rounds(s);
+  }
+#else
+  static_assert(PV_DENSE_PARTIAL == 0, "dense partial rounds need the FP64 MDS with folded constants");
 #pragma unroll 1
   for (int half = 0; half < 2; half++) {
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) full_round(s, c_rc + 12 * (26 * half + r), 4 * half + r);
-    if (half == 0) partial_rounds(s);
+    for (int r = 0; r < 4; r++) {
+      sbox_layer<true>(s, c_rc + 12 * (26 * half + r));
+#if PV_MDS_F64
+      mds_layer_f64(s, 0);
+#else
+      mds_layer_int(s);
+#endif
+    }
+    if (half == 0) sparse_partial_rounds(s);
   }
+#endif
 }
 
 

@@ -21,6 +21,10 @@ struct PoseidonTablesHost {
   u64 fast_init[121];  // [r-1][c-1], out[c] += in[r] * init
   u64 fast_w_hat[242]; // [round][i-1]
   u64 fast_v[242];     // [round][i-1]
+  // The same sparse tables for a permutation whose first `dense` partial rounds run in the textbook form
+  // (constants, s-box on lane 0, dense MDS) and only the remaining 22 - dense in the sparse form.
+  int dense;
+  u64 h_first[12], h_rc[22], h_init[121], h_w_hat[242], h_v[242];
 };
 
 static const u64 kMdsCirc[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -121,7 +125,61 @@ static inline Mx mx_inv(Mx A, int n) {  // Gauss-Jordan
 
 }  // namespace detail
 
-static inline void build_poseidon_tables(PoseidonTablesHost* T) {
+// Sparse form of the partial rounds 4 + D .. 25 (D = number of leading partial rounds kept dense):
+// first[12] replaces the constants of round 4 + D, frc[r] is added to lane 0 after the s-box of sparse round r,
+// init is the 11x11 matrix applied before the first sparse round, w_hat / v the per-round sparse factors.
+static inline void build_sparse_tables(const u64* rc, const detail::Mx& Mt, const detail::Mx& Minv, int D, u64* first,
+                                       u64* frc, u64* init, u64* w_hat, u64* vv) {
+  using namespace detail;
+  const int W = 12, R = 22 - D, p0 = 4 + D;
+  // Equivalent round constants for the sparse rounds (rounds p0..25).
+  u64 c[30][12];
+  memcpy(c, rc, sizeof c);
+  for (int i = 24; i >= p0; i--) {
+    u64 t[12];
+    for (int r = 0; r < W; r++) {
+      u64 s = 0;
+      for (int k = 0; k < W; k++) s = glh::add(s, glh::mul(Minv[r * W + k], c[i + 1][k]));
+      t[r] = s;
+    }
+    for (int k = 1; k < W; k++) c[i][k] = glh::add(c[i][k], t[k]);
+    memset(c[i + 1], 0, sizeof c[i + 1]);
+    c[i + 1][0] = t[0];
+  }
+  memcpy(first, c[p0], 12 * sizeof(u64));
+  for (int r = 0; r < 22; r++) frc[r] = r < R - 1 ? c[p0 + 1 + r][0] : 0;
+
+  // Sparse factorisation, walking the rounds backwards.
+  Mx Mmul = Mt;
+  for (int i = R - 1; i >= 0; i--) {
+    Mx Mhat(11 * 11), w(11), v(11);
+    for (int a = 0; a < 11; a++) {
+      for (int b = 0; b < 11; b++) Mhat[a * 11 + b] = Mmul[(a + 1) * W + (b + 1)];
+      w[a] = Mmul[(a + 1) * W + 0];
+      v[a] = Mmul[0 * W + (a + 1)];
+    }
+    Mx MhatInv = mx_inv(Mhat, 11);
+    for (int a = 0; a < 11; a++) {
+      u64 s = 0;
+      for (int b = 0; b < 11; b++) s = glh::add(s, glh::mul(MhatInv[a * 11 + b], w[b]));
+      w_hat[i * 11 + a] = s;
+      vv[i * 11 + a] = v[a];
+    }
+    Mx Mi(W * W, 0);
+    Mi[0] = 1;
+    for (int a = 0; a < 11; a++)
+      for (int b = 0; b < 11; b++) Mi[(a + 1) * W + (b + 1)] = Mhat[a * 11 + b];
+    if (i > 0) {
+      Mmul = mx_mul(Mt, Mi, W);
+    } else {
+      // state_row * Mi is applied before the first sparse round
+      for (int a = 0; a < 11; a++)
+        for (int b = 0; b < 11; b++) init[a * 11 + b] = Mhat[a * 11 + b];
+    }
+  }
+}
+
+static inline void build_poseidon_tables(PoseidonTablesHost* T, int dense = 0) {
   using namespace detail;
   typedef unsigned __int128 u128;
   // 360 x gen_range(0..p) (rand 0.8 widening-multiply rejection sampling; zone = p - 1)
@@ -146,66 +204,44 @@ static inline void build_poseidon_tables(PoseidonTablesHost* T) {
     for (int c = 0; c < W; c++) M[r * W + c] = Mt[c * W + r];
   Mx Minv = mx_inv(M, W);
 
-  // Equivalent round constants for the 22 partial rounds (rounds 4..25).
-  u64 c[30][12];
-  memcpy(c, T->rc, sizeof c);
-  for (int i = 24; i >= 4; i--) {
-    u64 t[12];
-    for (int r = 0; r < W; r++) {
-      u64 s = 0;
-      for (int k = 0; k < W; k++) s = glh::add(s, glh::mul(Minv[r * W + k], c[i + 1][k]));
-      t[r] = s;
-    }
-    for (int k = 1; k < W; k++) c[i][k] = glh::add(c[i][k], t[k]);
-    memset(c[i + 1], 0, sizeof c[i + 1]);
-    c[i + 1][0] = t[0];
-  }
-  memcpy(T->fast_first, c[4], sizeof T->fast_first);
-  for (int r = 0; r < 22; r++) T->fast_rc[r] = r < 21 ? c[5 + r][0] : 0;
-
-  // Sparse factorisation, walking the rounds backwards.
-  Mx Mmul = Mt;
-  for (int i = 21; i >= 0; i--) {
-    Mx Mhat(11 * 11), w(11), v(11);
-    for (int a = 0; a < 11; a++) {
-      for (int b = 0; b < 11; b++) Mhat[a * 11 + b] = Mmul[(a + 1) * W + (b + 1)];
-      w[a] = Mmul[(a + 1) * W + 0];
-      v[a] = Mmul[0 * W + (a + 1)];
-    }
-    Mx MhatInv = mx_inv(Mhat, 11);
-    for (int a = 0; a < 11; a++) {
-      u64 s = 0;
-      for (int b = 0; b < 11; b++) s = glh::add(s, glh::mul(MhatInv[a * 11 + b], w[b]));
-      T->fast_w_hat[i * 11 + a] = s;
-      T->fast_v[i * 11 + a] = v[a];
-    }
-    Mx Mi(W * W, 0);
-    Mi[0] = 1;
-    for (int a = 0; a < 11; a++)
-      for (int b = 0; b < 11; b++) Mi[(a + 1) * W + (b + 1)] = Mhat[a * 11 + b];
-    if (i > 0) {
-      Mmul = mx_mul(Mt, Mi, W);
-    } else {
-      // state_row * Mi is applied before the first partial round
-      for (int a = 0; a < 11; a++)
-        for (int b = 0; b < 11; b++) T->fast_init[a * 11 + b] = Mhat[a * 11 + b];
-    }
-  }
+  build_sparse_tables(T->rc, Mt, Minv, 0, T->fast_first, T->fast_rc, T->fast_init, T->fast_w_hat, T->fast_v);
+  T->dense = dense;
+  build_sparse_tables(T->rc, Mt, Minv, dense, T->h_first, T->h_rc, T->h_init, T->h_w_hat, T->h_v);
 }
 
-// Constants added by the FP64 MDS layer of full round j (0..7, both halves) on behalf of the round that
-// follows it, as the 32-bit halves of each word in doubles: [j][half][lane]. Layers 0-2 and 4-6 carry the
-// next full round's constants, layer 3 the first constants of the partial rounds, layer 7 zeros.
-static inline void poseidon_next_rc_f64(const PoseidonTablesHost& T, double (*out)[2][12]) {
-  for (int j = 0; j < 8; j++)
+// Constants added by FP64 MDS layer L on behalf of the round that follows it, as the 32-bit halves of each word
+// in doubles: [L][half][lane]. Layers 0..3 are the first four full rounds, 4..3+D the dense partial rounds,
+// 4+D..7+D the last four full rounds. Every layer carries the next round's constants; the last layer before the
+// sparse rounds carries their `first` constants; layer 3+D... the very last layer carries zeros. (The first
+// round of each block of full rounds that follows sparse rounds adds its own constants.)
+#define QPZK_MDS_LAYERS_MAX 30
+static inline void poseidon_next_rc_f64(const PoseidonTablesHost& T, double (*out)[2][12], bool split) {
+  const int D = T.dense;
+  for (int L = 0; L < QPZK_MDS_LAYERS_MAX; L++)
     for (int i = 0; i < 12; i++) {
       u64 c = 0;
-      if (j < 3) c = T.rc[12 * (j + 1) + i];
-      else if (j == 3) c = T.fast_first[i];
-      else if (j < 7) c = T.rc[12 * (26 + (j - 4) + 1) + i];
-      out[j][0][i] = (double)(uint32_t)c;
-      out[j][1][i] = (double)(uint32_t)(c >> 32);
+      if (L < 3 + D) c = T.rc[12 * (L + 1) + i];                  // next full / dense partial round
+      else if (L == 3 + D) c = D == 22 ? T.rc[12 * 26 + i] : T.h_first[i];  // first sparse round (or round 26)
+      else if (L < 7 + D) c = T.rc[12 * (26 + (L - 4 - D) + 1) + i];
+      out[L][0][i] = (double)(uint32_t)c;
+      out[L][1][i] = (double)(uint32_t)(c >> 32);
     }
+  // the split MDS layer (poseidon.cuh) wants (rc[r] + rc[r+6]) / 2 in slot r and (rc[r] - rc[r+6]) / 2 in slot r+6
+  if (split)
+    for (int L = 0; L < QPZK_MDS_LAYERS_MAX; L++)
+      for (int k = 0; k < 2; k++)
+        for (int r = 0; r < 6; r++) {
+          double a = out[L][k][r], b = out[L][k][r + 6];
+          out[L][k][r] = 0.5 * (a + b);
+          out[L][k][r + 6] = 0.5 * (a - b);
+        }
+}
+// (c[i] + c[i+6]) / 2, i < 6, then (c[i] - c[i+6]) / 2: the constants of the split circulant product
+static inline void poseidon_mds_half_f64(double* out) {
+  for (int i = 0; i < 6; i++) {
+    out[i] = 0.5 * ((double)kMdsCirc[i] + (double)kMdsCirc[i + 6]);
+    out[6 + i] = 0.5 * ((double)kMdsCirc[i] - (double)kMdsCirc[i + 6]);
+  }
 }
 
 }  // namespace qpzk

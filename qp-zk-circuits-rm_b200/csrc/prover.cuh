@@ -247,11 +247,11 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer_f64(s, 7);  // layer 7: no constants folded in
+    mds_layer_f64(s, 29);  // layer 29: no constants folded in
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
-  partial_init_layer(s);
+  partial_init_layer<false>(s);
   u64 in_next = nx[0];  // wire 65
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
@@ -294,7 +294,7 @@ GL_DEV void poseidon_gate_eval(const WireRow& w, AlphaAcc& a) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = t[0]; s[9] = t[1]; s[10] = t[2]; s[11] = t[3];
     }
-    mds_layer_f64(s, 7);
+    mds_layer_f64(s, 29);
   }
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {

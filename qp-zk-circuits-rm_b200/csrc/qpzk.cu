@@ -409,7 +409,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
     static PoseidonTablesHost* T = nullptr;
     if (!T) {
       T = new PoseidonTablesHost();
-      build_poseidon_tables(T);
+      build_poseidon_tables(T, PV_DENSE_PARTIAL);
     }
     if (device < 64 && !device_ready[device]) {
       CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
@@ -419,6 +419,10 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
       CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
       CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
       CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
+      CU(cudaMemcpyToSymbol(c_h_rc, T->h_rc, sizeof T->h_rc));
+      CU(cudaMemcpyToSymbol(c_h_init, T->h_init, sizeof T->h_init));
+      CU(cudaMemcpyToSymbol(c_h_w_hat, T->h_w_hat, sizeof T->h_w_hat));
+      CU(cudaMemcpyToSymbol(c_h_v, T->h_v, sizeof T->h_v));
       u32 circ[12];
       for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
       u32 diag0 = (u32)kMdsDiag0;
@@ -428,8 +432,11 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
       double circ_d[12];
       for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
       CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
-      static double next_rc[8][2][12];
-      poseidon_next_rc_f64(*T, next_rc);
+      static double next_rc[QPZK_MDS_LAYERS_MAX][2][12];
+      poseidon_next_rc_f64(*T, next_rc, PV_MDS_SPLIT != 0);
+      static double half_d[12];
+      poseidon_mds_half_f64(half_d);
+      CU(cudaMemcpyToSymbol(c_mds_half_d, half_d, sizeof half_d));
       CU(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
 #endif
       // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default

@@ -60,7 +60,7 @@ static void host_permute(const PoseidonTablesHost& T, u64* s) {
 
 int main(int argc, char** argv) {
   PoseidonTablesHost* T = new PoseidonTablesHost();
-  build_poseidon_tables(T);
+  build_poseidon_tables(T, PV_DENSE_PARTIAL);
   {  // validate the host reference itself (SURVEY App. A.2 KAT)
     u64 z[12] = {0};
     host_permute(*T, z);
@@ -74,6 +74,10 @@ int main(int argc, char** argv) {
   CK(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
   CK(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
   CK(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
+  CK(cudaMemcpyToSymbol(c_h_rc, T->h_rc, sizeof T->h_rc));
+  CK(cudaMemcpyToSymbol(c_h_init, T->h_init, sizeof T->h_init));
+  CK(cudaMemcpyToSymbol(c_h_w_hat, T->h_w_hat, sizeof T->h_w_hat));
+  CK(cudaMemcpyToSymbol(c_h_v, T->h_v, sizeof T->h_v));
   u32 circ[12];
   for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
   u32 diag0 = (u32)kMdsDiag0;
@@ -84,8 +88,11 @@ int main(int argc, char** argv) {
     double cd[12];
     for (int i = 0; i < 12; i++) cd[i] = (double)kMdsCirc[i];
     CK(cudaMemcpyToSymbol(c_mds_circ_d, cd, sizeof cd));
-    static double next_rc[8][2][12];
-    poseidon_next_rc_f64(*T, next_rc);
+    static double next_rc[QPZK_MDS_LAYERS_MAX][2][12];
+    poseidon_next_rc_f64(*T, next_rc, PV_MDS_SPLIT != 0);
+      static double half_d[12];
+      poseidon_mds_half_f64(half_d);
+      CK(cudaMemcpyToSymbol(c_mds_half_d, half_d, sizeof half_d));
     CK(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
   }
 #endif
