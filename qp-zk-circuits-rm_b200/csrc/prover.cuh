@@ -551,20 +551,48 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
         for (u32 t = 0; t < 4; t++) aa_emit(a, gl_sub(w[t], pi_hash[t]));
         break;
       case G_BASE_SUM_2: {
+        // One pass from the top limb down, eight limbs requested at a time (fetched one by one the Horner
+        // chain waited for every load). Term 0 is the sum check, term 1 + t the range check of limb t: the
+        // alpha-power table lets each go straight to its slot.
         const u32 nl = d.gate_param[g];
+        const u32 t0 = a.t;
+        const u64 w0 = w[0];
         u64 sum = 0;
-        for (int t = (int)nl - 1; t >= 0; t--) sum = gl_add(gl_add(sum, sum), w[1 + t]);
-        aa_emit(a, gl_sub(sum, w[0]));
-        for (u32 t = 0; t < nl; t++) {
+        int t = (int)nl - 1;
+        for (; t >= 7; t -= 8) {
+          u64 l[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) l[e] = w[1 + t - e];
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            sum = gl_add(gl_add(sum, sum), l[e]);
+            a.t = t0 + 1 + (u32)(t - e);
+            aa_emit(a, gl_mul(l[e], gl_sub(l[e], 1)));
+          }
+        }
+        for (; t >= 0; t--) {
           u64 l = w[1 + t];
+          sum = gl_add(gl_add(sum, sum), l);
+          a.t = t0 + 1 + (u32)t;
           aa_emit(a, gl_mul(l, gl_sub(l, 1)));
         }
+        a.t = t0;
+        aa_emit(a, gl_sub(sum, w0));
+        a.t = t0 + 1 + nl;
         break;
       }
       case G_ARITHMETIC: {
         const u64 c0 = cs[d.num_selectors], c1 = cs[d.num_selectors + 1];
-        for (u32 t = 0; t < d.gate_param[g]; t++) {
-          u64 m0 = w[4 * t], m1 = w[4 * t + 1], ad = w[4 * t + 2], o = w[4 * t + 3];
+        const u32 nops = d.gate_param[g];
+        u64 nx[4];  // the next operation's wires, requested one operation ahead
+#pragma unroll
+        for (int e = 0; e < 4; e++) nx[e] = w[e];
+        for (u32 t = 0; t < nops; t++) {
+          const u64 m0 = nx[0], m1 = nx[1], ad = nx[2], o = nx[3];
+          if (t + 1 < nops) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) nx[e] = w[4 * (t + 1) + e];
+          }
           u64 comp = gl_mad(gl_mul(m0, m1), c0, gl_mul(ad, c1));
           aa_emit(a, gl_sub(o, comp));
         }
