@@ -483,19 +483,25 @@ def run_gpu(args, rank, local_rank, world):
                       "note": "gate definitions restated from upstream plonky2, not pinned by a reference fixture"}
         for q in acircs:
             q.free()
-        # a flat 16-ary aggregation node is ~2^16 rows: single-proof latency at that degree
-        bk = 16
-        bc = synth.build_recursion(bk, zk=True, seed=10, provider=synth.GpuProvider(ctx0))
-        bcirc = qpzk.Circuit(ctx0, bc["common"], bc["digest"], bc["constants_sigmas"])
-        blat = []
-        for i in range(4):
-            t0 = time.perf_counter()
-            bproof = bcirc.prove(bc["wires"], bc["public_inputs"], bc["salts"])
-            if i:
-                blat.append((time.perf_counter() - t0) * 1e3)
-        aggregator["flat_node_2^%d_rows" % bk] = {"latency_ms_median": float(np.median(blat)), "proof_bytes": len(bproof),
-                                                  "stage_ms": bcirc.stage_ms()}
-        bcirc.free()
+        # a flat 16-ary aggregation node is ~2^16 rows, BASELINE configs[4] quotes ~2^17-2^18:
+        # single-proof latency at 2^16, 2^17 and 2^18 rows, each proof accepted by the restated verifier
+        from oracle import oracle as orc  # the checker: the restated plonky2 verifier
+        for bk in (16, 17, 18):
+            bc = synth.build_recursion(bk, zk=True, seed=10, provider=synth.GpuProvider(ctx0))
+            bcirc = qpzk.Circuit(ctx0, bc["common"], bc["digest"], bc["constants_sigmas"])
+            blat = []
+            for i in range(4):
+                t0 = time.perf_counter()
+                bproof = bcirc.prove(bc["wires"], bc["public_inputs"], bc["salts"])
+                if i:
+                    blat.append((time.perf_counter() - t0) * 1e3)
+            rc, _ = orc.verify(bc["common"], bcirc.verifier_only_bytes(), bproof)
+            if rc != 0:
+                raise SystemExit("2^%d-row recursion-shaped proof rejected by the restated verifier (rc %d)" % (bk, rc))
+            aggregator["flat_node_2^%d_rows" % bk] = {"latency_ms_median": float(np.median(blat)), "proof_bytes": len(bproof),
+                                                      "verifier_accepts": True, "stage_ms": bcirc.stage_ms()}
+            bcirc.free()
+            del bc
 
     sharded = None
     if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:

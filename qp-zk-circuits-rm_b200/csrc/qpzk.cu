@@ -270,7 +270,7 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
   QP(get_root_tab(c, k, true, &tab));
   u64 ninv = glh::inv(((u64)1 << k) % GL_P);
   if (k <= kSmallMaxLog) return launch_small<true>(c, values, src_stride, coeffs, dst_stride, nullptr, tab, ncols, 1, k, 0, ninv, 0);
-  if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "from_values: degree_bits > 20 not supported");
+  if (k > 22) return fail(QPZK_ERR_UNSUPPORTED, "ifft: more than 2^22 points not supported");
   int a = (k + 1) / 2, b = k - a;
   const u64* twm;
   QP(get_tw_matrix(c, k, a, true, &twm));
