@@ -78,6 +78,26 @@ def test_gpu_recursion_proof_matches_oracle(k, zk):
     ctx.close()
 
 
+@pytest.mark.gpu
+def test_gpu_recursion_proof_of_2p18_rows_is_accepted():
+    """BASELINE configs[4] quotes aggregation nodes of degree ~2^17-2^18: the largest of them through
+    `qpzk_prove` (a 2^21-point quotient domain, the two-pass IFFT beyond 2^20 points) and the restated verifier.
+    Too large for the CPU oracle prover in a test, so acceptance and tamper-rejection are the checks."""
+    import qpzk
+    ctx = qpzk.Context(0)
+    circ = synth.build_recursion(18, zk=True, seed=48, provider=synth.GpuProvider(ctx))
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    proof = gc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
+    rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), proof)
+    assert rc == 0
+    w = circ["wires"].copy()
+    w[36, int(np.where(circ["gate"] == synth.R_COSET)[0][-1])] ^= np.uint64(1)
+    rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), gc.prove(w, circ["public_inputs"], circ["salts"]))
+    assert rc != 0
+    gc.free()
+    ctx.close()
+
+
 # ---- what the gates MEAN (independent of wire order): the rows the builder fills, and the constraints accept,
 # compute the functions an in-circuit FRI verifier needs them for ----
 def _ext(w, r, i):
