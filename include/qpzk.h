@@ -17,10 +17,15 @@
  *    points take device pointers valid on the context's device.
  *  - Handles own device memory and are released with their *_free function.
  *  - Every function returns QPZK_OK (0) or a negative qpzk_status; nothing throws or aborts across
- *    the ABI. `qpzk_last_error` returns a human-readable message for the calling thread.
+ *    the ABI (every entry point that allocates runs inside an exception guard). `qpzk_last_error` returns a
+ *    human-readable message for the calling thread.
  *  - Re-entrant: one qpzk_ctx per calling thread (the aggregator proves chunks concurrently from
  *    rayon workers, /root/reference/wormhole/aggregator/src/circuits/tree.rs:92-103). A context
- *    owns one CUDA stream; calls on different contexts overlap on the device.
+ *    owns one CUDA stream; calls on different contexts overlap on the device. Handles (batches, trees,
+ *    circuits, FRI provers) belong to the context they were created on and must not be used from two
+ *    threads at once; a qpzk_circuit carries ONE proof at a time (its calls are serialised by a mutex).
+ *  - Device memory comes from the library's own stream-ordered pool (one per device); the device's default
+ *    pool and its attributes are not touched.
  *  - There is NO CPU fallback: if no CUDA device is usable, qpzk_ctx_create fails.
  */
 #ifndef QPZK_H
@@ -38,7 +43,8 @@ typedef enum qpzk_status {
   QPZK_ERR_BAD_ARG = -1,
   QPZK_ERR_CUDA = -2,
   QPZK_ERR_OOM = -3,
-  QPZK_ERR_NOT_DIVISIBLE = -4, /* quotient: vanishing polynomial not divisible by Z_H */
+  QPZK_ERR_NOT_DIVISIBLE = -4, /* reserved: the prover does not test divisibility by Z_H (an unsatisfied
+                                  witness yields a proof the verifier rejects, as in plonky2 release builds) */
   QPZK_ERR_UNSUPPORTED = -5
 } qpzk_status;
 
@@ -60,8 +66,9 @@ enum {
 };
 
 /* ---- context ---- */
-/* flags: how a call waits for its stream (the Fiat-Shamir transcript stays on the host, so one proof waits
- * about a dozen times). Default: spin on a host core - lowest latency, right when proving threads <= cores.
+/* flags: how a call waits for its stream (a proof is one stream-ordered enqueue - the Fiat-Shamir transcript
+ * runs on the device - so qpzk_prove waits once, at the end).
+ * Default: spin on a host core - lowest latency, right when proving threads <= cores.
  * QPZK_CTX_BLOCKING_SYNC - sleep on a blocking-sync event (interrupt wake-up, tens of microseconds each).
  * QPZK_CTX_YIELD_SYNC    - poll the event and sched_yield() between polls: spinning latency while cores are
  *                          free, and proving threads x processes may exceed the host cores (many rayon
@@ -145,8 +152,14 @@ int qpzk_batch_from_coeffs_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32
  * all-gathers the 2^cap_height x 32-byte subtree roots (NCCL on `qpzk_batch_cap_dev`, or on the host
  * followed by `qpzk_batch_set_cap`). The range must be a multiple of 2^(cap_height - rate_bits)
  * subtrees when cap_height > rate_bits (QPZK_ERR_UNSUPPORTED otherwise). Rows, Merkle paths and
- * `get_lde_values` are served for the owned leaves. */
+ * `get_lde_values` are served for the owned leaves ONLY: a shard allocates just its own rows, and
+ * qpzk_batch_open / _get_lde_rows return QPZK_ERR_BAD_ARG for a leaf of another rank (qpzk_batch_export
+ * refuses shards). salts_dev stays [salt_cols][N] in natural order on every rank. */
 int qpzk_batch_from_values_shard_dev(qpzk_ctx* ctx, const uint64_t* values_dev, uint32_t ncols,
+                                     uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                                     const uint64_t* salts_dev, uint32_t salt_cols,
+                                     uint32_t subtree_begin, uint32_t subtree_end, qpzk_batch** out);
+int qpzk_batch_from_coeffs_shard_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t ncols,
                                      uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                      const uint64_t* salts_dev, uint32_t salt_cols,
                                      uint32_t subtree_begin, uint32_t subtree_end, qpzk_batch** out);
@@ -184,14 +197,21 @@ void qpzk_batch_free(qpzk_batch* b);
  * digest and the constants|sigmas value columns ([num_constants + num_routed_wires][n], values on
  * the subgroup), performs the constants|sigmas commit ONCE and keeps everything device-resident for
  * every later proof of the same circuit. Supported gate set: Noop, Constant, PublicInput,
- * BaseSum<2>, Arithmetic, Poseidon (the wormhole and voting circuits); anything else returns
- * QPZK_ERR_UNSUPPORTED at creation. */
+ * BaseSum<2>, Arithmetic, Poseidon (the wormhole and voting circuits) and the recursion set
+ * ArithmeticExtension, MulExtension, PoseidonMds, RandomAccess, Reducing, ReducingExtension,
+ * Exponentiation, CosetInterpolation (aggregation nodes); anything else returns QPZK_ERR_UNSUPPORTED
+ * at creation. The common data is untrusted input: every count, index and size in it is range-checked
+ * before anything is launched, and constants_sigmas_words must equal
+ * (num_constants + num_routed_wires) << degree_bits (QPZK_ERR_BAD_ARG otherwise). */
 typedef struct qpzk_circuit qpzk_circuit;
 int qpzk_circuit_create(qpzk_ctx* ctx, const uint8_t* common_bytes, size_t common_len,
                         const uint64_t* circuit_digest /* [4] */, const uint64_t* constants_sigmas,
-                        qpzk_circuit** out);
-/* `verifier_only.constants_sigmas_cap`: [2^cap_height][4]. */
-int qpzk_circuit_cap(const qpzk_circuit* c, uint64_t* out);
+                        size_t constants_sigmas_words, qpzk_circuit** out);
+/* `verifier_only.constants_sigmas_cap`: [2^cap_height][4]; cap_words = capacity of `out` in u64. */
+int qpzk_circuit_cap(const qpzk_circuit* c, uint64_t* out, size_t cap_words);
+/* Shape of the circuit as parsed from the common data: out[0..8) = degree_bits, rate_bits, cap_height,
+ * num_wires, num_routed_wires, num_challenges, salt columns per blinded oracle (0 or 4), num_public_inputs. */
+int qpzk_circuit_info(const qpzk_circuit* c, uint32_t* out /* [8] */);
 /* `VerifierOnlyCircuitData::to_bytes()`; returns the length (writes only if it fits in cap). */
 size_t qpzk_circuit_verifier_only(const qpzk_circuit* c, uint8_t* out, size_t cap);
 void qpzk_circuit_free(qpzk_circuit* c);
@@ -204,11 +224,24 @@ void qpzk_circuit_free(qpzk_circuit* c);
  * [4][n << rate_bits] per blinded oracle. The proof-of-work witness is the
  * smallest valid one (the reference returns whichever a rayon worker finds first; any valid witness
  * verifies). flags bit 0: keep intermediates for qpzk_prove_trace; bit 1: `wires` and the salt
- * pointers are DEVICE pointers on the context's device (HBM-resident witness). */
-int qpzk_prove(qpzk_circuit* c, const uint64_t* wires, const uint64_t* public_inputs,
+ * pointers are DEVICE pointers on the context's device (HBM-resident witness).
+ * wires_words / salt_words: element counts of `wires` and of EACH salt array, checked against the circuit
+ * (num_wires << degree_bits, 4 << (degree_bits + rate_bits)).
+ * The whole proof is enqueued on the context's stream without a host round trip (the transcript is a
+ * device kernel, the challenges never leave HBM); the call waits once, at the end. */
+int qpzk_prove(qpzk_circuit* c, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
                uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
-               const uint64_t* salts_quotient, uint32_t flags, uint8_t* proof_out, size_t proof_cap,
-               size_t* proof_len);
+               const uint64_t* salts_quotient, size_t salt_words, uint32_t flags, uint8_t* proof_out,
+               size_t proof_cap, size_t* proof_len);
+/* The same in two halves, so that ONE host thread can keep several contexts busy (the aggregator's
+ * concurrent chunk proofs, /root/reference/wormhole/aggregator/src/circuits/tree.rs:92-103, without a
+ * thread per proof): qpzk_prove_begin enqueues the proof and returns; qpzk_prove_end waits for it and
+ * writes the bytes. One proof in flight per circuit handle; host input buffers must stay valid (and, for
+ * an asynchronous upload, pinned) until qpzk_prove_end returns. */
+int qpzk_prove_begin(qpzk_circuit* c, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+                     uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+                     const uint64_t* salts_quotient, size_t salt_words, uint32_t flags);
+int qpzk_prove_end(qpzk_circuit* c, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 /* Per-stage hooks for a fork that keeps plonky2's own `prove()` loop and transcript (integration depth (b),
  * INTEGRATION.md): the same device code qpzk_prove runs.
  * qpzk_zs_partial_products = `all_wires_permutation_partial_products` + the running product (qp-plonky2

@@ -107,6 +107,65 @@ GL_DEV u64 gl_mul(u64 a, u64 b) {
 }
 GL_DEV u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 
+// The same products spelled for a kernel whose limiter is the multiplier (FMA-heavy) pipe - Poseidon. On
+// sm_100a every IMAD.* form issues to that pipe: IMAD.WIDE / IMAD.HI hold it for 4 cycles per warp, IMAD,
+// IMAD.X and IMAD.MOV for 2. From the mad.lo.cc / madc.hi.cc chains of gl_mul_wide ptxas emits, per product,
+// 3 IMAD.WIDE + IMAD + IMAD.HI (the a1*b1 product split in two because its halves are not a register pair)
+// + IMAD.MOV + 2 IMAD.X = 24 pipe cycles, and it computes a0*a1 twice for a square (26 cycles). Here the
+// partial products are four (three for a square) independent mul.wide - IMAD.WIDE with a zero addend - and
+// every addition is an add.cc / addc chain that ptxas keeps on the ALU pipe as IADD3 / IADD3.X: 16 + 4 and
+// 12 + 2 pipe cycles with the same (mul) or a smaller (sqr: 18 against 20) instruction count.
+GL_DEV void gl_mul_wide_alu(u64 a, u64 b, u32& r0, u32& r1, u32& r2, u32& r3) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+  asm("{\n\t.reg .b64 p, q, s, t;\n\t.reg .b32 p1, q0, q1, s0, s1, t0, t1, m2;\n\t"
+      "mul.wide.u32 p, %4, %6;\n\t"
+      "mul.wide.u32 q, %4, %7;\n\t"
+      "mul.wide.u32 s, %5, %6;\n\t"
+      "mul.wide.u32 t, %5, %7;\n\t"
+      "mov.b64 {%0, p1}, p;\n\t"
+      "mov.b64 {q0, q1}, q;\n\t"
+      "mov.b64 {s0, s1}, s;\n\t"
+      "mov.b64 {t0, t1}, t;\n\t"
+      "add.cc.u32 q0, q0, s0;\n\t"
+      "addc.cc.u32 q1, q1, s1;\n\t"
+      "addc.u32 m2, 0, 0;\n\t"
+      "add.cc.u32 %1, p1, q0;\n\t"
+      "addc.cc.u32 %2, t0, q1;\n\t"
+      "addc.u32 %3, t1, m2;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+      : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+}
+GL_DEV void gl_sqr_wide_alu(u64 a, u32& r0, u32& r1, u32& r2, u32& r3) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+  asm("{\n\t.reg .b64 p, q, t;\n\t.reg .b32 p1, q0, q1, t0, t1, m0, m1, m2;\n\t"
+      "mul.wide.u32 p, %4, %4;\n\t"
+      "mul.wide.u32 q, %4, %5;\n\t"
+      "mul.wide.u32 t, %5, %5;\n\t"
+      "mov.b64 {%0, p1}, p;\n\t"
+      "mov.b64 {q0, q1}, q;\n\t"
+      "mov.b64 {t0, t1}, t;\n\t"
+      "shl.b32 m0, q0, 1;\n\t"              // 2*a0*a1 as 65 bits
+      "shf.l.wrap.b32 m1, q0, q1, 1;\n\t"
+      "shr.u32 m2, q1, 31;\n\t"
+      "add.cc.u32 %1, p1, m0;\n\t"
+      "addc.cc.u32 %2, t0, m1;\n\t"
+      "addc.u32 %3, t1, m2;\n\t"
+      "}"
+      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+      : "r"(a0), "r"(a1));
+}
+GL_DEV u64 gl_mul_alu(u64 a, u64 b) {
+  u32 r0, r1, r2, r3;
+  gl_mul_wide_alu(a, b, r0, r1, r2, r3);
+  return gl_reduce4(r0, r1, r2, r3);
+}
+GL_DEV u64 gl_sqr_alu(u64 a) {
+  u32 r0, r1, r2, r3;
+  gl_sqr_wide_alu(a, r0, r1, r2, r3);
+  return gl_reduce4(r0, r1, r2, r3);
+}
+
 // a*b + c, one reduction (a*b + c < 2^128 always). The addend rides on the first partial product:
 // (r1:r0) = a0*b0 + c is one IMAD.WIDE with carry-out, (r3:r2) = a1*b1 + carry one IMAD.WIDE.X.
 GL_DEV u64 gl_mad(u64 a, u64 b, u64 c) {
@@ -158,6 +217,21 @@ GL_DEV u64 gl_add_c(u64 a, u64 b_canon) {
       "addc.u32 c, 0, 0;\n\t"
       "mad.lo.cc.u32 %0, c, 0xffffffff, %0;\n\t"
       "madc.hi.u32 %1, c, 0xffffffff, %1;\n\t"
+      "}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(b0), "r"(b1));
+  return ((u64)a1 << 32) | a0;
+}
+// gl_add_c with both corrections on the ALU pipe (no IMAD / IMAD.HI by 2^32 - 1).
+GL_DEV u64 gl_add_c_alu(u64 a, u64 b_canon) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b_canon, b1 = (u32)(b_canon >> 32);
+  asm("{\n\t.reg .u32 c;\n\t"
+      "add.cc.u32 %0, %0, %2;\n\t"
+      "addc.cc.u32 %1, %1, %3;\n\t"
+      "addc.u32 c, 0, 0;\n\t"            // carry: + 2^64 == + EPS = + 2^32 - 1: low word - c, high word + c - borrow
+      "sub.cc.u32 %0, %0, c;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "add.u32 %1, %1, c;\n\t"
       "}"
       : "+r"(a0), "+r"(a1)
       : "r"(b0), "r"(b1));

@@ -62,40 +62,73 @@ k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
   o[1] = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
 }
 
-// ---- low-latency variants (16 lanes per row / node) for trees too small to fill the machine ----
+// ---- low-latency path (16 lanes per row / node) for trees and tree tops too small to fill the machine ----
+// ONE launch takes a subtree from its first level to the cap: a 16-lane group computes one node, then
+// bumps the arrival counter of its parent; the group that arrives second finds both children published
+// and goes on to compute the parent, the first one retires. There is no grid-wide barrier and no spinning,
+// so nothing has to be co-resident, and the dependent chain is exactly one permutation per level (the
+// per-level launches this replaces added a launch gap per level: 16 % of the GPU time of a proof sat in
+// ~1,300 such launches, profiles/r1_bench_launch_list_summary.txt). Counters are reset by the group that
+// consumes them, so one small per-context array serves every tree built on the context's stream.
 #define QPZK_COOP_THREADS 128
 #define QPZK_COOP_GROUPS (QPZK_COOP_THREADS / 16)
-__global__ void __launch_bounds__(QPZK_COOP_THREADS)
-k_leaf_hash_coop(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 width, u64 nrows,
-                 u64* __restrict__ digests) {
-  __shared__ u64 xch[QPZK_COOP_GROUPS][24];
-  const u32 g = threadIdx.x >> 4, lane = threadIdx.x & 15;
-  u64 row = (u64)blockIdx.x * QPZK_COOP_GROUPS + g;
-  const bool live = row < nrows;
-  if (!live) row = nrows - 1;  // keep the whole warp in the exchange; results are discarded
-  const u64* p = src + row * row_stride;
-  u64 s = 0;
-  if (width <= 4) {  // hash_or_noop: short rows are copied, zero padded
-    if (lane < width) s = p[lane * col_stride];
-  } else {
-    for (u32 off = 0; off < width; off += 8) {
-      if (lane < 8 && off + lane < width) s = __ldg(p + (u64)(off + lane) * col_stride);  // overwrite-mode absorb
-      s = poseidon_permute_coop(s, lane, xch[g]);
-    }
-  }
-  if (live && lane < 4) digests[row * 4 + lane] = gl_canon(s);
-}
+#define QPZK_CLIMB_MAX_START 8192  // most nodes a climb may start from (sizes the counter array: 2x this)
 
+// FROM_LEAVES: group g hashes leaf row (first + g) [hash_or_noop] = node (0, first + g).
+// otherwise  : group g computes node (l0 + 1, first + g) from its two children at level l0.
+// Then it climbs while it is the second arrival, up to level `top` = log_n - cap_height.
+// `levels`: level l at word offset (2N - (2N >> l)) * 4. counters: [2 * count] u32, all zero on entry and on exit.
+template <bool FROM_LEAVES>
 __global__ void __launch_bounds__(QPZK_COOP_THREADS)
-k_merkle_level_coop(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
-  __shared__ u64 xch[QPZK_COOP_GROUPS][24];
+k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 width, u64* __restrict__ levels,
+             u32 log_n, u32 cap_height, u32 l0, u64 first, u64 count, u32* __restrict__ counters) {
+  __shared__ u64 xch[QPZK_COOP_GROUPS][COOP_XCH_WORDS];
   const u32 g = threadIdx.x >> 4, lane = threadIdx.x & 15;
-  u64 t = (u64)blockIdx.x * QPZK_COOP_GROUPS + g;
-  const bool live = t < nout;
-  if (!live) t = nout - 1;
-  u64 s = lane < 8 ? in[t * 8 + lane] : 0;
-  s = poseidon_permute_coop(s, lane, xch[g]);
-  if (live && lane < 4) out[t * 4 + lane] = gl_canon(s);
+  const u32 mask = 0xffffu << (threadIdx.x & 16);  // this group's half of the warp
+  const u64 gi = (u64)blockIdx.x * QPZK_COOP_GROUPS + g;
+  if (gi >= count) return;  // whole groups retire together
+  const u64 twoN = (u64)2 << log_n;
+  const u32 top = log_n - cap_height;
+  u32 l = FROM_LEAVES ? 0 : l0 + 1;
+  const u32 l_start = l;
+  u64 t = first + gi;
+  u64 s = 0;
+  if (FROM_LEAVES) {
+    const u64* p = src + t * row_stride;
+    if (width <= 4) {  // hash_or_noop: short rows are copied, zero padded
+      if (lane < width) s = p[lane * col_stride];
+    } else {
+      for (u32 off = 0; off < width; off += 8) {
+        if (lane < 8 && off + lane < width) s = __ldg(p + (u64)(off + lane) * col_stride);  // overwrite-mode absorb
+        s = poseidon_permute_coop(s, lane, xch[g], mask);
+      }
+    }
+  } else {
+    const u64* in = levels + (twoN - (twoN >> l0) + 2 * t) * 4;
+    s = lane < 8 ? in[lane] : 0;
+    s = poseidon_permute_coop(s, lane, xch[g], mask);
+  }
+  for (;;) {
+    u64* out = levels + (twoN - (twoN >> l) + t) * 4;
+    if (lane < 4) out[lane] = gl_canon(s);
+    if (l >= top) break;
+    // publish, then pair up with the sibling subtree
+    __threadfence();
+    __syncwarp(mask);
+    const u32 d = l + 1 - l_start;                                   // parent's depth above the start level
+    const u64 ci = 2 * count - ((2 * count) >> d) + ((t >> 1) - (first >> d));
+    u32 old = 0;
+    if (lane == 0) old = atomicAdd(&counters[ci], 1u);
+    old = __shfl_sync(mask, old, 0, 16);
+    if (old == 0) break;                                             // the sibling will take the parent
+    if (lane == 0) counters[ci] = 0;
+    __threadfence();
+    l++;
+    t >>= 1;
+    const u64* in = levels + (twoN - (twoN >> (l - 1)) + 2 * t) * 4;
+    s = lane < 8 ? __ldcg(in + lane) : 0;                            // L2: the sibling was written by another SM
+    s = poseidon_permute_coop(s, lane, xch[g], mask);
+  }
 }
 
 // Generic batched sponge / permutation entry points (KATs, host API).

@@ -385,14 +385,17 @@ k_ntt_pass_b_transpose(const u64* __restrict__ tmp, u64 tmp_stride, u64* __restr
   }
 }
 
-// Salt columns arrive in natural LDE order; leaves are stored bit-reversed.
-__global__ void k_bitrev_rows(const u64* __restrict__ src, u64* __restrict__ dst, int log_n,
-                              u32 ncols) {
+// Salt columns arrive in natural LDE order ([ncols][N]); leaves are stored bit-reversed. Leaves
+// [leaf0, leaf0 + count) are written, column c at dst + c * dst_stride + leaf (a multi-GPU shard passes its
+// own range and a destination shifted back by leaf0, see qpzk_batch::lde).
+__global__ void k_bitrev_rows(const u64* __restrict__ src, u64* __restrict__ dst, u64 dst_stride, u64 leaf0, u64 count,
+                              int log_n, u32 ncols) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   u64 N = (u64)1 << log_n;
-  if (i >= N) return;
-  u64 j = __brevll(i) >> (64 - log_n);
-  for (u32 c = blockIdx.y; c < ncols; c += gridDim.y) dst[(u64)c * N + i] = gl_canon(src[(u64)c * N + j]);
+  if (i >= count) return;
+  i += leaf0;
+  u64 j = log_n ? __brevll(i) >> (64 - log_n) : 0;
+  for (u32 c = blockIdx.y; c < ncols; c += gridDim.y) dst[(u64)c * dst_stride + i] = gl_canon(src[(u64)c * N + j]);
 }
 
 // Column-major [width][N] -> row-major [N][width] (export of `merkle_tree.leaves`).
@@ -413,20 +416,19 @@ __global__ void k_transpose_to_rows(const u64* __restrict__ src, u64* __restrict
 }
 
 // get_lde_values for a list of indices: out[i][c] = lde[c][rev(idx[i]*step)]
-__global__ void k_gather_rows(const u64* __restrict__ lde, int log_n, const u32* __restrict__ idx,
+__global__ void k_gather_rows(const u64* __restrict__ lde, u64 stride, int log_n, const u32* __restrict__ idx,
                               u32 nidx, u32 step, u32 ncols, u64* __restrict__ out) {
   u32 i = blockIdx.x;
   if (i >= nidx) return;
-  u64 N = (u64)1 << log_n;
   u64 nat = (u64)idx[i] * step;
-  u64 leaf = __brevll(nat) >> (64 - log_n);
-  for (u32 c = threadIdx.x; c < ncols; c += blockDim.x) out[(u64)i * ncols + c] = lde[(u64)c * N + leaf];
+  u64 leaf = log_n ? __brevll(nat) >> (64 - log_n) : 0;
+  for (u32 c = threadIdx.x; c < ncols; c += blockDim.x) out[(u64)i * ncols + c] = lde[(u64)c * stride + leaf];
 }
 
 // One salted leaf row by leaf index (already bit-reversed position).
-__global__ void k_gather_leaf(const u64* __restrict__ lde, u64 N, u64 leaf, u32 width,
+__global__ void k_gather_leaf(const u64* __restrict__ lde, u64 stride, u64 leaf, u32 width,
                               u64* __restrict__ out) {
-  for (u32 c = threadIdx.x; c < width; c += blockDim.x) out[c] = lde[(u64)c * N + leaf];
+  for (u32 c = threadIdx.x; c < width; c += blockDim.x) out[c] = lde[(u64)c * stride + leaf];
 }
 
 }  // namespace qpzk

@@ -37,16 +37,72 @@ __constant__ u64 c_h_v[242];
 __constant__ u32 c_mds_circ[12];
 __constant__ u32 c_mds_diag0;
 
+// PV_SBOX_ALU / PV_COMBINE_ALU / PV_ADDC_ALU (experiments, off): the s-box products, the MDS recombination
+// and the round-constant additions spelled so that every addition stays on the ALU pipe (gl.cuh,
+// gl_mul_wide_alu). The SASS model said this should win - the FMA-heavy pipe is the busiest unit (76 %,
+// profiles/r1_leaf_hash_v5_twoplane_ncu_full.txt) and the spelling takes 17-20 % of its cycles away for 1-2 %
+// more instructions - but the permutation got SLOWER: 1106.9 (off) / 1065.0 (s-box) / 1050.3 (+ combine) /
+// 1049.6 (+ add) M perm/s, and the dependent 16-lane permutation 9.11 -> 9.28 us. The ALU pipe issues one
+// warp instruction every two cycles and is the one that matters once the two are this close.
+#ifndef PV_SBOX_ALU
+#define PV_SBOX_ALU 0
+#endif
+#ifndef PV_SQR_ALU
+#define PV_SQR_ALU 0
+#endif
+#ifndef PV_COMBINE_ALU
+#define PV_COMBINE_ALU 0
+#endif
+#ifndef PV_ADDC_ALU
+#define PV_ADDC_ALU 0
+#endif
 GL_DEV u64 sbox7(u64 x) {
+#if PV_SBOX_ALU
+  u64 x2 = gl_sqr_alu(x);
+  u64 x4 = gl_sqr_alu(x2);
+  u64 x3 = gl_mul_alu(x, x2);
+  return gl_mul_alu(x3, x4);
+#elif PV_SQR_ALU  // only the squarings (18 instructions against 20, one partial product fewer)
+  u64 x2 = gl_sqr_alu(x);
+  u64 x4 = gl_sqr_alu(x2);
+  u64 x3 = gl_mul(x, x2);
+  return gl_mul(x3, x4);
+#else
   u64 x2 = gl_sqr(x);
   u64 x4 = gl_sqr(x2);
   u64 x3 = gl_mul(x, x2);
   return gl_mul(x3, x4);
+#endif
+}
+GL_DEV u64 pv_add_c(u64 a, u64 b_canon) {
+#if PV_ADDC_ALU
+  return gl_add_c_alu(a, b_canon);
+#else
+  return gl_add_c(a, b_canon);
+#endif
 }
 
 // MDS lane recombination: al + ah*2^32 with al = l1:l0, ah = h1:h0 < 2^42, folded to 64 bits.
 //   value = l0 + (l1 + h0)*2^32 + (h1 + carry)*2^64,  2^64 == EPS; the multiply-add by EPS can carry once.
 GL_DEV u64 mds_combine(u32 l0, u32 l1, u32 h0, u32 h1) {
+#if PV_COMBINE_ALU
+  // r2 = h1 + carry < 2^22: add r2 * (2^32 - 1) = (r2 - [r2 != 0] : -r2) as a 64-bit number, then one
+  // correction by 2^32 - 1 if that wrapped (the wrapped sum is below 2^54, so it cannot wrap again)
+  asm("{\n\t.reg .u32 c, e0, e1;\n\t"
+      "add.cc.u32 %1, %1, %2;\n\t"
+      "addc.u32 %3, %3, 0;\n\t"
+      "sub.cc.u32 e0, 0, %3;\n\t"
+      "subc.u32 e1, %3, 0;\n\t"
+      "add.cc.u32 %0, %0, e0;\n\t"
+      "addc.cc.u32 %1, %1, e1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, c;\n\t"
+      "subc.u32 %1, %1, 0;\n\t"
+      "add.u32 %1, %1, c;\n\t"
+      "}"
+      : "+r"(l0), "+r"(l1), "+r"(h0), "+r"(h1));
+  return ((u64)l1 << 32) | l0;
+#endif
   asm("{\n\t.reg .u32 c;\n\t"
       "add.cc.u32 %1, %1, %2;\n\t"
       "addc.u32 %3, %3, 0;\n\t"
@@ -234,7 +290,7 @@ GL_DEV void sbox_layer(u64 (&s)[12], const u64* __restrict__ rc) {
   for (int g = 0; g < PV_SBOX_TRIPS; g++) {
     u64 t[LANES];
 #pragma unroll
-    for (int j = 0; j < LANES; j++) t[j] = sbox7(ADD_RC ? gl_add_c(s[j], rc[LANES * g + j]) : s[j]);
+    for (int j = 0; j < LANES; j++) t[j] = sbox7(ADD_RC ? pv_add_c(s[j], rc[LANES * g + j]) : s[j]);
 #pragma unroll
     for (int i = 0; i < 12 - LANES; i++) s[i] = s[i + LANES];
 #pragma unroll
@@ -299,13 +355,13 @@ GL_DEV void partial_init_layer(u64 (&s)[12]) {
 GL_DEV void sparse_partial_rounds(u64 (&s)[12]) {
 #if !(PV_MDS_F64 && PV_RC_FOLD)  // otherwise the MDS layer before them added the first constants
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_fast_first[i]);
+  for (int i = 0; i < 12; i++) s[i] = pv_add_c(s[i], c_fast_first[i]);
 #endif
   partial_init_layer<true>(s);
 PV_UNROLL(PV_PARTIAL_UNROLL)
   for (int r = 0; r < 22 - PV_DENSE_PARTIAL; r++) {
     u64 s0 = sbox7(s[0]);
-    s0 = gl_add_c(s0, c_h_rc[r]);  // the last entry is zero
+    s0 = pv_add_c(s0, c_h_rc[r]);  // the last entry is zero
     Acc160 a;
     acc_init(a);
     acc_mac(a, s0, 25);  // MDS[0][0] = 17 + 8
@@ -331,7 +387,7 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
   for (int half = 0; half < 2; half++) {
     const u64* rc = c_rc + 12 * 26 * half;  // the rounds not preceded by an FP64 MDS layer add their constants
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[i]);
+    for (int i = 0; i < 12; i++) s[i] = pv_add_c(s[i], rc[i]);
     const int nrounds = half ? 4 : 4 + PV_DENSE_PARTIAL, layer0 = half ? 4 + PV_DENSE_PARTIAL : 0;
 #pragma unroll 1
     for (int r = 0; r < nrounds; r++) {
@@ -368,22 +424,31 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
 // the other 11 words from a shared-memory exchange: ~4.8k serial instructions per permutation. Every
 // round is executed in the textbook form (constants, s-box on all lanes or on lane 0, MDS) - the same
 // permutation as the sparse partial-round form, so results are bit-identical.
-__device__ u64 g_rc[360];  // lane-indexed reads: global/L1, not the constant bank (divergent index)
+__device__ u64 g_rc[372];  // lane-indexed reads: global/L1, not the constant bank (divergent index); 12 zeros appended
+#define COOP_XCH_WORDS 24
 
 // s: this lane's state word (lanes 12..15 of the group carry garbage and must be ignored by the caller).
-// xch: 24 u64 of shared memory private to the 16-lane group (double buffer).
-GL_DEV u64 poseidon_permute_coop(u64 s, u32 lane, u64* xch) {
+// xch: COOP_XCH_WORDS u64 of shared memory private to the 16-lane group (double buffer).
+// mask: the lanes that execute this call together (__syncwarp mask) - the whole warp when both 16-lane
+// groups of a warp run in lockstep, one half when they may diverge (tree climbing, merkle.cuh).
+// The constants of round r + 1 enter as the initial value of round r's MDS accumulators (their 32-bit halves
+// join the low / high column sums: free), and they are requested one round ahead, so neither the modular
+// addition nor the load sits on the dependent chain.
+GL_DEV u64 poseidon_permute_coop(u64 s, u32 lane, u64* xch, u32 mask = 0xffffffffu) {
   const bool act = lane < 12;
   const u32 li = act ? lane : 0;
+  s = pv_add_c(s, __ldg(&g_rc[li]));
+  u64 rc_next = __ldg(&g_rc[12 + li]);
 #pragma unroll 1
   for (int r = 0; r < 30; r++) {
-    s = gl_add_c(s, __ldg(&g_rc[r * 12 + li]));
+    const u64 rc = rc_next;
+    rc_next = __ldg(&g_rc[(r < 28 ? r + 2 : 30) * 12 + li]);  // the last two trips read the zero padding
     const bool full = r < 4 || r >= 26;
     if (full || lane == 0) s = sbox7(s);
     u64* buf = xch + (r & 1) * 12;
     if (act) buf[lane] = s;
-    __syncwarp();
-    u32 al0 = 0, al1 = 0, ah0 = 0, ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
+    __syncwarp(mask);
+    u32 al0 = (u32)rc, al1 = 0, ah0 = (u32)(rc >> 32), ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
 #pragma unroll
     for (int i = 0; i < 12; i += 2) {
       u32 j0 = li + i, j1 = li + i + 1;

@@ -16,6 +16,7 @@
 #pragma once
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "transcript.cuh"
 
 namespace qpzk {
 
@@ -42,7 +43,6 @@ GL_HD bool gate_is_recursion_only(u32 id) {
 }
 
 #define QPZK_MAX_GATES 16
-#define QPZK_MAX_CHALLENGES 4
 
 // Everything the quotient / Z kernels need to know about the circuit (passed by value).
 struct CircuitDesc {
@@ -55,9 +55,8 @@ struct CircuitDesc {
   const u64* coset_aux;  // CosetInterpolation: [2^bits] subgroup points then [2^bits] barycentric weights (device)
 };
 
-struct Challenges {
-  u64 beta[QPZK_MAX_CHALLENGES], gamma[QPZK_MAX_CHALLENGES], alpha[QPZK_MAX_CHALLENGES];
-};
+// Challenges (transcript.cuh) reach the kernels as a pointer into the device-resident transcript: they are
+// produced on the device and never visit the host on the proving path.
 
 // ---------------------------------------------------------------------------------------------
 // H8  Z and partial products
@@ -66,7 +65,7 @@ struct Challenges {
 // wires / cs are value columns on the subgroup, [.][n]. k_is in constant-like global memory.
 __global__ void __launch_bounds__(128)
 k_zs_chunk_quotients(const u64* __restrict__ wires, const u64* __restrict__ cs, const u64* __restrict__ k_is,
-                     CircuitDesc d, Challenges ch, RootTab tab, u64* __restrict__ chunk_q /*[nch][nchunks][n]*/,
+                     CircuitDesc d, const Challenges* __restrict__ chp, RootTab tab, u64* __restrict__ chunk_q /*[nch][nchunks][n]*/,
                      u64* __restrict__ row_prod /*[nch][n]*/) {
   const u64 n = (u64)1 << d.degree_bits;
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,7 +73,7 @@ k_zs_chunk_quotients(const u64* __restrict__ wires, const u64* __restrict__ cs, 
   const u32 c = blockIdx.y;
   const u32 nchunks = d.num_partial_products + 1;
   const u64 x = root_pow(tab, i);
-  const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+  const u64 beta = __ldg(&chp->beta[c]), gamma = __ldg(&chp->gamma[c]);
   const u64 bx = gl_mul(beta, x);
   u64 nums[12], dens[12];  // nchunks <= 12
   u64 dprod = 1;
@@ -446,7 +445,7 @@ template <bool RECURSION>
 __global__ void __launch_bounds__(128, RECURSION ? 3 : 4)
 k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, const u64* __restrict__ zs_lde,
            u64 cs_stride, u64 wires_stride, u64 zs_stride, u32 step_bits, const u64* __restrict__ k_is,
-           CircuitDesc d, Challenges ch, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
+           CircuitDesc d, const Challenges* __restrict__ chp, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
            const u64* __restrict__ zh_inv, const u64* __restrict__ apw /* alpha powers [2][QPZK_APW_STRIDE] */,
            const u64* __restrict__ l0_den_inv /* [2^lb]: 1 / (n (x_i - 1)) */, RootTab tab /* size degree_bits + qdb */,
            u64* __restrict__ out) {
@@ -484,9 +483,11 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
   const u32 nchunks = npp + 1;
   const u32 pp_base = a.t;
   {
-    u64 bx[2], prev[2];
+    u64 bx[2], prev[2], betas[2], gammas[2];
     for (u32 c = 0; c < nch; c++) {
-      bx[c] = gl_mul(ch.beta[c], x);
+      betas[c] = __ldg(&chp->beta[c]);
+      gammas[c] = __ldg(&chp->gamma[c]);
+      bx[c] = gl_mul(betas[c], x);
       prev[c] = zs[c];
     }
     for (u32 k = 0; k < nchunks; k++) {
@@ -502,7 +503,7 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
           kk[e] = __ldg(k_is + j0 + e);
         }
         for (u32 c = 0; c < nch; c++) {
-          const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+          const u64 beta = betas[c], gamma = gammas[c];
           u64 num = gl_add(gl_mad(bx[c], kk[0], wv[0]), gamma);
           u64 den = gl_add(gl_mad(beta, sg[0], wv[0]), gamma);
 #pragma unroll
@@ -515,7 +516,7 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
         }
       } else {  // other chunk sizes, ragged last chunk
         for (u32 c = 0; c < nch; c++) {
-          const u64 beta = ch.beta[c], gamma = ch.gamma[c];
+          const u64 beta = betas[c], gamma = gammas[c];
           u64 num = 1, den = 1;
           for (u32 j = j0; j < j0 + d.qdf && j < d.num_routed; j++) {
             u64 wv = w[j];
@@ -625,10 +626,10 @@ __global__ void k_scale_by_powers(u64* __restrict__ data, u64 n, RootTab tab) {
 // H10  openings: evaluate base-field coefficient columns at an extension point
 // ---------------------------------------------------------------------------------------------
 // pw[m] = z^m (ext), m < n.
-__global__ void k_ext_powers(gl2 z, u64 n, u64* __restrict__ pw /*[n][2]*/) {
+__global__ void k_ext_powers(const u64* __restrict__ zp /* [2], device */, u64 n, u64* __restrict__ pw /*[n][2]*/) {
   u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
-  gl2 r = gl2_make(1, 0), b = z;
+  gl2 r = gl2_make(1, 0), b = gl2_make(__ldg(zp), __ldg(zp + 1));
   for (u64 e = m; e; e >>= 1) {
     if (e & 1) r = gl2_mul(r, b);
     b = gl2_mul(b, b);
@@ -699,8 +700,9 @@ k_fri_compose(PolyList pl, u64 n, const u64* __restrict__ apow, u64* __restrict_
 // under composition: log2(T) shared-memory steps instead of a T-step sequential walk (which was
 // 0.24 ms of pure latency per call at n = 2^14).
 __global__ void __launch_bounds__(1024)
-k_divide_by_linear(const u64* __restrict__ p, u64* __restrict__ q, u64 n, gl2 z) {
+k_divide_by_linear(const u64* __restrict__ p, u64* __restrict__ q, u64 n, const u64* __restrict__ zp /* [2], device */) {
   __shared__ u64 la[1024], lb[1024], za[1024], zb[1024];
+  const gl2 z = gl2_make(__ldg(zp), __ldg(zp + 1));
   const u32 t = threadIdx.x, T = blockDim.x;
   const u64 per = (n + T - 1) / T;
   const u64 lo = (u64)t * per < n ? (u64)t * per : n, hi = lo + per < n ? lo + per : n;  // segment [lo, hi)
@@ -744,10 +746,11 @@ k_divide_by_linear(const u64* __restrict__ p, u64* __restrict__ q, u64 n, gl2 z)
 }
 
 // final = q0 * s + q1  (ext scalar s), SoA [2][n]
-__global__ void k_ext_axpy(const u64* __restrict__ q0, const u64* __restrict__ q1, gl2 s, u64 n,
-                           u64* __restrict__ out) {
+__global__ void k_ext_axpy(const u64* __restrict__ q0, const u64* __restrict__ q1, const u64* __restrict__ sp /* [2], device */,
+                           u64 n, u64* __restrict__ out) {
   u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
+  const gl2 s = gl2_make(__ldg(sp), __ldg(sp + 1));
   gl2 v = gl2_add(gl2_mul(gl2_make(q0[m], q0[n + m]), s), gl2_make(q1[m], q1[n + m]));
   out[m] = gl_canon(v.a);
   out[n + m] = gl_canon(v.b);
@@ -757,10 +760,12 @@ __global__ void k_ext_axpy(const u64* __restrict__ q0, const u64* __restrict__ q
 // H12  FRI fold and leaf packing
 // ---------------------------------------------------------------------------------------------
 // out[m] = sum_{j<arity} in[m*arity + j] * beta^j  (ext Horner). in: SoA [2][n_in], out: SoA [2][n_in/arity]
-__global__ void k_fri_fold(const u64* __restrict__ in, u64 n_in, u32 arity_bits, gl2 beta, u64* __restrict__ out) {
+__global__ void k_fri_fold(const u64* __restrict__ in, u64 n_in, u32 arity_bits, const u64* __restrict__ bp /* [2], device */,
+                           u64* __restrict__ out) {
   u64 n_out = n_in >> arity_bits;
   u64 m = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_out) return;
+  const gl2 beta = gl2_make(__ldg(bp), __ldg(bp + 1));
   u32 arity = 1u << arity_bits;
   gl2 acc = gl2_make(0, 0);
   for (int j = (int)arity - 1; j >= 0; j--) {
@@ -800,6 +805,32 @@ k_pow_grind(PowState st, u32 pos, u32 min_lz, u64 start, u64 count, unsigned lon
   u64 resp = gl_canon(s[7]);
   u32 lz = resp ? (u32)__clzll((long long)resp) : 64;
   if (lz >= min_lz) atomicMin(best, (unsigned long long)cand);
+}
+
+// The same search driven from the device-resident transcript, without a host round trip per window: the
+// sponge state and the input position come from `T`, the grid strides over the candidates and a thread
+// stops at the first candidate of its own that is not below the best witness found so far. Every candidate
+// below the final witness has then been tried by the thread that owns it, so the result is still the
+// SMALLEST valid witness. T->pow_witness must be ~0 on entry (k_transcript_init).
+__global__ void __launch_bounds__(128)
+k_pow_grind_dev(TranscriptDev* __restrict__ T, u32 min_lz) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  u64 cand = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 pos = T->in_len;
+  u64 s0[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s0[i] = T->state[i];
+  volatile unsigned long long* best = reinterpret_cast<volatile unsigned long long*>(&T->pow_witness);
+  while (cand < *best) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = i == (int)pos ? cand : s0[i];
+    poseidon_permute(s);
+    const u64 resp = gl_canon(s[7]);
+    const u32 lz = resp ? (u32)__clzll((long long)resp) : 64;
+    if (lz >= min_lz) atomicMin(reinterpret_cast<unsigned long long*>(&T->pow_witness), (unsigned long long)cand);
+    cand += stride;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -228,6 +228,89 @@ static bool parse_common_host(const uint8_t* p, size_t n, CommonHost* c, std::st
   return true;
 }
 
+// Everything the kernels index with comes from these bytes, so every range is checked here, once, before a
+// single launch: the CircuitDesc arrays are 16 entries, the alpha-power table QPZK_APW_STRIDE, a gate reads
+// the wires and constants its layout says, shifts by degree_bits must stay below 64, and so on.
+static bool validate_common(const CommonHost& c, std::string* err) {
+#define QPZK_REQUIRE(cond, msg) \
+  do {                          \
+    if (!(cond)) {              \
+      *err = msg;               \
+      return false;             \
+    }                           \
+  } while (0)
+  QPZK_REQUIRE(c.degree_bits <= 30 && c.rate_bits <= 30 && c.degree_bits + c.rate_bits <= 30, "degree_bits + rate_bits above 30");
+  QPZK_REQUIRE(c.cap_height <= c.degree_bits + c.rate_bits && c.cap_height <= 16, "cap_height out of range");
+  QPZK_REQUIRE(c.num_challenges >= 1 && c.num_challenges <= 2, "num_challenges must be 1 or 2");
+  QPZK_REQUIRE(c.num_wires >= 1 && c.num_wires <= 4096 && c.num_routed <= c.num_wires, "bad wire counts");
+  QPZK_REQUIRE(c.num_constants <= 4096 && c.num_public_inputs <= (1u << 20), "bad constant / public input counts");
+  QPZK_REQUIRE(c.num_queries >= 1 && c.num_queries <= QPZK_MAX_QUERIES, "num_queries out of range");
+  QPZK_REQUIRE(c.pow_bits <= 40, "proof-of-work bits above 40");
+  QPZK_REQUIRE(c.arities.size() <= QPZK_MAX_FRI_ROUNDS, "too many FRI rounds");
+  {
+    u64 kcur = c.degree_bits;
+    for (u64 ab : c.arities) {
+      QPZK_REQUIRE(ab >= 1 && ab <= 8 && ab <= kcur, "bad FRI arity");
+      QPZK_REQUIRE(kcur + c.rate_bits - ab >= c.cap_height, "FRI tree smaller than the cap");
+      kcur -= ab;
+    }
+  }
+  u32 qdb = 0;
+  while ((1ull << qdb) < c.qdf && qdb < 32) qdb++;
+  QPZK_REQUIRE(c.qdf >= 1 && (1ull << qdb) == c.qdf && qdb <= c.rate_bits, "quotient_degree_factor must be a power of two within the rate");
+  QPZK_REQUIRE(c.num_partial_products + 1 <= 12, "more than 11 partial products");
+  QPZK_REQUIRE((c.num_partial_products + 1) * c.qdf >= c.num_routed, "partial-product chunks do not cover the routed wires");
+  QPZK_REQUIRE(c.k_is.size() == c.num_routed, "k_is / num_routed_wires mismatch");
+  const size_t ng = c.gates.size(), ns = c.groups.size();
+  QPZK_REQUIRE(ng >= 1 && ng <= QPZK_MAX_GATES && ns >= 1 && ns <= QPZK_MAX_GATES, "bad gate / selector group counts");
+  QPZK_REQUIRE(c.selector_indices.size() == ng && c.num_constants >= ns, "selector data mismatch");
+  for (size_t s = 0; s < ns; s++)
+    QPZK_REQUIRE(c.groups[s].first <= c.groups[s].second && c.groups[s].second <= ng, "selector group out of range");
+  u64 max_constraints = 0;
+  for (size_t g = 0; g < ng; g++) {
+    const u64 si = c.selector_indices[g];
+    QPZK_REQUIRE(si < ns && c.groups[si].first <= g && g < c.groups[si].second, "gate outside its selector group");
+    const u64 p1 = c.gates[g].second, p2 = c.gate_p2[g], p3 = c.gate_p3[g];
+    u64 wires = 0, consts = 0, cons = 0;  // what the evaluator reads / emits
+    switch (c.gates[g].first) {
+      case G_NOOP: break;
+      case G_CONSTANT: wires = p1; consts = p1; cons = p1; break;
+      case G_PUBLIC_INPUT: wires = 4; cons = 4; break;
+      case G_BASE_SUM_2: wires = 1 + p1; cons = 1 + p1; break;
+      case G_ARITHMETIC: wires = 4 * p1; consts = 2; cons = p1; break;
+      case G_POSEIDON: wires = 135; cons = 123; break;
+      case G_ARITHMETIC_EXT: wires = 8 * p1; consts = 2; cons = 2 * p1; break;
+      case G_MUL_EXT: wires = 6 * p1; consts = 1; cons = 2 * p1; break;
+      case G_POSEIDON_MDS: wires = 48; cons = 24; break;
+      case G_RANDOM_ACCESS: {
+        const u64 vec = 1ull << p1;
+        wires = (2 + vec) * p2 + p3 + p2 * p1;
+        consts = p3;
+        cons = p2 * (p1 + 2) + p3;
+        break;
+      }
+      case G_REDUCING: QPZK_REQUIRE(p1 >= 1, "ReducingGate without coefficients"); wires = 6 + p1 + 2 * (p1 - 1); cons = 2 * p1; break;
+      case G_REDUCING_EXT: QPZK_REQUIRE(p1 >= 1, "ReducingExtensionGate without coefficients"); wires = 6 + 2 * p1 + 2 * (p1 - 1); cons = 2 * p1; break;
+      case G_EXPONENTIATION: wires = 2 + 2 * p1; cons = p1 + 1; break;
+      case G_COSET_INTERPOLATION: {
+        const u64 np = 1ull << p1, nint = (np - 2) / (p2 - 1);
+        wires = 1 + 2 * np + 2 + 2 + 4 * nint + 2;
+        cons = 2 + 4 * nint + 2;
+        break;
+      }
+      default: *err = "unsupported gate"; return false;
+    }
+    QPZK_REQUIRE(p1 <= 4096 && wires <= c.num_wires, "gate needs more wires than the circuit has");
+    QPZK_REQUIRE(ns + consts <= c.num_constants, "gate needs more constants than the circuit has");
+    if (cons > max_constraints) max_constraints = cons;
+  }
+  QPZK_REQUIRE(max_constraints <= c.num_gate_constraints, "num_gate_constraints smaller than a gate's constraint count");
+  QPZK_REQUIRE(c.num_challenges * (1 + c.num_partial_products + 1) + c.num_gate_constraints <= QPZK_APW_STRIDE,
+               "too many constraint terms for the alpha-power table");
+#undef QPZK_REQUIRE
+  return true;
+}
+
 struct ByteWriter {
   std::vector<uint8_t> b;
   void u(u64 v, size_t bytes) { for (size_t i = 0; i < bytes; i++) b.push_back((uint8_t)(v >> (8 * i))); }
@@ -236,44 +319,112 @@ struct ByteWriter {
 
 }  // namespace qpzk
 
+// Where the pieces of a proof land in the per-circuit arena (u64 word offsets). The arena is one device
+// buffer, mirrored by one pinned host buffer and copied back ONCE per proof; word 0 holds the transcript
+// (challenges, PoW witness, query indices).
+struct ArenaLayout {
+  size_t caps = 0;        // [3][capw]   wires, zs|partial products, quotient
+  size_t opens = 0;       // [(total_polys + nch)][2]  oracle order, then Z(g zeta)
+  size_t fri_caps = 0;    // [rounds][capw]
+  size_t final_poly = 0;  // [m][2]
+  size_t init_open[4] = {0, 0, 0, 0};   // [nq][width_o + 4 L0]
+  size_t step_open[QPZK_MAX_FRI_ROUNDS] = {0};  // [nq][2 * 2^arity + 4 L_s]
+  size_t total = 0;
+  u32 capw = 0, total_polys = 0, final_len = 0, L0 = 0;
+  u32 width[4] = {0, 0, 0, 0};
+  u32 step_width[QPZK_MAX_FRI_ROUNDS] = {0}, step_L[QPZK_MAX_FRI_ROUNDS] = {0};
+};
+
 struct qpzk_circuit {
-  qpzk_ctx* ctx;
+  qpzk_ctx* ctx = nullptr;
   CommonHost common;
   CircuitDesc desc;
-  u64 digest[4];
+  u64 digest[4] = {0, 0, 0, 0};
   u64* k_is_dev = nullptr;
   u64* coset_aux_dev = nullptr;
   u64* l0_den_inv_dev = nullptr;   // [2^(degree_bits + qdb)], see k_build_l0_den_inv
-  u64* cs_values = nullptr;  // [num_constants + num_routed][n] values on the subgroup (for Z)
+  u64* zh_dev = nullptr;           // Z_H on the quotient coset: [2^qdb] values, then their inverses
+  u64* cs_values = nullptr;        // [num_constants + num_routed][n] values on the subgroup (for Z)
   qpzk_batch* cs_batch = nullptr;
   std::vector<u64> cs_cap;
+  // one proof at a time per circuit handle: the arena and the transcript in it belong to the proof in flight
+  ArenaLayout lay;
+  u64* arena_dev = nullptr;
+  u64* arena_host = nullptr;       // pinned
+  cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+  std::vector<u64> pis;            // canonical public inputs of the proof in flight
   // debug trace of the last proof
+  bool want_trace = false;
   std::vector<u64> tr_challenges, tr_zs_pp, tr_quotient, tr_final_poly;
   float stage_ms[16] = {0};
+  std::mutex mu;                   // serialises begin / end on this handle
+  TranscriptDev* transcript() const { return reinterpret_cast<TranscriptDev*>(arena_dev); }
+  ~qpzk_circuit() {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (in_flight) ctx_wait(ctx);
+    dev_free(ctx, k_is_dev);
+    dev_free(ctx, coset_aux_dev);
+    dev_free(ctx, l0_den_inv_dev);
+    dev_free(ctx, zh_dev);
+    dev_free(ctx, cs_values);
+    dev_free(ctx, arena_dev);
+    if (arena_host) cudaFreeHost(arena_host);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (done) cudaEventDestroy(done);
+    delete cs_batch;
+  }
 };
 
 namespace qpzk {
 
-struct DevBuf {  // scoped stream-ordered allocation
-  qpzk_ctx* c;
-  u64* p = nullptr;
-  explicit DevBuf(qpzk_ctx* c_) : c(c_) {}
-  ~DevBuf() { dev_free(c, p); }
-  int alloc(size_t bytes) { return dev_alloc(c, bytes, &p); }
-};
+static const size_t kTranscriptWords = (sizeof(TranscriptDev) + 7) / 8;
 
-}  // namespace qpzk
+static void layout_arena(const CommonHost& cm, const CircuitDesc& d, ArenaLayout* L) {
+  const u32 h = (u32)cm.cap_height, nq = (u32)cm.num_queries, salt = cm.hiding ? QPZK_SALT_SIZE : 0;
+  L->capw = 4u << h;
+  L->width[0] = d.num_constants + d.num_routed;
+  L->width[1] = d.num_wires + salt;
+  L->width[2] = d.num_challenges * (1 + d.num_partial_products) + salt;
+  L->width[3] = d.num_challenges * d.qdf + salt;
+  L->total_polys = L->width[0] + (L->width[1] - salt) + (L->width[2] - salt) + (L->width[3] - salt);
+  L->L0 = d.degree_bits + d.rate_bits - h;
+  size_t off = (kTranscriptWords + 3) & ~(size_t)3;
+  L->caps = off; off += 3 * (size_t)L->capw;
+  L->opens = off; off += 2 * (size_t)(L->total_polys + d.num_challenges);
+  L->fri_caps = off; off += cm.arities.size() * (size_t)L->capw;
+  u32 kcur = d.degree_bits;
+  for (size_t s = 0; s < cm.arities.size(); s++) {
+    const u32 ab = (u32)cm.arities[s];
+    L->step_width[s] = 2u << ab;
+    L->step_L[s] = kcur + d.rate_bits - ab - h;
+    kcur -= ab;
+  }
+  L->final_len = 1u << kcur;
+  L->final_poly = off; off += 2 * (size_t)L->final_len;
+  for (int o = 0; o < 4; o++) {
+    L->init_open[o] = off;
+    off += (size_t)nq * (L->width[o] + 4 * (size_t)L->L0);
+  }
+  for (size_t s = 0; s < cm.arities.size(); s++) {
+    L->step_open[s] = off;
+    off += (size_t)nq * (L->step_width[s] + 4 * (size_t)L->step_L[s]);
+  }
+  L->total = off;
+}
 
-namespace qpzk {
 // fri_proof_of_work: the smallest w such that the permutation of the sponge state with w written at
 // `pos` has >= min_lz leading zero bits in output word 7. Candidate windows grow from the expected
 // witness size (2^min_lz) upwards: a window much larger than that only burns permutations behind
-// the witness before the early exit can see it.
+// the witness before the early exit can see it. (Host-driven form, behind the qpzk_fri_pow hook; the proof
+// pipeline grinds from the device-resident transcript with k_pow_grind_dev.)
 static int grind_pow(qpzk_ctx* c, const PowState& ps, u32 pos, u32 min_lz, u64* witness) {
   DevBuf best(c);
   QP(best.alloc(8));
-  unsigned long long init = ~0ull;
-  CU(cudaMemcpyAsync(best.p, &init, 8, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(best.p, 0xff, 8, c->stream));
   u64 batch = 1ull << (min_lz < 12 ? 12 : (min_lz > 20 ? 20 : min_lz));
   u64 start = 0;
   unsigned long long found = ~0ull;
@@ -289,6 +440,11 @@ static int grind_pow(qpzk_ctx* c, const PowState& ps, u32 pos, u32 min_lz, u64* 
   }
   *witness = found;
   return QPZK_OK;
+}
+
+static u32 pow_grid_blocks(u32 min_lz) {  // candidates per sweep of k_pow_grind_dev ~ the expected witness
+  const u32 lg = min_lz < 12 ? 12 : (min_lz > 16 ? 16 : min_lz);
+  return (1u << lg) / 128;
 }
 }  // namespace qpzk
 
@@ -309,12 +465,17 @@ int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point, uint64_t* ou
   qpzk_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
   const u64 n = 1ull << b->degree_bits;
-  DevBuf zpow(c), res(c);
+  DevBuf zpow(c), res(c), pt(c);
   QP(zpow.alloc(n * 16));
   QP(res.alloc((size_t)b->ncols * 16));
-  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(gl2{point[0], point[1]}, n, zpow.p);
+  QP(pt.alloc(16));
+  Words16 w;
+  w.w[0] = point[0];
+  w.w[1] = point[1];
+  k_set_words<<<1, 32, 0, c->stream>>>(pt.p, w, 2);
+  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pt.p, n, zpow.p);
   k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, res.p);
-  c->launches += 2;
+  c->launches += 3;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out, res.p, (size_t)b->ncols * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
@@ -322,116 +483,128 @@ int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point, uint64_t* ou
 }
 
 int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len, const uint64_t* digest4,
-                        const uint64_t* constants_sigmas, qpzk_circuit** out) {
-  if (!c || !common_bytes || !digest4 || !constants_sigmas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(c->device));
-  qpzk_circuit* q = new qpzk_circuit();
-  q->ctx = c;
-  std::string err;
-  if (!parse_common_host(common_bytes, common_len, &q->common, &err)) {
-    delete q;
-    return fail(QPZK_ERR_UNSUPPORTED, err);
-  }
-  const CommonHost& cm = q->common;
-  u32 qdb = 0;
-  while ((1ull << qdb) < cm.qdf) qdb++;
-  if ((1ull << qdb) != cm.qdf || qdb > cm.rate_bits || cm.num_challenges > 2 || cm.num_partial_products + 1 > 12 ||
-      cm.num_constants < cm.groups.size() || cm.k_is.size() != cm.num_routed) {
-    delete q;
-    return fail(QPZK_ERR_UNSUPPORTED, "unsupported circuit configuration");
-  }
-  CircuitDesc& d = q->desc;
-  memset(&d, 0, sizeof d);
-  d.degree_bits = (u32)cm.degree_bits; d.rate_bits = (u32)cm.rate_bits; d.quotient_degree_bits = qdb;
-  d.num_wires = (u32)cm.num_wires; d.num_routed = (u32)cm.num_routed; d.num_constants = (u32)cm.num_constants;
-  d.num_challenges = (u32)cm.num_challenges; d.num_partial_products = (u32)cm.num_partial_products;
-  d.qdf = (u32)cm.qdf; d.num_selectors = (u32)cm.groups.size(); d.num_gates = (u32)cm.gates.size();
-  d.num_gate_constraints = (u32)cm.num_gate_constraints;
-  for (size_t g = 0; g < cm.gates.size(); g++) {
-    d.gate_id[g] = cm.gates[g].first;
-    d.gate_param[g] = (u32)cm.gates[g].second;
-    d.gate_param2[g] = (u32)cm.gate_p2[g];
-    d.gate_param3[g] = (u32)cm.gate_p3[g];
-    d.gate_selector[g] = (u32)cm.selector_indices[g];
-  }
-  for (size_t s = 0; s < cm.groups.size(); s++) {
-    d.group_lo[s] = (u32)cm.groups[s].first;
-    d.group_hi[s] = (u32)cm.groups[s].second;
-  }
-  memcpy(q->digest, digest4, 32);
-  const u64 n = 1ull << cm.degree_bits;
-  const u32 ncs = (u32)(cm.num_constants + cm.num_routed);
-  QP(dev_alloc(c, cm.k_is.size() * 8, &q->k_is_dev));
-  CU(cudaMemcpyAsync(q->k_is_dev, cm.k_is.data(), cm.k_is.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  if (!cm.coset_weights.empty()) {  // subgroup points, then the barycentric weights from the common data
-    const size_t np = cm.coset_weights.size();
-    u32 bits = 0;
-    while ((1ull << bits) < np) bits++;
-    std::vector<u64> aux(2 * np);
-    u64 g = glh::root_of_unity(bits);
-    aux[0] = 1;
-    for (size_t i = 1; i < np; i++) aux[i] = glh::mul(aux[i - 1], g);
-    for (size_t i = 0; i < np; i++) aux[np + i] = cm.coset_weights[i];
-    QP(dev_alloc(c, aux.size() * 8, &q->coset_aux_dev));
-    CU(cudaMemcpyAsync(q->coset_aux_dev, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(ctx_wait(c));
-    d.coset_aux = q->coset_aux_dev;
-  }
-  QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
-  CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
-  // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
-  int rc = commit_impl(c, q->cs_values, false, false, ncs, (u32)cm.degree_bits, (u32)cm.rate_bits, (u32)cm.cap_height,
-                       nullptr, false, 0, &q->cs_batch);
-  if (rc != QPZK_OK) {
-    dev_free(c, q->k_is_dev);
-    dev_free(c, q->cs_values);
-    delete q;
-    return rc;
-  }
-  q->cs_cap.resize(4ull << cm.cap_height);
-  QP(qpzk_batch_cap(q->cs_batch, q->cs_cap.data()));
-  {
-    const u32 qlb = (u32)cm.degree_bits + qdb;
-    if (cm.num_challenges * (1 + cm.num_partial_products + 1) + cm.num_gate_constraints > QPZK_APW_STRIDE) {
-      qpzk_circuit_free(q);
-      return fail(QPZK_ERR_UNSUPPORTED, "too many constraint terms for the alpha-power table");
+                        const uint64_t* constants_sigmas, size_t constants_sigmas_words, qpzk_circuit** out) {
+  return guarded([&]() -> int {
+    if (!c || !common_bytes || !digest4 || !constants_sigmas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<qpzk_circuit> q(new qpzk_circuit());
+    q->ctx = c;
+    std::string err;
+    if (!parse_common_host(common_bytes, common_len, &q->common, &err)) return fail(QPZK_ERR_UNSUPPORTED, err);
+    if (!validate_common(q->common, &err)) return fail(QPZK_ERR_UNSUPPORTED, "unsupported circuit configuration: " + err);
+    const CommonHost& cm = q->common;
+    u32 qdb = 0;
+    while ((1ull << qdb) < cm.qdf) qdb++;
+    const u64 n = 1ull << cm.degree_bits;
+    const u32 ncs = (u32)(cm.num_constants + cm.num_routed);
+    if (constants_sigmas_words != (size_t)ncs * n)
+      return fail(QPZK_ERR_BAD_ARG, "constants_sigmas must hold (num_constants + num_routed_wires) * 2^degree_bits words");
+    CircuitDesc& d = q->desc;
+    memset(&d, 0, sizeof d);
+    d.degree_bits = (u32)cm.degree_bits; d.rate_bits = (u32)cm.rate_bits; d.quotient_degree_bits = qdb;
+    d.num_wires = (u32)cm.num_wires; d.num_routed = (u32)cm.num_routed; d.num_constants = (u32)cm.num_constants;
+    d.num_challenges = (u32)cm.num_challenges; d.num_partial_products = (u32)cm.num_partial_products;
+    d.qdf = (u32)cm.qdf; d.num_selectors = (u32)cm.groups.size(); d.num_gates = (u32)cm.gates.size();
+    d.num_gate_constraints = (u32)cm.num_gate_constraints;
+    for (size_t g = 0; g < cm.gates.size(); g++) {
+      d.gate_id[g] = cm.gates[g].first;
+      d.gate_param[g] = (u32)cm.gates[g].second;
+      d.gate_param2[g] = (u32)cm.gate_p2[g];
+      d.gate_param3[g] = (u32)cm.gate_p3[g];
+      d.gate_selector[g] = (u32)cm.selector_indices[g];
     }
-    RootTab tab_q;
-    QP(get_root_tab(c, (int)qlb, false, &tab_q));
-    QP(dev_alloc(c, sizeof(u64) << qlb, &q->l0_den_inv_dev));
-    k_build_l0_den_inv<<<(unsigned)(((1ull << qlb) + 127) / 128), 128, 0, c->stream>>>(q->l0_den_inv_dev, tab_q,
-                                                                                    (u32)cm.degree_bits, qlb);
-    c->launches++;
-    CU(cudaGetLastError());
+    for (size_t s = 0; s < cm.groups.size(); s++) {
+      d.group_lo[s] = (u32)cm.groups[s].first;
+      d.group_hi[s] = (u32)cm.groups[s].second;
+    }
+    memcpy(q->digest, digest4, 32);
+    // small per-circuit tables: k_is, the coset-interpolation points and weights, Z_H on the quotient coset.
+    // They are staged through host vectors that live until the wait below.
+    QP(dev_alloc(c, (cm.k_is.size() ? cm.k_is.size() : 1) * 8, &q->k_is_dev));
+    CU(cudaMemcpyAsync(q->k_is_dev, cm.k_is.data(), cm.k_is.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    std::vector<u64> aux;
+    if (!cm.coset_weights.empty()) {  // subgroup points, then the barycentric weights from the common data
+      const size_t np = cm.coset_weights.size();
+      u32 bits = 0;
+      while ((1ull << bits) < np) bits++;
+      aux.resize(2 * np);
+      u64 g = glh::root_of_unity(bits);
+      aux[0] = 1;
+      for (size_t i = 1; i < np; i++) aux[i] = glh::mul(aux[i - 1], g);
+      for (size_t i = 0; i < np; i++) aux[np + i] = cm.coset_weights[i];
+      QP(dev_alloc(c, aux.size() * 8, &q->coset_aux_dev));
+      CU(cudaMemcpyAsync(q->coset_aux_dev, aux.data(), aux.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      d.coset_aux = q->coset_aux_dev;
+    }
+    std::vector<u64> zh(2u << qdb);
+    {
+      u64 gn = glh::pow(GL_GEN, n), wq = glh::root_of_unity(qdb);
+      for (u32 i = 0; i < (1u << qdb); i++) {
+        zh[i] = glh::sub(glh::mul(gn, glh::pow(wq, i)), 1);
+        zh[(1u << qdb) + i] = glh::inv(zh[i]);
+      }
+    }
+    QP(dev_alloc(c, zh.size() * 8, &q->zh_dev));
+    CU(cudaMemcpyAsync(q->zh_dev, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
+    CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
+    // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
+    QP(commit_impl(c, q->cs_values, false, false, ncs, (u32)cm.degree_bits, (u32)cm.rate_bits, (u32)cm.cap_height, nullptr,
+                   false, 0, &q->cs_batch));
+    q->cs_cap.resize(4ull << cm.cap_height);
+    QP(qpzk_batch_cap(q->cs_batch, q->cs_cap.data()));
+    {
+      const u32 qlb = (u32)cm.degree_bits + qdb;
+      RootTab tab_q;
+      QP(get_root_tab(c, (int)qlb, false, &tab_q));
+      QP(dev_alloc(c, sizeof(u64) << qlb, &q->l0_den_inv_dev));
+      k_build_l0_den_inv<<<(unsigned)(((1ull << qlb) + 127) / 128), 128, 0, c->stream>>>(q->l0_den_inv_dev, tab_q,
+                                                                                      (u32)cm.degree_bits, qlb);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
+    layout_arena(cm, d, &q->lay);
+    QP(dev_alloc(c, q->lay.total * 8, &q->arena_dev));
+    CU(cudaHostAlloc((void**)&q->arena_host, q->lay.total * 8, cudaHostAllocDefault));
+    for (auto& e : q->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&q->done, cudaEventBlockingSync | cudaEventDisableTiming));
     CU(ctx_wait(c));
-  }
-  *out = q;
-  return QPZK_OK;
+    *out = q.release();
+    return QPZK_OK;
+  });
 }
 
-int qpzk_circuit_cap(const qpzk_circuit* q, uint64_t* out) {
+int qpzk_circuit_cap(const qpzk_circuit* q, uint64_t* out, size_t cap_words) {
   if (!q || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (cap_words < q->cs_cap.size()) return fail(QPZK_ERR_BAD_ARG, "buffer too small for 2^cap_height digests");
   memcpy(out, q->cs_cap.data(), q->cs_cap.size() * 8);
+  return QPZK_OK;
+}
+int qpzk_circuit_info(const qpzk_circuit* q, uint32_t* out) {
+  if (!q || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  const CommonHost& cm = q->common;
+  const uint32_t v[8] = {(uint32_t)cm.degree_bits, (uint32_t)cm.rate_bits, (uint32_t)cm.cap_height, (uint32_t)cm.num_wires,
+                         (uint32_t)cm.num_routed, (uint32_t)cm.num_challenges, cm.hiding ? QPZK_SALT_SIZE : 0u,
+                         (uint32_t)cm.num_public_inputs};
+  memcpy(out, v, sizeof v);
   return QPZK_OK;
 }
 // VerifierOnlyCircuitData bytes (cap_height, constants_sigmas_cap, circuit_digest); returns length.
 size_t qpzk_circuit_verifier_only(const qpzk_circuit* q, uint8_t* out, size_t cap) {
   if (!q) return 0;
-  ByteWriter w;
-  w.u(q->common.cap_height, 8);
-  w.felts(q->cs_cap.data(), q->cs_cap.size());
-  w.felts(q->digest, 4);
-  if (out && w.b.size() <= cap) memcpy(out, w.b.data(), w.b.size());
-  return w.b.size();
+  try {
+    ByteWriter w;
+    w.u(q->common.cap_height, 8);
+    w.felts(q->cs_cap.data(), q->cs_cap.size());
+    w.felts(q->digest, 4);
+    if (out && w.b.size() <= cap) memcpy(out, w.b.data(), w.b.size());
+    return w.b.size();
+  } catch (...) {
+    return 0;
+  }
 }
 void qpzk_circuit_free(qpzk_circuit* q) {
   if (!q) return;
-  cudaSetDevice(q->ctx->device);
-  dev_free(q->ctx, q->k_is_dev);
-  dev_free(q->ctx, q->coset_aux_dev);
-  dev_free(q->ctx, q->l0_den_inv_dev);
-  dev_free(q->ctx, q->cs_values);
-  qpzk_batch_free(q->cs_batch);
   delete q;
 }
 
@@ -456,10 +629,11 @@ int qpzk_prove_stage_ms(const qpzk_circuit* q, float* out16) {
 
 namespace qpzk {
 
-// Proof of one witness. wires_host: [num_wires][n]. Salts: NULL or host [4][N] per blinded oracle.
 // ---- H11-H14: the FRI prover as a resumable object (prove_openings, fri_committed_trees,
-// fri_prover_query_rounds of qp-plonky2 fri/oracle.rs, fri/prover.rs). The transcript stays with the
-// caller: begin -> [commit_round -> (observe cap, squeeze beta) -> fold]* -> final_poly -> queries. ----
+// fri_prover_query_rounds of qp-plonky2 fri/oracle.rs, fri/prover.rs). Every challenge it needs is a
+// DEVICE pointer: into the transcript when qpzk_prove drives it, into its own small scratch when the caller
+// owns the transcript (qpzk_fri_* hooks): begin -> [commit_round -> (observe cap, squeeze beta) -> fold]*
+// -> final_poly -> queries. ----
 struct FriTree {
   u64* leaves = nullptr;  // AoS [nleaves][2*arity]
   u64* levels = nullptr;
@@ -472,6 +646,7 @@ struct qpzk_fri {
   qpzk_ctx* c = nullptr;
   const qpzk_batch* oracles[4] = {nullptr, nullptr, nullptr, nullptr};
   u64 *fpoly = nullptr, *fold_a = nullptr, *fold_b = nullptr, *vals = nullptr;  // device
+  u64* chal = nullptr;        // hooks only: zeta[2] | zeta_next[2] | alpha[2] | beta[2]
   u64* coeffs_cur = nullptr;  // SoA [2][cur_n]
   u64 cur_n = 0, shift = GL_GEN;
   u32 cur_k = 0;
@@ -489,6 +664,7 @@ struct qpzk_fri {
     dev_free(c, fold_a);
     dev_free(c, fold_b);
     dev_free(c, vals);
+    dev_free(c, chal);
   }
 };
 
@@ -496,12 +672,12 @@ namespace qpzk {
 
 // prove_openings up to the polynomial that enters FRI: batch 0 = every polynomial of the four oracles
 // at zeta, batch 1 = the Z polynomials at g*zeta; final = q0 * alpha^(len batch 1) + q1 (no multiply-by-X).
-static int fri_begin(qpzk_circuit* q, qpzk_batch* const* oracles, const u64* zeta, const u64* alpha, qpzk_fri** out) {
+static int fri_begin(qpzk_circuit* q, const qpzk_batch* const* oracles, const u64* zeta_dev, const u64* zeta_next_dev,
+                     const u64* alpha_dev, qpzk_fri* F) {
   qpzk_ctx* c = q->ctx;
   const CircuitDesc& d = q->desc;
   const u32 k = d.degree_bits, r = d.rate_bits, nch = d.num_challenges;
   const u64 n = 1ull << k, N = n << r;
-  std::unique_ptr<qpzk_fri> F(new qpzk_fri());
   F->q = q;
   F->c = c;
   u32 total_polys = 0;
@@ -509,23 +685,8 @@ static int fri_begin(qpzk_circuit* q, qpzk_batch* const* oracles, const u64* zet
     F->oracles[o] = oracles[o];
     total_polys += oracles[o]->ncols;
   }
-  u64 wn = glh::root_of_unity(k);
-  u64 zeta_next[2] = {glh::mul(zeta[0], wn), glh::mul(zeta[1], wn)};
-  std::vector<u64> apow((size_t)total_polys * 2);
-  {
-    u64 a = 1, b = 0;
-    for (u32 j = 0; j < total_polys; j++) {
-      apow[2 * j] = a;
-      apow[2 * j + 1] = b;
-      u64 na = glh::add(glh::mul(a, alpha[0]), glh::mul(7, glh::mul(b, alpha[1])));
-      u64 nb = glh::add(glh::mul(a, alpha[1]), glh::mul(b, alpha[0]));
-      a = na;
-      b = nb;
-    }
-  }
-  DevBuf apow_dev(c), comp0(c), comp1(c), q0(c), q1(c);
-  QP(apow_dev.alloc(apow.size() * 8));
-  CU(cudaMemcpyAsync(apow_dev.p, apow.data(), apow.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  DevBuf apow(c), comp0(c), comp1(c), q0(c), q1(c);
+  QP(apow.alloc((size_t)total_polys * 16));
   QP(comp0.alloc(n * 16)); QP(comp1.alloc(n * 16)); QP(q0.alloc(n * 16)); QP(q1.alloc(n * 16));
   QP(dev_alloc(c, n * 16, &F->fpoly));
   QP(dev_alloc(c, n * 16 / 2 + 64, &F->fold_a));
@@ -538,24 +699,23 @@ static int fri_begin(qpzk_circuit* q, qpzk_batch* const* oracles, const u64* zet
   PolyList pl1;
   memset(&pl1, 0, sizeof pl1);
   pl1.noracles = 1; pl1.base[0] = oracles[2]->coeffs; pl1.count[0] = nch;
-  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl0, n, apow_dev.p, comp0.p);
-  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl1, n, apow_dev.p, comp1.p);
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp0.p, q0.p, n, gl2{zeta[0], zeta[1]});
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp1.p, q1.p, n, gl2{zeta_next[0], zeta_next[1]});
-  gl2 shift_s = gl2{apow[2 * nch], apow[2 * nch + 1]};
-  k_ext_axpy<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(q0.p, q1.p, shift_s, n, F->fpoly);
-  c->launches += 5;
+  k_ext_powers<<<(unsigned)((total_polys + 127) / 128), 128, 0, c->stream>>>(alpha_dev, total_polys, apow.p);  // alpha^j
+  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl0, n, apow.p, comp0.p);
+  k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl1, n, apow.p, comp1.p);
+  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp0.p, q0.p, n, zeta_dev);
+  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp1.p, q1.p, n, zeta_next_dev);
+  k_ext_axpy<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(q0.p, q1.p, apow.p + 2ull * nch, n, F->fpoly);
+  c->launches += 6;
   CU(cudaGetLastError());
   F->coeffs_cur = F->fpoly;
   F->cur_n = n;
   F->cur_k = k;
-  *out = F.release();
   return QPZK_OK;
 }
 
 // One commit-phase round: LDE of the current coefficients on the coset shift*<w>, leaves of 2^arity_bits
-// extension evaluations, MerkleTree::new; the cap goes back to the caller's transcript.
-static int fri_commit_round(qpzk_fri* F, u64* cap_out) {
+// extension evaluations, MerkleTree::new. Returns the device pointer of the cap.
+static int fri_commit_round(qpzk_fri* F, const u64** cap_dev) {
   qpzk_ctx* c = F->c;
   const CommonHost& cm = F->q->common;
   const u32 r = F->q->desc.rate_bits, h = (u32)cm.cap_height;
@@ -574,13 +734,12 @@ static int fri_commit_round(qpzk_fri* F, u64* cap_out) {
   k_ext_interleave<<<(unsigned)((NV + 255) / 256), 256, 0, c->stream>>>(F->vals, NV, t.leaves);
   c->launches++;
   QP(build_tree(c, t.leaves, 2ull << ab, 1, 2u << ab, t.log_n, h, t.levels, nullptr));
-  CU(cudaMemcpyAsync(cap_out, cap_ptr(t.levels, t.log_n, h), (size_t)32 << h, cudaMemcpyDeviceToHost, c->stream));
-  CU(ctx_wait(c));
+  *cap_dev = cap_ptr(t.levels, t.log_n, h);
   return QPZK_OK;
 }
 
 // Fold in coefficient space: chunks of 2^arity_bits coefficients combined with powers of beta.
-static int fri_fold(qpzk_fri* F, u64 b0, u64 b1) {
+static int fri_fold(qpzk_fri* F, const u64* beta_dev) {
   qpzk_ctx* c = F->c;
   const CommonHost& cm = F->q->common;
   if (F->round >= cm.arities.size() || F->trees.size() != F->round + 1) return fail(QPZK_ERR_BAD_ARG, "FRI fold out of order");
@@ -588,7 +747,7 @@ static int fri_fold(qpzk_fri* F, u64 b0, u64 b1) {
   u64* dst = F->flip ? F->fold_b : F->fold_a;
   F->flip = !F->flip;
   u64 n_out = F->cur_n >> ab;
-  k_fri_fold<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(F->coeffs_cur, F->cur_n, (u32)ab, gl2{b0, b1}, dst);
+  k_fri_fold<<<(unsigned)((n_out + 127) / 128), 128, 0, c->stream>>>(F->coeffs_cur, F->cur_n, (u32)ab, beta_dev, dst);
   c->launches++;
   CU(cudaGetLastError());
   F->coeffs_cur = dst;
@@ -599,71 +758,32 @@ static int fri_fold(qpzk_fri* F, u64 b0, u64 b1) {
   return QPZK_OK;
 }
 
-// The polynomial left after the last fold, as interleaved extension coefficients [len][2].
-static int fri_final_poly(qpzk_fri* F, std::vector<u64>* out) {
-  qpzk_ctx* c = F->c;
-  if (F->round != F->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
-  const u64 m = F->cur_n;
-  std::vector<u64> soa(2 * m);
-  out->resize(2 * m);
-  CU(cudaMemcpyAsync(soa.data(), F->coeffs_cur, m * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(soa.data() + m, F->coeffs_cur + m, m * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(ctx_wait(c));
-  for (u64 i = 0; i < m; i++) {
-    (*out)[2 * i] = soa[i];
-    (*out)[2 * i + 1] = soa[m + i];
-  }
-  return QPZK_OK;
-}
-
-// fri_prover_query_rounds for nq indices at once. init_open[o] = nq x (salted row | path), step_open[s] =
-// nq x (2^arity ext evaluations | path).
-static int fri_queries(qpzk_fri* F, const u64* xidx, u32 nq, std::vector<std::vector<u64>>* init_open,
-                       std::vector<std::vector<u64>>* step_open) {
+// fri_prover_query_rounds for nq indices at once (indices on the device). init_out[o] = nq x (salted row | path),
+// step_out[s] = nq x (2^arity ext evaluations | path): device destinations.
+static int fri_queries(qpzk_fri* F, const u64* xidx_dev, u32 nq, u64* const* init_out, u64* const* step_out) {
   qpzk_ctx* c = F->c;
   const CircuitDesc& d = F->q->desc;
   const u32 h = (u32)F->q->common.cap_height, lb = d.degree_bits + d.rate_bits;
-  const u64 N = 1ull << lb;
-  const u32 L0 = lb - h;
-  DevBuf xdev(c);
-  QP(xdev.alloc((size_t)nq * 8));
-  CU(cudaMemcpyAsync(xdev.p, xidx, (size_t)nq * 8, cudaMemcpyHostToDevice, c->stream));
-  init_open->assign(4, {});
-  step_open->assign(F->trees.size(), {});
-  std::vector<std::unique_ptr<DevBuf>> keep;
   for (int o = 0; o < 4; o++) {
-    u32 width = F->oracles[o]->width();
-    size_t per = width + 4ull * L0;
-    keep.emplace_back(new DevBuf(c));
-    QP(keep.back()->alloc(per * nq * 8));
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(F->oracles[o]->lde, 1, N, width, F->oracles[o]->levels, lb, h, xdev.p, 0,
-                                                 keep.back()->p);
+    const qpzk_batch* b = F->oracles[o];
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(b->lde, 1, b->lde_stride, b->width(), b->levels, lb, h, xidx_dev, 0, init_out[o]);
     c->launches++;
-    (*init_open)[o].resize(per * nq);
-    CU(cudaMemcpyAsync((*init_open)[o].data(), keep.back()->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   u32 sh = 0;
   for (size_t s = 0; s < F->trees.size(); s++) {
     const FriTree& t = F->trees[s];
     sh += t.arity_bits;
-    u32 width = 2u << t.arity_bits, L = t.log_n - h;
-    size_t per = width + 4ull * L;
-    keep.emplace_back(new DevBuf(c));
-    QP(keep.back()->alloc(per * nq * 8));
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(t.leaves, width, 1, width, t.levels, t.log_n, h, xdev.p, sh,
-                                                 keep.back()->p);
+    const u32 width = 2u << t.arity_bits;
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(t.leaves, width, 1, width, t.levels, t.log_n, h, xidx_dev, sh, step_out[s]);
     c->launches++;
-    (*step_open)[s].resize(per * nq);
-    CU(cudaMemcpyAsync((*step_open)[s].data(), keep.back()->p, per * nq * 8, cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaGetLastError());
-  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
 // ---- H8: Z and partial products on the subgroup: zs_vals [nch*(1+npp)][n] = Z_0..Z_{nch-1}, then the
 // partial products of each challenge (all_wires_permutation_partial_products + the running product) ----
-static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, const Challenges& chal, DevBuf* zs_vals) {
+static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, const Challenges* chal_dev, DevBuf* zs_vals) {
   qpzk_ctx* c = q->ctx;
   const CircuitDesc& d = q->desc;
   const u32 k = d.degree_bits, nch = d.num_challenges, npp = d.num_partial_products;
@@ -676,7 +796,7 @@ static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, co
   QP(row_prod.alloc((size_t)nch * n * 8));
   QP(zs_vals->alloc((size_t)nzs * n * 8));
   k_zs_chunk_quotients<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(
-      wires_dev, q->cs_values, q->k_is_dev, d, chal, tab_n, chunk_q.p, row_prod.p);
+      wires_dev, q->cs_values, q->k_is_dev, d, chal_dev, tab_n, chunk_q.p, row_prod.p);
   k_prefix_product<<<nch, 1024, 0, c->stream>>>(row_prod.p, zs_vals->p, n);
   k_partial_products<<<dim3((unsigned)((n + 127) / 128), nch), 128, 0, c->stream>>>(chunk_q.p, zs_vals->p, nch, npp, n,
                                                                                    zs_vals->p + (size_t)nch * n);
@@ -686,50 +806,31 @@ static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, co
 }
 
 // ---- H9: compute_quotient_polys: vanishing(x)/Z_H(x) on the quotient coset from the three committed
-// oracles, coset IFFT, coefficients [nch][qdf*n] (= nch*qdf chunks of n) ----
-static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash,
-                                   const Challenges& chal, DevBuf* qcoeffs) {
+// oracles, coset IFFT, coefficients [nch][qdf*n] (= nch*qdf chunks of n). apw_dev: alpha powers
+// [nch][QPZK_APW_STRIDE] (k_alpha_powers); chal_dev / pi_hash_dev: device pointers ----
+static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash_dev,
+                                   const Challenges* chal_dev, const u64* apw_dev, DevBuf* qcoeffs) {
   qpzk_ctx* c = q->ctx;
   const CommonHost& cm = q->common;
   const CircuitDesc& d = q->desc;
   const u32 k = d.degree_bits, r = d.rate_bits, nch = d.num_challenges, qdb = d.quotient_degree_bits;
-  const u64 n = 1ull << k, N = n << r;
   const u32 qlb = k + qdb;
   const u64 qlde = 1ull << qlb;
-  std::vector<u64> zh(1u << qdb), zh_inv(1u << qdb);
-  {
-    u64 gn = glh::pow(GL_GEN, n), wq = glh::root_of_unity(qdb);
-    for (u32 i = 0; i < (1u << qdb); i++) {
-      zh[i] = glh::sub(glh::mul(gn, glh::pow(wq, i)), 1);
-      zh_inv[i] = glh::inv(zh[i]);
-    }
-  }
-  DevBuf small(c), qvals(c);
-  std::vector<u64> apw(2 * QPZK_APW_STRIDE, 0);   // alpha_c^t for the reduction of the constraint terms
-  for (u32 ci = 0; ci < nch; ci++) {
-    u64 pwr = 1;
-    for (u32 t = 0; t < QPZK_APW_STRIDE; t++) {
-      apw[ci * QPZK_APW_STRIDE + t] = pwr;
-      pwr = glh::mul(pwr, chal.alpha[ci]);
-    }
-  }
-  QP(small.alloc((4 + 2 * (1u << qdb) + 2 * QPZK_APW_STRIDE) * 8));
-  CU(cudaMemcpyAsync(small.p + 4 + 2 * (1u << qdb), apw.data(), apw.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p, pi_hash, 32, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p + 4, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(small.p + 4 + zh.size(), zh_inv.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  DevBuf qvals(c);
   QP(qvals.alloc((size_t)nch * qlde * 8));
   QP(qcoeffs->alloc((size_t)nch * qlde * 8));
   RootTab tab_q;
   QP(get_root_tab(c, (int)qlb, false, &tab_q));
+  const u64* zh = q->zh_dev;
+  const u64* zh_inv = q->zh_dev + (1u << qdb);
   if (cm.recursion)
     k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
-        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, q->cs_batch->lde_stride, wires_b->lde_stride, zs_b->lde_stride, r - qdb,
+        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, qvals.p);
   else
     k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
-        q->cs_batch->lde, wires_b->lde, zs_b->lde, N, N, N, r - qdb, q->k_is_dev, d, chal, small.p, small.p + 4,
-        small.p + 4 + zh.size(), small.p + 4 + 2 * zh.size(), q->l0_den_inv_dev, tab_q, qvals.p);
+        q->cs_batch->lde, wires_b->lde, zs_b->lde, q->cs_batch->lde_stride, wires_b->lde_stride, zs_b->lde_stride, r - qdb,
+        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, qvals.p);
   c->launches++;
   CU(cudaGetLastError());
   // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)
@@ -739,80 +840,72 @@ static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, c
   k_scale_by_powers<<<dim3((unsigned)((qlde + 255) / 256), nch), 256, 0, c->stream>>>(qcoeffs->p, qlde, tab_ginv);
   c->launches++;
   CU(cudaGetLastError());
-  // the small staging vectors above are pageable host memory: the copies must have left before they die
-  CU(ctx_wait(c));
   return QPZK_OK;
 }
 
-static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u32 npi, const u64* salt_w,
-                      const u64* salt_z, const u64* salt_q, u32 flags, std::vector<uint8_t>* proof) {
+static inline void tr_step(qpzk_ctx* c, TranscriptDev* T, const u64* src, u32 n, u32 src_mode, u64 m, u64* copy, u32 nsq1,
+                           u32 dst1, u32 nsq2, u32 dst2, u32 post, u64 aux) {
+  k_transcript_step<<<1, 16, 0, c->stream>>>(T, src, n, src_mode, m, copy, nsq1, dst1, nsq2, dst2, post, aux);
+  c->launches++;
+}
+
+// One proof, enqueued: the order of operations of `prove()` with NO host synchronisation. Everything lands
+// in the circuit's arena; prove_finish waits once and serialises.
+static int prove_enqueue(qpzk_circuit* q, const u64* wires_in, const u64* pis, u32 npi, const u64* salt_w,
+                         const u64* salt_z, const u64* salt_q, u32 flags) {
   qpzk_ctx* c = q->ctx;
   const CommonHost& cm = q->common;
   const CircuitDesc& d = q->desc;
+  const ArenaLayout& L = q->lay;
   const u32 k = d.degree_bits, r = d.rate_bits, h = (u32)cm.cap_height, nch = d.num_challenges;
   const u32 npp = d.num_partial_products, nw = d.num_wires, qdf = d.qdf, qdb = d.quotient_degree_bits;
   const u64 n = 1ull << k, N = n << r;
-  const u32 lb = k + r;
   const u32 salt_cols = cm.hiding ? QPZK_SALT_SIZE : 0;
-  if (cm.hiding && !(salt_w && salt_z && salt_q)) return fail(QPZK_ERR_BAD_ARG, "hiding circuit needs salts");
-  if (npi != cm.num_public_inputs) return fail(QPZK_ERR_BAD_ARG, "public input count mismatch");
   const bool want_trace = flags & 1;
   const bool on_device = flags & 2;  // wires / salts are device pointers (HBM-resident witness)
-  cudaEvent_t evs[2];
-  CU(cudaEventCreate(&evs[0]));
-  CU(cudaEventCreate(&evs[1]));
-  int stage = 0;
-  memset(q->stage_ms, 0, sizeof q->stage_ms);
-  auto tic = [&]() { cudaEventRecord(evs[0], c->stream); };
-  auto toc = [&]() {
-    cudaEventRecord(evs[1], c->stream);
-    cudaEventSynchronize(evs[1]);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, evs[0], evs[1]);
-    if (stage < 16) q->stage_ms[stage++] = ms;
-  };
+  TranscriptDev* T = q->transcript();
+  u64* A = q->arena_dev;
 
-  u64 pi_hash[4];
-  host_hash_no_pad(pis, npi, pi_hash);
-  HostChallenger ch;
-  ch.observe_n(q->digest, 4);
-  ch.observe_n(pi_hash, 4);
+  // the transcript up to the first commitment is host work on inputs only: circuit digest | H(public inputs)
+  TranscriptInit init;
+  {
+    host_hash_no_pad(pis, npi, init.pi_hash);
+    HostChallenger ch;
+    ch.observe_n(q->digest, 4);
+    ch.observe_n(init.pi_hash, 4);   // the eighth observation runs the duplex
+    memcpy(init.state, ch.state, sizeof init.state);
+  }
+  q->pis.assign(npi, 0);
+  for (u32 i = 0; i < npi; i++) q->pis[i] = pis[i] >= GL_P ? pis[i] - GL_P : pis[i];
+  q->want_trace = want_trace;
+  memset(q->stage_ms, 0, sizeof q->stage_ms);
+  k_transcript_init<<<1, 32, 0, c->stream>>>(T, init);
+  c->launches++;
 
   // ---- (2) commit wires ----
-  tic();
+  CU(cudaEventRecord(q->ev[0], c->stream));
   DevBuf wires_up(c);
-  const u64* wires_dev = wires_host;
+  const u64* wires_dev = wires_in;
   if (!on_device) {
     QP(wires_up.alloc((size_t)nw * n * 8));
-    CU(cudaMemcpyAsync(wires_up.p, wires_host, (size_t)nw * n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(wires_up.p, wires_in, (size_t)nw * n * 8, cudaMemcpyHostToDevice, c->stream));
     wires_dev = wires_up.p;
   }
-  qpzk_batch* wires_b = nullptr;
-  QP(commit_impl(c, wires_dev, false, false, nw, k, r, h, cm.hiding ? salt_w : nullptr, !on_device, salt_cols, &wires_b));
-  std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> wires_guard(wires_b, qpzk_batch_free);
-  std::vector<u64> cap(4ull << h);
-  QP(qpzk_batch_cap(wires_b, cap.data()));
-  std::vector<u64> wires_cap = cap;
-  ch.observe_n(cap.data(), cap.size());
-  toc();  // stage 0: wires commit
-  Challenges chal;
-  memset(&chal, 0, sizeof chal);
-  for (u32 i = 0; i < nch; i++) chal.beta[i] = ch.get();
-  for (u32 i = 0; i < nch; i++) chal.gamma[i] = ch.get();
+  qpzk_batch* raw = nullptr;
+  QP(commit_impl(c, wires_dev, false, false, nw, k, r, h, cm.hiding ? salt_w : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
+  std::unique_ptr<qpzk_batch> wires_b(raw);
+  tr_step(c, T, cap_ptr(wires_b->levels, k + r, h), L.capw, 0, 0, A + L.caps, nch, QPZK_TR_OFF(ch.beta), nch,
+          QPZK_TR_OFF(ch.gamma), 0, 0);
+  CU(cudaEventRecord(q->ev[1], c->stream));  // stage 0: wires commit
 
   // ---- (4,5) Z + partial products, commit ----
-  tic();
   const u32 nzs = nch * (1 + npp);
   DevBuf zs_vals(c);
-  QP(compute_zs_partial_products(q, wires_dev, chal, &zs_vals));
-  qpzk_batch* zs_b = nullptr;
-  QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, !on_device, salt_cols, &zs_b));
-  std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> zs_guard(zs_b, qpzk_batch_free);
-  QP(qpzk_batch_cap(zs_b, cap.data()));
-  std::vector<u64> zs_cap = cap;
-  ch.observe_n(cap.data(), cap.size());
-  toc();  // stage 1: Z/pp + commit
-  for (u32 i = 0; i < nch; i++) chal.alpha[i] = ch.get();
+  QP(compute_zs_partial_products(q, wires_dev, &T->ch, &zs_vals));
+  QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
+  std::unique_ptr<qpzk_batch> zs_b(raw);
+  tr_step(c, T, cap_ptr(zs_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + L.capw, nch, QPZK_TR_OFF(ch.alpha), 0, 0, 0, 0);
+  CU(cudaEventRecord(q->ev[2], c->stream));  // stage 1: Z/pp + commit
   if (want_trace) {
     q->tr_zs_pp.resize((size_t)nzs * n);
     CU(cudaMemcpyAsync(q->tr_zs_pp.data(), zs_vals.p, (size_t)nzs * n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -820,68 +913,55 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
   }
 
   // ---- (6,7) quotient ----
-  tic();
   const u32 qlb = k + qdb;
   const u64 qlde = 1ull << qlb;
-  DevBuf qcoeffs(c);
-  QP(compute_quotient_chunks(q, wires_b, zs_b, pi_hash, chal, &qcoeffs));
-  qpzk_batch* q_b = nullptr;
-  QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, !on_device, salt_cols, &q_b));
-  std::unique_ptr<qpzk_batch, void (*)(qpzk_batch*)> q_guard(q_b, qpzk_batch_free);
-  QP(qpzk_batch_cap(q_b, cap.data()));
-  std::vector<u64> q_cap = cap;
-  ch.observe_n(cap.data(), cap.size());
-  toc();  // stage 2: quotient + commit
+  DevBuf qcoeffs(c), apw(c);
+  QP(apw.alloc((size_t)2 * QPZK_APW_STRIDE * 8));
+  k_alpha_powers<<<nch, 256, 0, c->stream>>>(T, QPZK_APW_STRIDE, apw.p);
+  c->launches++;
+  QP(compute_quotient_chunks(q, wires_b.get(), zs_b.get(), T->pi_hash, &T->ch, apw.p, &qcoeffs));
+  QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
+  std::unique_ptr<qpzk_batch> q_b(raw);
+  tr_step(c, T, cap_ptr(q_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + 2 * (size_t)L.capw, 2, QPZK_TR_OFF(zeta), 0, 0, 1,
+          glh::root_of_unity(k));
+  CU(cudaEventRecord(q->ev[3], c->stream));  // stage 2: quotient + commit
   if (want_trace) {
     q->tr_quotient.resize((size_t)nch * qlde);
     CU(cudaMemcpyAsync(q->tr_quotient.data(), qcoeffs.p, (size_t)nch * qlde * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(ctx_wait(c));
   }
-  u64 zeta[2] = {ch.get(), 0};
-  zeta[1] = ch.get();
 
-  // ---- (8) openings ----
-  tic();
-  qpzk_batch* oracles[4] = {q->cs_batch, wires_b, zs_b, q_b};
-  u32 total_polys = 0;
-  for (auto* b : oracles) total_polys += b->ncols;
-  u64 wn = glh::root_of_unity(k);
-  u64 zeta_next[2] = {glh::mul(zeta[0], wn), glh::mul(zeta[1], wn)};
-  DevBuf zpow(c), zpow_next(c), open_dev(c);
+  // ---- (8) openings: observe order constants, sigmas, wires, zs, partial_products, quotient (= oracle
+  // order), then zs_next ----
+  const qpzk_batch* oracles[4] = {q->cs_batch, wires_b.get(), zs_b.get(), q_b.get()};
+  const u32 total_polys = L.total_polys;
+  DevBuf zpow(c), zpow_next(c);
   QP(zpow.alloc(n * 16));
   QP(zpow_next.alloc(n * 16));
-  QP(open_dev.alloc((size_t)(total_polys + nch) * 16));
-  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(gl2{zeta[0], zeta[1]}, n, zpow.p);
-  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(gl2{zeta_next[0], zeta_next[1]}, n, zpow_next.p);
+  u64* open_dev = A + L.opens;
+  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta, n, zpow.p);
+  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta_next, n, zpow_next.p);
   c->launches += 2;
   {
     u32 off = 0;
     for (auto* b : oracles) {
-      k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, open_dev.p + 2ull * off);
+      k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, open_dev + 2ull * off);
       off += b->ncols;
       c->launches++;
     }
-    k_eval_at_ext<<<nch, 256, 0, c->stream>>>(zs_b->coeffs, n, zpow_next.p, open_dev.p + 2ull * off);
+    k_eval_at_ext<<<nch, 256, 0, c->stream>>>(zs_b->coeffs, n, zpow_next.p, open_dev + 2ull * off);
     c->launches++;
   }
   CU(cudaGetLastError());
-  std::vector<u64> opens((size_t)(total_polys + nch) * 2);
-  CU(cudaMemcpyAsync(opens.data(), open_dev.p, opens.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(ctx_wait(c));
-  // observe order: constants, sigmas, wires, zs, partial_products, quotient (= oracle order) then zs_next
-  ch.observe_n(opens.data(), opens.size());
-  toc();  // stage 3: openings
-  u64 alpha[2] = {ch.get(), 0};
-  alpha[1] = ch.get();
+  tr_step(c, T, open_dev, 2 * (total_polys + nch), 0, 0, nullptr, 2, QPZK_TR_OFF(fri_alpha), 0, 0, 0, 0);
+  CU(cudaEventRecord(q->ev[4], c->stream));  // stage 3: openings
 
   // ---- (9) FRI: batch combine ----
-  tic();
-  qpzk_fri* F = nullptr;
-  QP(fri_begin(q, oracles, zeta, alpha, &F));
-  std::unique_ptr<qpzk_fri> fri_guard(F);
+  qpzk_fri F;
+  QP(fri_begin(q, oracles, T->zeta, T->zeta_next, T->fri_alpha, &F));
   if (want_trace) {
     std::vector<u64> soa(2 * n);
-    CU(cudaMemcpyAsync(soa.data(), F->fpoly, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(soa.data(), F.fpoly, n * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(ctx_wait(c));
     q->tr_final_poly.resize(2 * n);
     for (u64 m = 0; m < n; m++) {
@@ -889,62 +969,73 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
       q->tr_final_poly[2 * m + 1] = soa[n + m];
     }
   }
-  toc();  // stage 4: FRI combine
+  CU(cudaEventRecord(q->ev[5], c->stream));  // stage 4: FRI combine
 
   // ---- (9) FRI: commit phase ----
-  tic();
-  std::vector<std::vector<u64>> fri_caps;
-  std::vector<u64> fri_betas;
   for (size_t round = 0; round < cm.arities.size(); round++) {
-    std::vector<u64> fc(4ull << h);
-    QP(fri_commit_round(F, fc.data()));
-    ch.observe_n(fc.data(), fc.size());
-    fri_caps.push_back(fc);
-    u64 b0 = ch.get(), b1 = ch.get();
-    fri_betas.push_back(b0);
-    fri_betas.push_back(b1);
-    QP(fri_fold(F, b0, b1));
+    const u64* cap_dev = nullptr;
+    QP(fri_commit_round(&F, &cap_dev));
+    tr_step(c, T, cap_dev, L.capw, 0, 0, A + L.fri_caps + round * (size_t)L.capw, 2, QPZK_TR_OFF(fri_beta) + 2 * (u32)round, 0, 0,
+            0, 0);
+    QP(fri_fold(&F, T->fri_beta[round]));
   }
-  std::vector<u64> final_poly;
-  QP(fri_final_poly(F, &final_poly));
-  ch.observe_n(final_poly.data(), final_poly.size());
-  toc();  // stage 5: FRI commit phase
+  // the polynomial left after the last fold, observed (and stored) as interleaved extension coefficients
+  tr_step(c, T, F.coeffs_cur, 2 * (u32)F.cur_n, 1, F.cur_n, A + L.final_poly, 0, 0, 0, 0, 0, 0);
+  CU(cudaEventRecord(q->ev[6], c->stream));  // stage 5: FRI commit phase
 
-  // ---- (9) proof of work ----
-  tic();
-  u64 pow_witness = 0;
-  {
-    PowState ps;
-    memcpy(ps.s, ch.state, sizeof ps.s);
-    u32 pos = (u32)ch.in.size();
-    for (u32 i = 0; i < pos; i++) ps.s[i] = ch.in[i];
-    QP(grind_pow(c, ps, pos, cm.pow_bits, &pow_witness));
-  }
-  ch.observe(pow_witness);
-  u64 pow_resp = ch.get();
-  if ((pow_resp >> (64 - cm.pow_bits)) != 0 && cm.pow_bits) return fail(QPZK_ERR_CUDA, "pow response mismatch");
-  toc();  // stage 6: PoW
+  // ---- (9) proof of work, then the response and the query indices ----
+  k_pow_grind_dev<<<pow_grid_blocks(cm.pow_bits), 128, 0, c->stream>>>(T, cm.pow_bits);
+  c->launches++;
+  const u32 nq = (u32)cm.num_queries;
+  tr_step(c, T, &T->pow_witness, 1, 0, 0, nullptr, 1 + nq, QPZK_TR_OFF(pow_resp), 0, 0, 2, N - 1);
+  CU(cudaEventRecord(q->ev[7], c->stream));  // stage 6: PoW
 
   // ---- (9) query rounds ----
-  tic();
-  const u32 nq = (u32)cm.num_queries;
-  std::vector<u64> xidx(nq);
-  for (u32 i = 0; i < nq; i++) xidx[i] = ch.get() & (N - 1);
-  std::vector<std::vector<u64>> init_open, step_open;
-  const u32 L0 = lb - h;
-  QP(fri_queries(F, xidx.data(), nq, &init_open, &step_open));
-  toc();  // stage 7: queries
+  u64* init_out[4];
+  u64* step_out[QPZK_MAX_FRI_ROUNDS];
+  for (int o = 0; o < 4; o++) init_out[o] = A + L.init_open[o];
+  for (size_t s = 0; s < cm.arities.size(); s++) step_out[s] = A + L.step_open[s];
+  QP(fri_queries(&F, T->xidx, nq, init_out, step_out));
+  CU(cudaEventRecord(q->ev[8], c->stream));  // stage 7: queries
 
-  // ---- (10) ProofWithPublicInputs::to_bytes ----
+  CU(cudaMemcpyAsync(q->arena_host, q->arena_dev, L.total * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(q->done, c->stream));
+  // F, the three batches and every scratch buffer are released here in stream order
+  return QPZK_OK;
+}
+
+// Wait for the proof in flight (the way the context waits), then ProofWithPublicInputs::to_bytes from the
+// pinned arena.
+static int prove_finish(qpzk_circuit* q, std::vector<uint8_t>* proof) {
+  qpzk_ctx* c = q->ctx;
+  const CommonHost& cm = q->common;
+  const CircuitDesc& d = q->desc;
+  const ArenaLayout& L = q->lay;
+  cudaError_t e;
+  if (c->blocking_sync)
+    e = cudaEventSynchronize(q->done);
+  else if (c->yield_sync) {
+    while ((e = cudaEventQuery(q->done)) == cudaErrorNotReady) sched_yield();
+  } else {
+    while ((e = cudaEventQuery(q->done)) == cudaErrorNotReady) {
+    }
+  }
+  CU(e);
+  for (int i = 0; i < 8; i++) cudaEventElapsedTime(&q->stage_ms[i], q->ev[i], q->ev[i + 1]);
+  const u64* H = q->arena_host;
+  const TranscriptDev* T = reinterpret_cast<const TranscriptDev*>(H);
+  const u32 nch = d.num_challenges, npp = d.num_partial_products, nw = d.num_wires, qdf = d.qdf;
+  const u32 nzs = nch * (1 + npp), nq = (u32)cm.num_queries;
+  if (T->pow_witness == ~0ull) return fail(QPZK_ERR_CUDA, "proof of work failed");
+  if (cm.pow_bits && (T->pow_resp >> (64 - cm.pow_bits)) != 0) return fail(QPZK_ERR_CUDA, "pow response mismatch");
   ByteWriter w;
-  w.felts(wires_cap.data(), wires_cap.size());
-  w.felts(zs_cap.data(), zs_cap.size());
-  w.felts(q_cap.data(), q_cap.size());
+  w.b.reserve(L.total * 8 + 64 * nq + 64);
+  w.felts(H + L.caps, 3 * (size_t)L.capw);
   {
     // openings in serialised order: constants, sigmas, wires, zs, zs_next, partial_products, quotient
-    const u64* o = opens.data();
+    const u64* o = H + L.opens;
     size_t n_cs = (size_t)(cm.num_constants + cm.num_routed), off_w = n_cs, off_z = off_w + nw;
-    size_t off_pp = off_z + nch, off_q = off_z + nzs, off_next = total_polys;
+    size_t off_pp = off_z + nch, off_q = off_z + nzs, off_next = L.total_polys;
     w.felts(o, 2 * n_cs);
     w.felts(o + 2 * off_w, 2ull * nw);
     w.felts(o + 2 * off_z, 2ull * nch);
@@ -952,41 +1043,41 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
     w.felts(o + 2 * off_pp, 2ull * nch * npp);
     w.felts(o + 2 * off_q, 2ull * nch * qdf);
   }
-  for (auto& fc : fri_caps) w.felts(fc.data(), fc.size());
+  w.felts(H + L.fri_caps, cm.arities.size() * (size_t)L.capw);
   for (u32 qi = 0; qi < nq; qi++) {
     for (int o = 0; o < 4; o++) {
-      u32 width = oracles[o]->width();
-      size_t per = width + 4ull * L0;
-      const u64* p = init_open[o].data() + per * qi;
+      const u32 width = L.width[o];
+      const size_t per = width + 4ull * L.L0;
+      const u64* p = H + L.init_open[o] + per * qi;
       w.felts(p, width);
-      w.u(L0, 1);
-      w.felts(p + width, 4ull * L0);
+      w.u(L.L0, 1);
+      w.felts(p + width, 4ull * L.L0);
     }
-    for (size_t s = 0; s < step_open.size(); s++) {
-      u32 width = 2u << cm.arities[s];
-      u32 L = (u32)((step_open[s].size() / nq - width) / 4);
-      const u64* p = step_open[s].data() + (size_t)(width + 4ull * L) * qi;
+    for (size_t s = 0; s < cm.arities.size(); s++) {
+      const u32 width = L.step_width[s], Ls = L.step_L[s];
+      const u64* p = H + L.step_open[s] + (size_t)(width + 4ull * Ls) * qi;
       w.felts(p, width);
-      w.u(L, 1);
-      w.felts(p + width, 4ull * L);
+      w.u(Ls, 1);
+      w.felts(p + width, 4ull * Ls);
     }
   }
-  w.felts(final_poly.data(), final_poly.size());
-  w.u(pow_witness, 8);
-  w.u(npi, 8);
-  for (u32 i = 0; i < npi; i++) w.u(pis[i] >= GL_P ? pis[i] - GL_P : pis[i], 8);
+  w.felts(H + L.final_poly, 2 * (size_t)L.final_len);
+  w.u(T->pow_witness, 8);
+  w.u(q->pis.size(), 8);
+  w.felts(q->pis.data(), q->pis.size());
   *proof = std::move(w.b);
-  if (want_trace) {
+  if (q->want_trace) {
     q->tr_challenges.clear();
-    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(chal.beta[i]);
-    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(chal.gamma[i]);
-    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(chal.alpha[i]);
-    q->tr_challenges.push_back(zeta[0]); q->tr_challenges.push_back(zeta[1]);
-    q->tr_challenges.push_back(alpha[0]); q->tr_challenges.push_back(alpha[1]);
-    for (u64 b : fri_betas) q->tr_challenges.push_back(b);
+    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(T->ch.beta[i]);
+    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(T->ch.gamma[i]);
+    for (u32 i = 0; i < nch; i++) q->tr_challenges.push_back(T->ch.alpha[i]);
+    q->tr_challenges.push_back(T->zeta[0]); q->tr_challenges.push_back(T->zeta[1]);
+    q->tr_challenges.push_back(T->fri_alpha[0]); q->tr_challenges.push_back(T->fri_alpha[1]);
+    for (size_t s = 0; s < cm.arities.size(); s++) {
+      q->tr_challenges.push_back(T->fri_beta[s][0]);
+      q->tr_challenges.push_back(T->fri_beta[s][1]);
+    }
   }
-  cudaEventDestroy(evs[0]);
-  cudaEventDestroy(evs[1]);
   return QPZK_OK;
 }
 
@@ -994,138 +1085,255 @@ static int prove_impl(qpzk_circuit* q, const u64* wires_host, const u64* pis, u3
 
 extern "C" {
 
-static int challenges_from(const qpzk_circuit* q, const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
-                           Challenges* chal) {
-  memset(chal, 0, sizeof *chal);
-  for (u32 i = 0; i < q->desc.num_challenges; i++) {
-    if (betas) chal->beta[i] = betas[i];
-    if (gammas) chal->gamma[i] = gammas[i];
-    if (alphas) chal->alpha[i] = alphas[i];
+// Caller-provided challenges for the per-stage hooks: written into a small device buffer by a kernel.
+static int upload_challenges(qpzk_circuit* q, const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas,
+                             const uint64_t* pi_hash, DevBuf* buf /* Challenges | pi_hash[4] */) {
+  qpzk_ctx* c = q->ctx;
+  QP(buf->alloc(sizeof(Challenges) + 32));
+  const u32 nch = q->desc.num_challenges;
+  Words16 w;
+  memset(&w, 0, sizeof w);
+  for (u32 i = 0; i < nch; i++) {
+    if (betas) w.w[i] = betas[i];
+    if (gammas) w.w[QPZK_MAX_CHALLENGES + i] = gammas[i];
+    if (alphas) w.w[2 * QPZK_MAX_CHALLENGES + i] = alphas[i];
   }
+  for (u32 i = 0; i < 4; i++)
+    if (pi_hash) w.w[3 * QPZK_MAX_CHALLENGES + i] = pi_hash[i];
+  static_assert(sizeof(Challenges) == 3 * QPZK_MAX_CHALLENGES * 8 && 3 * QPZK_MAX_CHALLENGES + 4 <= 16, "Words16 layout");
+  k_set_words<<<1, 32, 0, c->stream>>>(buf->p, w, 3 * QPZK_MAX_CHALLENGES + 4);
+  c->launches++;
+  CU(cudaGetLastError());
   return QPZK_OK;
 }
 
 int qpzk_zs_partial_products(qpzk_circuit* q, const uint64_t* wires, const uint64_t* betas, const uint64_t* gammas,
                              uint64_t* out) {
-  if (!q || !wires || !betas || !gammas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  qpzk_ctx* c = q->ctx;
-  CU(cudaSetDevice(c->device));
-  const CircuitDesc& d = q->desc;
-  const u64 n = 1ull << d.degree_bits;
-  Challenges chal;
-  challenges_from(q, betas, gammas, nullptr, &chal);
-  DevBuf wd(c), zs(c);
-  QP(wd.alloc((size_t)d.num_wires * n * 8));
-  CU(cudaMemcpyAsync(wd.p, wires, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
-  QP(compute_zs_partial_products(q, wd.p, chal, &zs));
-  const size_t cnt = (size_t)d.num_challenges * (1 + d.num_partial_products) * n;
-  CU(cudaMemcpyAsync(out, zs.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(ctx_wait(c));
-  return QPZK_OK;
+  return guarded([&]() -> int {
+    if (!q || !wires || !betas || !gammas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = q->ctx;
+    CU(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    const CircuitDesc& d = q->desc;
+    const u64 n = 1ull << d.degree_bits;
+    DevBuf wd(c), zs(c), chal(c);
+    QP(upload_challenges(q, betas, gammas, nullptr, nullptr, &chal));
+    QP(wd.alloc((size_t)d.num_wires * n * 8));
+    CU(cudaMemcpyAsync(wd.p, wires, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
+    QP(compute_zs_partial_products(q, wd.p, reinterpret_cast<const Challenges*>(chal.p), &zs));
+    const size_t cnt = (size_t)d.num_challenges * (1 + d.num_partial_products) * n;
+    CU(cudaMemcpyAsync(out, zs.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    return QPZK_OK;
+  });
 }
 
 int qpzk_quotient(qpzk_circuit* q, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch, const uint64_t* pi_hash,
                   const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas, uint64_t* out_chunks) {
-  if (!q || !wires_batch || !zs_batch || !pi_hash || !betas || !gammas || !alphas || !out_chunks)
-    return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  qpzk_ctx* c = q->ctx;
-  const CircuitDesc& d = q->desc;
-  if (wires_batch->ctx != c || zs_batch->ctx != c) return fail(QPZK_ERR_BAD_ARG, "batches belong to another context");
-  if (wires_batch->degree_bits != d.degree_bits || zs_batch->degree_bits != d.degree_bits ||
-      wires_batch->rate_bits != d.rate_bits || zs_batch->rate_bits != d.rate_bits || wires_batch->ncols != d.num_wires ||
-      zs_batch->ncols != d.num_challenges * (1 + d.num_partial_products))
-    return fail(QPZK_ERR_BAD_ARG, "batch shape does not match the circuit");
-  CU(cudaSetDevice(c->device));
-  Challenges chal;
-  challenges_from(q, betas, gammas, alphas, &chal);
-  DevBuf qc(c);
-  QP(compute_quotient_chunks(q, wires_batch, zs_batch, pi_hash, chal, &qc));
-  const size_t cnt = ((size_t)d.num_challenges << (d.degree_bits + d.quotient_degree_bits));
-  CU(cudaMemcpyAsync(out_chunks, qc.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(ctx_wait(c));
-  return QPZK_OK;
+  return guarded([&]() -> int {
+    if (!q || !wires_batch || !zs_batch || !pi_hash || !betas || !gammas || !alphas || !out_chunks)
+      return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    if (wires_batch->ctx != c || zs_batch->ctx != c) return fail(QPZK_ERR_BAD_ARG, "batches belong to another context");
+    if (wires_batch->degree_bits != d.degree_bits || zs_batch->degree_bits != d.degree_bits ||
+        wires_batch->rate_bits != d.rate_bits || zs_batch->rate_bits != d.rate_bits || wires_batch->ncols != d.num_wires ||
+        zs_batch->ncols != d.num_challenges * (1 + d.num_partial_products) || wires_batch->sharded() || zs_batch->sharded())
+      return fail(QPZK_ERR_BAD_ARG, "batch shape does not match the circuit");
+    CU(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    DevBuf chal(c), apw(c), qc(c);
+    QP(upload_challenges(q, betas, gammas, alphas, pi_hash, &chal));
+    QP(apw.alloc((size_t)2 * QPZK_APW_STRIDE * 8));
+    {
+      // alpha powers from the uploaded challenges: the Challenges block sits where k_alpha_powers expects
+      // TranscriptDev::ch, so hand it a pointer shifted back by that offset
+      const TranscriptDev* fake = reinterpret_cast<const TranscriptDev*>(reinterpret_cast<const char*>(chal.p) -
+                                                                         offsetof(TranscriptDev, ch));
+      k_alpha_powers<<<d.num_challenges, 256, 0, c->stream>>>(fake, QPZK_APW_STRIDE, apw.p);
+      c->launches++;
+    }
+    const Challenges* ch = reinterpret_cast<const Challenges*>(chal.p);
+    QP(compute_quotient_chunks(q, wires_batch, zs_batch, chal.p + 3 * QPZK_MAX_CHALLENGES, ch, apw.p, &qc));
+    const size_t cnt = ((size_t)d.num_challenges << (d.degree_bits + d.quotient_degree_bits));
+    CU(cudaMemcpyAsync(out_chunks, qc.p, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    return QPZK_OK;
+  });
 }
 
 int qpzk_fri_begin(qpzk_circuit* q, const qpzk_batch* wires_batch, const qpzk_batch* zs_batch,
                    const qpzk_batch* quotient_batch, const uint64_t* zeta, const uint64_t* alpha, qpzk_fri** out) {
-  if (!q || !wires_batch || !zs_batch || !quotient_batch || !zeta || !alpha || !out)
-    return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  qpzk_ctx* c = q->ctx;
-  const CircuitDesc& d = q->desc;
-  qpzk_batch* oracles[4] = {q->cs_batch, const_cast<qpzk_batch*>(wires_batch), const_cast<qpzk_batch*>(zs_batch),
-                            const_cast<qpzk_batch*>(quotient_batch)};
-  const u32 want[4] = {d.num_constants + d.num_routed, d.num_wires, d.num_challenges * (1 + d.num_partial_products),
-                       d.num_challenges * d.qdf};
-  for (int o = 0; o < 4; o++)
-    if (oracles[o]->ctx != c || oracles[o]->degree_bits != d.degree_bits || oracles[o]->rate_bits != d.rate_bits ||
-        oracles[o]->ncols != want[o] || oracles[o]->cap_height != q->common.cap_height)
-      return fail(QPZK_ERR_BAD_ARG, "oracle shape does not match the circuit");
-  CU(cudaSetDevice(c->device));
-  return fri_begin(q, oracles, zeta, alpha, out);
+  return guarded([&]() -> int {
+    if (!q || !wires_batch || !zs_batch || !quotient_batch || !zeta || !alpha || !out)
+      return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    const qpzk_batch* oracles[4] = {q->cs_batch, wires_batch, zs_batch, quotient_batch};
+    const u32 want[4] = {d.num_constants + d.num_routed, d.num_wires, d.num_challenges * (1 + d.num_partial_products),
+                         d.num_challenges * d.qdf};
+    for (int o = 0; o < 4; o++)
+      if (oracles[o]->ctx != c || oracles[o]->degree_bits != d.degree_bits || oracles[o]->rate_bits != d.rate_bits ||
+          oracles[o]->ncols != want[o] || oracles[o]->cap_height != q->common.cap_height || oracles[o]->sharded())
+        return fail(QPZK_ERR_BAD_ARG, "oracle shape does not match the circuit");
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<qpzk_fri> F(new qpzk_fri());
+    F->c = c;
+    QP(dev_alloc(c, 8 * 8, &F->chal));
+    const u64 wn = glh::root_of_unity(d.degree_bits);
+    Words16 w;
+    memset(&w, 0, sizeof w);
+    w.w[0] = zeta[0]; w.w[1] = zeta[1];
+    w.w[2] = glh::mul(zeta[0] % GL_P, wn); w.w[3] = glh::mul(zeta[1] % GL_P, wn);
+    w.w[4] = alpha[0]; w.w[5] = alpha[1];
+    k_set_words<<<1, 32, 0, c->stream>>>(F->chal, w, 6);
+    c->launches++;
+    QP(fri_begin(q, oracles, F->chal, F->chal + 2, F->chal + 4, F.get()));
+    *out = F.release();
+    return QPZK_OK;
+  });
 }
 uint32_t qpzk_fri_num_rounds(const qpzk_fri* f) { return f ? (uint32_t)f->q->common.arities.size() : 0; }
 int qpzk_fri_commit_round(qpzk_fri* f, uint64_t* cap_out) {
-  if (!f || !cap_out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(f->c->device));
-  return fri_commit_round(f, cap_out);
+  return guarded([&]() -> int {
+    if (!f || !cap_out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = f->c;
+    CU(cudaSetDevice(c->device));
+    const u64* cap_dev = nullptr;
+    QP(fri_commit_round(f, &cap_dev));
+    CU(cudaMemcpyAsync(cap_out, cap_dev, (size_t)32 << f->q->common.cap_height, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    return QPZK_OK;
+  });
 }
 int qpzk_fri_fold(qpzk_fri* f, const uint64_t* beta) {
-  if (!f || !beta) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(f->c->device));
-  return fri_fold(f, beta[0], beta[1]);
+  return guarded([&]() -> int {
+    if (!f || !beta) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = f->c;
+    CU(cudaSetDevice(c->device));
+    Words16 w;
+    memset(&w, 0, sizeof w);
+    w.w[0] = beta[0]; w.w[1] = beta[1];
+    k_set_words<<<1, 32, 0, c->stream>>>(f->chal + 6, w, 2);
+    c->launches++;
+    return fri_fold(f, f->chal + 6);
+  });
 }
 int qpzk_fri_final_poly(qpzk_fri* f, uint64_t* out, size_t cap_words, size_t* len_words) {
-  if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(f->c->device));
-  std::vector<u64> v;
-  QP(fri_final_poly(f, &v));
-  *len_words = v.size();
-  if (out) {
-    if (v.size() > cap_words) return fail(QPZK_ERR_BAD_ARG, "buffer too small");
-    memcpy(out, v.data(), v.size() * 8);
-  }
-  return QPZK_OK;
+  return guarded([&]() -> int {
+    if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    qpzk_ctx* c = f->c;
+    CU(cudaSetDevice(c->device));
+    if (f->round != f->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
+    const u64 m = f->cur_n;
+    *len_words = 2 * m;
+    if (!out) return QPZK_OK;
+    if (2 * m > cap_words) return fail(QPZK_ERR_BAD_ARG, "buffer too small");
+    std::vector<u64> soa(2 * m);
+    CU(cudaMemcpyAsync(soa.data(), f->coeffs_cur, 2 * m * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    for (u64 i = 0; i < m; i++) {
+      out[2 * i] = soa[i];
+      out[2 * i + 1] = soa[m + i];
+    }
+    return QPZK_OK;
+  });
 }
 int qpzk_fri_query(qpzk_fri* f, uint64_t x_index, uint64_t* out, size_t cap_words, size_t* len_words) {
-  if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  const CircuitDesc& d = f->q->desc;
-  if (x_index >> (d.degree_bits + d.rate_bits)) return fail(QPZK_ERR_BAD_ARG, "x_index out of range");
-  if (f->round != f->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
-  CU(cudaSetDevice(f->c->device));
-  std::vector<std::vector<u64>> init_open, step_open;
-  QP(fri_queries(f, &x_index, 1, &init_open, &step_open));
-  size_t total = 0;
-  for (auto& v : init_open) total += v.size();
-  for (auto& v : step_open) total += v.size();
-  *len_words = total;
-  if (out) {
+  return guarded([&]() -> int {
+    if (!f || !len_words) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    const CircuitDesc& d = f->q->desc;
+    const ArenaLayout& L = f->q->lay;
+    qpzk_ctx* c = f->c;
+    if (x_index >> (d.degree_bits + d.rate_bits)) return fail(QPZK_ERR_BAD_ARG, "x_index out of range");
+    if (f->round != f->q->common.arities.size()) return fail(QPZK_ERR_BAD_ARG, "FRI rounds not finished");
+    CU(cudaSetDevice(c->device));
+    size_t total = 0, off[4 + QPZK_MAX_FRI_ROUNDS];
+    for (int o = 0; o < 4; o++) { off[o] = total; total += f->oracles[o]->width() + 4ull * L.L0; }
+    for (size_t s = 0; s < f->trees.size(); s++) { off[4 + s] = total; total += L.step_width[s] + 4ull * L.step_L[s]; }
+    *len_words = total;
+    if (!out) return QPZK_OK;
     if (total > cap_words) return fail(QPZK_ERR_BAD_ARG, "buffer too small");
-    size_t off = 0;
-    for (auto& v : init_open) { memcpy(out + off, v.data(), v.size() * 8); off += v.size(); }
-    for (auto& v : step_open) { memcpy(out + off, v.data(), v.size() * 8); off += v.size(); }
-  }
-  return QPZK_OK;
+    DevBuf buf(c), xi(c);
+    QP(buf.alloc(total * 8));
+    QP(xi.alloc(8));
+    Words16 w;
+    memset(&w, 0, sizeof w);
+    w.w[0] = x_index;
+    k_set_words<<<1, 32, 0, c->stream>>>(xi.p, w, 1);
+    c->launches++;
+    u64* init_out[4];
+    u64* step_out[QPZK_MAX_FRI_ROUNDS];
+    for (int o = 0; o < 4; o++) init_out[o] = buf.p + off[o];
+    for (size_t s = 0; s < f->trees.size(); s++) step_out[s] = buf.p + off[4 + s];
+    QP(fri_queries(f, xi.p, 1, init_out, step_out));
+    CU(cudaMemcpyAsync(out, buf.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(ctx_wait(c));
+    return QPZK_OK;
+  });
 }
 void qpzk_fri_free(qpzk_fri* f) { delete f; }
 
-int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, const uint64_t* public_inputs, uint32_t num_public_inputs,
-               const uint64_t* salts_wires, const uint64_t* salts_zs, const uint64_t* salts_quotient, uint32_t flags,
-               uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
-  if (!q || !wires || (!public_inputs && num_public_inputs) || !proof_len)
-    return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  CU(cudaSetDevice(q->ctx->device));
-  std::vector<uint8_t> bytes;
-  int rc = prove_impl(q, wires, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, flags, &bytes);
-  if (rc != QPZK_OK) {
-    ctx_wait(q->ctx);
-    return rc;
-  }
-  *proof_len = bytes.size();
-  if (proof_out) {
-    if (bytes.size() > proof_cap) return fail(QPZK_ERR_BAD_ARG, "proof buffer too small");
-    memcpy(proof_out, bytes.data(), bytes.size());
+static int check_prove_args(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+                            uint32_t npi, const uint64_t* sw, const uint64_t* sz, const uint64_t* sq, size_t salt_words) {
+  if (!q || !wires || (!public_inputs && npi)) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  const CommonHost& cm = q->common;
+  if (npi != cm.num_public_inputs) return fail(QPZK_ERR_BAD_ARG, "public input count mismatch");
+  if (wires_words != ((size_t)cm.num_wires << cm.degree_bits))
+    return fail(QPZK_ERR_BAD_ARG, "wires must hold num_wires * 2^degree_bits words");
+  if (cm.hiding) {
+    if (!(sw && sz && sq)) return fail(QPZK_ERR_BAD_ARG, "hiding circuit needs salts");
+    if (salt_words != ((size_t)QPZK_SALT_SIZE << (cm.degree_bits + cm.rate_bits)))
+      return fail(QPZK_ERR_BAD_ARG, "each salt array must hold 4 * 2^(degree_bits + rate_bits) words");
   }
   return QPZK_OK;
+}
+
+int qpzk_prove_begin(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+                     uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+                     const uint64_t* salts_quotient, size_t salt_words, uint32_t flags) {
+  return guarded([&]() -> int {
+    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words));
+    CU(cudaSetDevice(q->ctx->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (q->in_flight) return fail(QPZK_ERR_BAD_ARG, "a proof is already in flight on this circuit handle: call qpzk_prove_end first");
+    int rc = prove_enqueue(q, wires, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, flags);
+    if (rc != QPZK_OK) {
+      ctx_wait(q->ctx);  // drain what was enqueued before the handles it used go away
+      return rc;
+    }
+    q->in_flight = true;
+    return QPZK_OK;
+  });
+}
+
+int qpzk_prove_end(qpzk_circuit* q, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  return guarded([&]() -> int {
+    if (!q || !proof_len) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(q->ctx->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (!q->in_flight) return fail(QPZK_ERR_BAD_ARG, "no proof in flight on this circuit handle");
+    q->in_flight = false;
+    std::vector<uint8_t> bytes;
+    QP(prove_finish(q, &bytes));
+    *proof_len = bytes.size();
+    if (proof_out) {
+      if (bytes.size() > proof_cap) return fail(QPZK_ERR_BAD_ARG, "proof buffer too small");
+      memcpy(proof_out, bytes.data(), bytes.size());
+    }
+    return QPZK_OK;
+  });
+}
+
+int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+               uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+               const uint64_t* salts_quotient, size_t salt_words, uint32_t flags, uint8_t* proof_out, size_t proof_cap,
+               size_t* proof_len) {
+  if (!proof_len) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  int rc = qpzk_prove_begin(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient,
+                            salt_words, flags);
+  if (rc != QPZK_OK) return rc;
+  return qpzk_prove_end(q, proof_out, proof_cap, proof_len);
 }
 
 }  // extern "C"

@@ -26,6 +26,7 @@
 #include "ntt.cuh"
 #include "poseidon.cuh"
 #include "poseidon_tables.hpp"
+#include "poseidon_upload.cuh"
 #include "prover.cuh"
 
 using namespace qpzk;
@@ -47,6 +48,26 @@ static int fail(int code, const std::string& msg) {
     int r_ = (x);         \
     if (r_ != QPZK_OK) return r_; \
   } while (0)
+// Nothing may unwind across the C ABI (include/qpzk.h): every extern "C" body that can allocate runs inside
+// this guard and turns an exception into a status code.
+template <class F>
+static int guarded(F&& f) noexcept {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    return fail(QPZK_ERR_OOM, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(QPZK_ERR_CUDA, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return fail(QPZK_ERR_CUDA, "internal error");
+  }
+}
+
+static inline u64 glh_bitrev(u64 x, u32 bits) {
+  u64 r = 0;
+  for (u32 i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
 
 struct TabKey {
   int k;
@@ -69,22 +90,45 @@ struct qpzk_ctx {
   std::map<std::pair<u64, int>, std::pair<u64*, u64*>> pow_tabs;  // (base, k) -> two-level base^e table
   std::map<std::tuple<int, int, bool>, u64*> tw_mats;    // (k, a, inverse) -> twiddle matrix [2^a][2^(k-a)]
   u64* scratch_path = nullptr;                           // small device scratch for openings
+  u32* climb_counters = nullptr;                         // k_tree_climb arrival counters (all zero between launches)
+  u64 coop_max = 4096;                                   // most permutations per step for the 16-lane kernels
+  cudaMemPool_t pool = nullptr;                          // the library's own stream-ordered pool on this device
 };
 
+static void dev_free(qpzk_ctx* c, void* p);
+
 struct qpzk_batch {
-  qpzk_ctx* ctx;
-  uint32_t ncols, salt_cols, degree_bits, rate_bits, cap_height;
+  qpzk_ctx* ctx = nullptr;
+  uint32_t ncols = 0, salt_cols = 0, degree_bits = 0, rate_bits = 0, cap_height = 0;
   u64* coeffs = nullptr;   // [ncols][n]
-  u64* lde = nullptr;      // [ncols+salt_cols][N], bit-reversed row order
-  u64* levels = nullptr;   // digest levels, 2N*4 u64
+  // LDE values, column-major in bit-reversed row order: element (column c, leaf L) at lde[c * lde_stride + L].
+  // A whole batch holds [ncols+salt_cols][N]. A multi-GPU shard allocates only its own leaves [leaf0, leaf1):
+  // lde_stride = leaf1 - leaf0 and `lde` is the allocation shifted back by leaf0, so kernels keep addressing
+  // by absolute leaf index and there is no foreign row to serve by mistake.
+  u64* lde_alloc = nullptr;
+  u64* lde = nullptr;
+  u64 lde_stride = 0;
+  u64* levels = nullptr;   // digest levels, 2N*4 u64 (a shard's foreign digests and cap entries are zero)
+  u64 leaf0 = 0, leaf1 = 0;  // the leaves this batch holds: everything, or one rank's shard of whole cap subtrees
   uint32_t log_N() const { return degree_bits + rate_bits; }
   uint32_t width() const { return ncols + salt_cols; }
+  bool sharded() const { return leaf0 != 0 || leaf1 != ((u64)1 << log_N()); }
+  bool owns(u64 leaf) const { return leaf >= leaf0 && leaf < leaf1; }
+  ~qpzk_batch() {
+    if (!ctx) return;
+    dev_free(ctx, coeffs);
+    dev_free(ctx, lde_alloc);
+    dev_free(ctx, levels);
+  }
 };
 
 struct qpzk_tree {
-  qpzk_ctx* ctx;
-  uint32_t log_n, cap_height, leaf_len;
+  qpzk_ctx* ctx = nullptr;
+  uint32_t log_n = 0, cap_height = 0, leaf_len = 0;
   u64* levels = nullptr;
+  ~qpzk_tree() {
+    if (ctx) dev_free(ctx, levels);
+  }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -103,13 +147,22 @@ static cudaError_t ctx_wait(qpzk_ctx* c) {
 
 static int dev_alloc(qpzk_ctx* c, size_t bytes, u64** out) {
   void* p = nullptr;
-  CU(cudaMallocAsync(&p, bytes ? bytes : 8, c->stream));
+  CU(cudaMallocFromPoolAsync(&p, bytes ? bytes : 8, c->pool, c->stream));
   *out = (u64*)p;
   return QPZK_OK;
 }
 static void dev_free(qpzk_ctx* c, void* p) {
   if (p) cudaFreeAsync(p, c->stream);
 }
+struct DevBuf {  // scoped stream-ordered allocation
+  qpzk_ctx* c;
+  u64* p = nullptr;
+  explicit DevBuf(qpzk_ctx* c_) : c(c_) {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { dev_free(c, p); }
+  int alloc(size_t bytes) { return dev_alloc(c, bytes, &p); }
+};
 
 static int get_root_tab(qpzk_ctx* c, int k, bool inverse, RootTab* out) {
   TabKey key{k, inverse};
@@ -292,37 +345,53 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
 }
 
 // Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
-// Below this many independent permutations a launch cannot fill the machine with one thread per
-// permutation and the 16-lane low-latency kernels win. They spend ~3.8x the lane-instructions per
-// permutation, so the threshold trades single-proof latency against throughput with several proofs in
-// flight. Measured (2^14 ZK proof, 6 streams): 0 -> 171 proofs/s / 9.8 ms latency; 1024 -> 175 / 8.9;
-// 4096 -> 175 / 8.8; 8192 -> 171 / 8.8. QPZK_COOP_MAX overrides.
-static u64 kCoopMaxPerms = 4096;
+// Above `coop_max` independent permutations a step runs one thread per permutation (throughput); at or below
+// it the rest of the tree - leaves included, if there are that few - is ONE k_tree_climb launch on the 16-lane
+// path. The 16-lane kernels spend ~3.8x the lane-instructions per permutation, so the threshold trades
+// single-proof latency against throughput with several proofs in flight. Measured with per-level launches
+// (2^14 ZK proof, 6 streams): 0 -> 171 proofs/s / 9.8 ms latency; 1024 -> 175 / 8.9; 4096 -> 175 / 8.8;
+// 8192 -> 171 / 8.8. QPZK_COOP_MAX (read once per process) overrides.
 // [leaf0, leaf0 + nleaves) restricts the work to a range of whole cap subtrees (multi-GPU shard); the
 // default is the whole tree.
+static u64 coop_max_from_env() {
+  static const u64 v = [] {
+    const char* e = getenv("QPZK_COOP_MAX");
+    u64 x = e ? strtoull(e, nullptr, 10) : 4096;
+    return x > QPZK_CLIMB_MAX_START ? (u64)QPZK_CLIMB_MAX_START : x;
+  }();
+  return v;
+}
 static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u32 log_n, u32 cap_height,
                       u64* levels, cudaEvent_t after_leaves, u64 leaf0 = 0, u64 nleaves = 0) {
-  u64 N = (u64)1 << log_n;
+  const u64 N = (u64)1 << log_n;
   if (nleaves == 0) nleaves = N - leaf0;
-  if (nleaves <= kCoopMaxPerms)
-    k_leaf_hash_coop<<<(unsigned)((nleaves + QPZK_COOP_GROUPS - 1) / QPZK_COOP_GROUPS), QPZK_COOP_THREADS, 0, c->stream>>>(
-        src + leaf0 * rs, rs, cs, width, nleaves, levels + leaf0 * 4);
-  else
-    k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
-                                                                         levels + leaf0 * 4);
+  const u32 top = log_n - cap_height;
+  auto groups = [](u64 count) { return (unsigned)((count + QPZK_COOP_GROUPS - 1) / QPZK_COOP_GROUPS); };
+  if (nleaves <= c->coop_max) {
+    k_tree_climb<true><<<groups(nleaves), QPZK_COOP_THREADS, 0, c->stream>>>(src, rs, cs, width, levels, log_n, cap_height, 0,
+                                                                            leaf0, nleaves, c->climb_counters);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
+    return QPZK_OK;
+  }
+  k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
+                                                                       levels + leaf0 * 4);
   c->launches++;
   CU(cudaGetLastError());
   if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
-  u64 twoN = 2 * N;
-  for (u32 l = 0; l < log_n - cap_height; l++) {
-    u64 nout = nleaves >> (l + 1), first = leaf0 >> (l + 1);
+  const u64 twoN = 2 * N;
+  for (u32 l = 0; l < top; l++) {
+    const u64 nout = nleaves >> (l + 1), first = leaf0 >> (l + 1);
+    if (nout <= c->coop_max) {  // the rest of the way in one launch
+      k_tree_climb<false><<<groups(nout), QPZK_COOP_THREADS, 0, c->stream>>>(nullptr, 0, 0, 0, levels, log_n, cap_height, l, first,
+                                                                           nout, c->climb_counters);
+      c->launches++;
+      break;
+    }
     const u64* in = levels + (twoN - (twoN >> l) + 2 * first) * 4;
     u64* out = levels + (twoN - (twoN >> (l + 1)) + first) * 4;
-    if (nout <= kCoopMaxPerms)
-      k_merkle_level_coop<<<(unsigned)((nout + QPZK_COOP_GROUPS - 1) / QPZK_COOP_GROUPS), QPZK_COOP_THREADS, 0, c->stream>>>(
-          in, out, nout);
-    else
-      k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
+    k_merkle_level<<<(unsigned)((nout + 127) / 128), 128, 0, c->stream>>>(in, out, nout);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -379,90 +448,61 @@ extern "C" {
 
 const char* qpzk_last_error(void) { return g_err.c_str(); }
 
-int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
-  if (!out) return fail(QPZK_ERR_BAD_ARG, "out is NULL");
-  int ndev = 0;
-  CU(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return fail(QPZK_ERR_BAD_ARG, "no such CUDA device (there is no CPU fallback)");
-  CU(cudaSetDevice(device));
-  if (const char* e = getenv("QPZK_COOP_MAX")) kCoopMaxPerms = strtoull(e, nullptr, 10);  // tuning knob
-  qpzk_ctx* c = new qpzk_ctx();
-  c->device = device;
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  c->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  c->blocking_sync = (flags & QPZK_CTX_BLOCKING_SYNC) != 0;
-  c->yield_sync = !c->blocking_sync && (flags & QPZK_CTX_YIELD_SYNC) != 0;
-  CU(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
-  for (auto& e : c->ev) CU(cudaEventCreate(&e));
-  // keep freed blocks in the pool: commits allocate and release hundreds of MB per call
-  cudaMemPool_t pool;
-  CU(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thresh = ~0ull;
-  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-  // Poseidon tables -> __constant__, once per device (kernels of other contexts may be reading them)
+// The library allocates from its own stream-ordered pool (one per device, shared by the contexts on it,
+// never trimmed: a commit allocates and releases hundreds of MB per call) instead of reconfiguring the
+// device's default pool under the host application.
+static int device_pool(int device, cudaMemPool_t* out) {
   static std::mutex mu;
-  static bool device_ready[64] = {false};
-  {
-    std::lock_guard<std::mutex> lk(mu);
-    static PoseidonTablesHost* T = nullptr;
-    if (!T) {
-      T = new PoseidonTablesHost();
-      build_poseidon_tables(T, PV_DENSE_PARTIAL);
-    }
-    if (device < 64 && !device_ready[device]) {
-      CU(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
-      CU(cudaMemcpyToSymbol(g_rc, T->rc, sizeof T->rc));
-      CU(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
-      CU(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
-      CU(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
-      CU(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
-      CU(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
-      CU(cudaMemcpyToSymbol(c_h_rc, T->h_rc, sizeof T->h_rc));
-      CU(cudaMemcpyToSymbol(c_h_init, T->h_init, sizeof T->h_init));
-      CU(cudaMemcpyToSymbol(c_h_w_hat, T->h_w_hat, sizeof T->h_w_hat));
-      CU(cudaMemcpyToSymbol(c_h_v, T->h_v, sizeof T->h_v));
-      u32 circ[12];
-      for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
-      u32 diag0 = (u32)kMdsDiag0;
-      CU(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
-      CU(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
-#if PV_MDS_F64
-      double circ_d[12];
-      for (int i = 0; i < 12; i++) circ_d[i] = (double)kMdsCirc[i];
-      CU(cudaMemcpyToSymbol(c_mds_circ_d, circ_d, sizeof circ_d));
-      static double next_rc[QPZK_MDS_LAYERS_MAX][2][12];
-      poseidon_next_rc_f64(*T, next_rc, PV_MDS_SPLIT != 0);
-      static double half_d[12];
-      poseidon_mds_half_f64(half_d);
-      CU(cudaMemcpyToSymbol(c_mds_half_d, half_d, sizeof half_d));
-      CU(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
-#endif
-      // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
-      const int kMaxSmem = 72 * 1024;
-      CU(cudaFuncSetAttribute(k_ntt_small<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
-      CU(cudaFuncSetAttribute(k_ntt_small<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
-      CU(cudaFuncSetAttribute(k_ntt_small<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
-      CU(cudaFuncSetAttribute(k_ntt_small<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
-      CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-      CU(cudaDeviceSynchronize());
-      device_ready[device] = true;
-    }
+  static cudaMemPool_t pools[64] = {nullptr};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device >= 64) return fail(QPZK_ERR_UNSUPPORTED, "device index above 63");
+  if (!pools[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CU(cudaMemPoolCreate(&pools[device], &props));
+    uint64_t thresh = ~0ull;
+    CU(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &thresh));
   }
-  QP(dev_alloc(c, 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
-  CU(ctx_wait(c));
-  *out = c;
+  *out = pools[device];
   return QPZK_OK;
 }
 
-void qpzk_ctx_destroy(qpzk_ctx* c) {
+// Poseidon tables -> __constant__ and kernel attributes, once per device (kernels of other contexts may be
+// reading them).
+static int device_init_once(int device) {
+  static std::mutex mu;
+  static bool device_ready[64] = {false};
+  std::lock_guard<std::mutex> lk(mu);
+  static PoseidonTablesHost* T = nullptr;
+  if (!T) {
+    T = new PoseidonTablesHost();
+    build_poseidon_tables(T, PV_DENSE_PARTIAL);
+  }
+  if (device_ready[device]) return QPZK_OK;
+  CU(poseidon_upload_tables(*T));
+  // transforms of 2^12 points stage 48 KB + twiddles in shared memory: opt in above the 48 KB default
+  const int kMaxSmem = 72 * 1024;
+  CU(cudaFuncSetAttribute(k_ntt_small<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_small<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_small<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_small<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CU(cudaFuncSetAttribute(k_ntt_pass_b_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  CU(cudaDeviceSynchronize());
+  device_ready[device] = true;
+  return QPZK_OK;
+}
+
+static void ctx_release(qpzk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  ctx_wait(c);
+  if (c->stream) ctx_wait(c);
   for (auto& kv : c->root_tabs) {
     dev_free(c, kv.second.first);
     dev_free(c, kv.second.second);
@@ -474,12 +514,49 @@ void qpzk_ctx_destroy(qpzk_ctx* c) {
     dev_free(c, kv.second.second);
   }
   dev_free(c, c->scratch_path);
-  ctx_wait(c);
-  for (auto& e : c->ev) cudaEventDestroy(e);
-  cudaEventDestroy(c->sync_ev);
-  cudaStreamDestroy(c->stream);
+  dev_free(c, c->climb_counters);
+  if (c->stream) ctx_wait(c);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->sync_ev) cudaEventDestroy(c->sync_ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
+
+int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
+  return guarded([&]() -> int {
+    if (!out) return fail(QPZK_ERR_BAD_ARG, "out is NULL");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev || device >= 64)
+      return fail(QPZK_ERR_BAD_ARG, "no such CUDA device (there is no CPU fallback)");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<qpzk_ctx, void (*)(qpzk_ctx*)> c(new qpzk_ctx(), ctx_release);
+    c->device = device;
+    for (auto& e : c->ev) e = nullptr;
+    c->coop_max = coop_max_from_env();
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    QP(device_pool(device, &c->pool));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->blocking_sync = (flags & QPZK_CTX_BLOCKING_SYNC) != 0;
+    c->yield_sync = !c->blocking_sync && (flags & QPZK_CTX_YIELD_SYNC) != 0;
+    CU(cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    for (auto& e : c->ev) CU(cudaEventCreate(&e));
+    QP(device_init_once(device));
+    QP(dev_alloc(c.get(), 64 * 4 * 8 + 4096 * 8, &c->scratch_path));
+    u64* cnt = nullptr;
+    QP(dev_alloc(c.get(), 2 * QPZK_CLIMB_MAX_START * sizeof(u32), &cnt));
+    c->climb_counters = reinterpret_cast<u32*>(cnt);
+    CU(cudaMemsetAsync(c->climb_counters, 0, 2 * QPZK_CLIMB_MAX_START * sizeof(u32), c->stream));
+    CU(ctx_wait(c.get()));
+    *out = c.release();
+    return QPZK_OK;
+  });
+}
+
+void qpzk_ctx_destroy(qpzk_ctx* c) { ctx_release(c); }
 
 int qpzk_ctx_sync(qpzk_ctx* c) {
   if (!c) return fail(QPZK_ERR_BAD_ARG, "ctx is NULL");
@@ -495,16 +572,16 @@ int qpzk_ctx_stage_ms(qpzk_ctx* c, float* out_ms) {
 }
 
 void* qpzk_poseidon_tables_host(void) {  // test hook: the generated tables (PoseidonTablesHost*)
-  static PoseidonTablesHost T;
-  static bool done = false;
-  if (!done) {
-    build_poseidon_tables(&T);
-    done = true;
-  }
-  return &T;
+  static PoseidonTablesHost* T = [] {
+    PoseidonTablesHost* t = new (std::nothrow) PoseidonTablesHost();
+    if (t) build_poseidon_tables(t);
+    return t;
+  }();
+  return T;
 }
 
 int qpzk_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   CU(cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault));
   return QPZK_OK;
 }
@@ -523,11 +600,15 @@ void qpzk_dev_free(qpzk_ctx* c, void* p) {
   if (c) dev_free(c, p);
 }
 int qpzk_memcpy_h2d(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || !dst || !src) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
 int qpzk_memcpy_d2h(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || !dst || !src) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
@@ -538,14 +619,13 @@ int qpzk_poseidon_permute(qpzk_ctx* c, uint64_t* states, uint64_t n) {
   if (!c || (!states && n)) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   if (!n) return QPZK_OK;
   CU(cudaSetDevice(c->device));
-  u64* d;
-  QP(dev_alloc(c, n * 96, &d));
-  CU(cudaMemcpyAsync(d, states, n * 96, cudaMemcpyHostToDevice, c->stream));
-  k_permute<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d, n);
+  DevBuf d(c);
+  QP(d.alloc(n * 96));
+  CU(cudaMemcpyAsync(d.p, states, n * 96, cudaMemcpyHostToDevice, c->stream));
+  k_permute<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d.p, n);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(states, d, n * 96, cudaMemcpyDeviceToHost, c->stream));
-  dev_free(c, d);
+  CU(cudaMemcpyAsync(states, d.p, n * 96, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
@@ -555,16 +635,14 @@ int qpzk_hash_no_pad(qpzk_ctx* c, const uint64_t* inputs, uint64_t n, uint32_t l
   if (!n) return QPZK_OK;
   if (len == 0) return fail(QPZK_ERR_BAD_ARG, "len must be > 0");
   CU(cudaSetDevice(c->device));
-  u64 *din, *dout;
-  QP(dev_alloc(c, n * len * 8, &din));
-  QP(dev_alloc(c, n * 32, &dout));
-  CU(cudaMemcpyAsync(din, inputs, n * len * 8, cudaMemcpyHostToDevice, c->stream));
-  k_hash_no_pad<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din, n, len, dout);
+  DevBuf din(c), dout(c);
+  QP(din.alloc(n * len * 8));
+  QP(dout.alloc(n * 32));
+  CU(cudaMemcpyAsync(din.p, inputs, n * len * 8, cudaMemcpyHostToDevice, c->stream));
+  k_hash_no_pad<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din.p, n, len, dout.p);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
-  dev_free(c, din);
-  dev_free(c, dout);
+  CU(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
@@ -573,16 +651,14 @@ int qpzk_two_to_one(qpzk_ctx* c, const uint64_t* pairs, uint64_t n, uint64_t* ou
   if (!c || !pairs || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   if (!n) return QPZK_OK;
   CU(cudaSetDevice(c->device));
-  u64 *din, *dout;
-  QP(dev_alloc(c, n * 64, &din));
-  QP(dev_alloc(c, n * 32, &dout));
-  CU(cudaMemcpyAsync(din, pairs, n * 64, cudaMemcpyHostToDevice, c->stream));
-  k_merkle_level<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din, dout, n);
+  DevBuf din(c), dout(c);
+  QP(din.alloc(n * 64));
+  QP(dout.alloc(n * 32));
+  CU(cudaMemcpyAsync(din.p, pairs, n * 64, cudaMemcpyHostToDevice, c->stream));
+  k_merkle_level<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(din.p, dout.p, n);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, c->stream));
-  dev_free(c, din);
-  dev_free(c, dout);
+  CU(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
@@ -597,31 +673,27 @@ static uint32_t ilog2(uint64_t x) {
 
 int qpzk_merkle_new(qpzk_ctx* c, const uint64_t* leaves, uint64_t nleaves, uint32_t leaf_len,
                     uint32_t cap_height, qpzk_tree** out) {
-  if (!c || !leaves || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-  if (!is_pow2(nleaves)) return fail(QPZK_ERR_BAD_ARG, "nleaves must be a power of two");
-  uint32_t log_n = ilog2(nleaves);
-  if (cap_height > log_n)
-    return fail(QPZK_ERR_BAD_ARG, "cap_height must be at most log2(nleaves)");  // plonky2 asserts the same
-  CU(cudaSetDevice(c->device));
-  qpzk_tree* t = new qpzk_tree();
-  t->ctx = c;
-  t->log_n = log_n;
-  t->cap_height = cap_height;
-  t->leaf_len = leaf_len;
-  u64* dl = nullptr;
-  int rc = dev_alloc(c, nleaves * (leaf_len ? leaf_len : 1) * 8, &dl);
-  if (rc == QPZK_OK) rc = dev_alloc(c, nleaves * 2 * 32, &t->levels);
-  if (rc != QPZK_OK) {
-    dev_free(c, dl);
-    delete t;
-    return rc;
-  }
-  CU(cudaMemcpyAsync(dl, leaves, nleaves * leaf_len * 8, cudaMemcpyHostToDevice, c->stream));
-  QP(build_tree(c, dl, leaf_len, 1, leaf_len, log_n, cap_height, t->levels, nullptr));
-  dev_free(c, dl);
-  CU(ctx_wait(c));
-  *out = t;
-  return QPZK_OK;
+  return guarded([&]() -> int {
+    if (!c || !leaves || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    if (!is_pow2(nleaves) || nleaves > ((uint64_t)1 << 30)) return fail(QPZK_ERR_BAD_ARG, "nleaves must be a power of two, at most 2^30");
+    uint32_t log_n = ilog2(nleaves);
+    if (cap_height > log_n)
+      return fail(QPZK_ERR_BAD_ARG, "cap_height must be at most log2(nleaves)");  // plonky2 asserts the same
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<qpzk_tree> t(new qpzk_tree());
+    t->ctx = c;
+    t->log_n = log_n;
+    t->cap_height = cap_height;
+    t->leaf_len = leaf_len;
+    DevBuf dl(c);
+    QP(dl.alloc(nleaves * (leaf_len ? leaf_len : 1) * 8));
+    QP(dev_alloc(c, nleaves * 2 * 32, &t->levels));
+    CU(cudaMemcpyAsync(dl.p, leaves, nleaves * leaf_len * 8, cudaMemcpyHostToDevice, c->stream));
+    QP(build_tree(c, dl.p, leaf_len, 1, leaf_len, log_n, cap_height, t->levels, nullptr));
+    CU(ctx_wait(c));
+    *out = t.release();
+    return QPZK_OK;
+  });
 }
 
 int qpzk_tree_cap(const qpzk_tree* t, uint64_t* out) {
@@ -656,13 +728,12 @@ int qpzk_tree_prove(const qpzk_tree* t, uint64_t leaf_index, uint64_t* siblings)
 static int export_digests(qpzk_ctx* c, const u64* levels, u32 log_n, u32 cap_height, uint64_t* out) {
   u64 total = ((u64)2 << log_n) - ((u64)2 << cap_height);
   if (!total) return QPZK_OK;
-  u64* d;
-  QP(dev_alloc(c, total * 32, &d));
-  k_export_digests<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(levels, log_n, cap_height, d);
+  DevBuf d(c);
+  QP(d.alloc(total * 32));
+  k_export_digests<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(levels, log_n, cap_height, d.p);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, d, total * 32, cudaMemcpyDeviceToHost, c->stream));
-  dev_free(c, d);
+  CU(cudaMemcpyAsync(out, d.p, total * 32, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
@@ -676,18 +747,22 @@ int qpzk_tree_digests(const qpzk_tree* t, uint64_t* out) {
 void qpzk_tree_free(qpzk_tree* t) {
   if (!t) return;
   cudaSetDevice(t->ctx->device);
-  dev_free(t->ctx, t->levels);
   delete t;
 }
 
+}  // extern "C"
+
 // ---- PolynomialBatch ----
+// sync = false: everything is enqueued on the context's stream and the call returns without waiting (the
+// prover pipeline); per-stage times are then not collected.
 static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is_coeffs, uint32_t ncols,
                        uint32_t k, uint32_t r, uint32_t cap_height, const uint64_t* salts, bool salts_host,
-                       uint32_t salt_cols, qpzk_batch** out, uint32_t sub_begin = 0, uint32_t sub_end = 0) {
+                       uint32_t salt_cols, qpzk_batch** out, uint32_t sub_begin = 0, uint32_t sub_end = 0,
+                       bool sync = true) {
   if (!c || !in || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   if (ncols == 0) return fail(QPZK_ERR_BAD_ARG, "ncols must be > 0");
   if (!salts) salt_cols = 0;
-  if (k + r > 30) return fail(QPZK_ERR_UNSUPPORTED, "LDE domain too large");
+  if (k > 30 || r > 30 || k + r > 30) return fail(QPZK_ERR_UNSUPPORTED, "LDE domain too large");
   if (cap_height > k + r) return fail(QPZK_ERR_BAD_ARG, "cap_height must be at most degree_bits + rate_bits");
   CU(cudaSetDevice(c->device));
   const u64 n = (u64)1 << k, N = n << r;
@@ -700,36 +775,31 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
   if (sharded && ((leaf0 & (n - 1)) || (leaf1 & (n - 1))))
     return fail(QPZK_ERR_UNSUPPORTED, "shard must cover whole cosets: subtree range must be a multiple of 2^(cap_height - rate_bits)");
   const u32 blk0 = (u32)(leaf0 >> k), nblk = (u32)((leaf1 - leaf0) >> k);
-  qpzk_batch* b = new qpzk_batch();
+  std::unique_ptr<qpzk_batch> b(new qpzk_batch());
   b->ctx = c;
   b->ncols = ncols;
   b->salt_cols = salt_cols;
   b->degree_bits = k;
   b->rate_bits = r;
   b->cap_height = cap_height;
-  u64 *staging = nullptr, *salt_staging = nullptr;
-  auto cleanup = [&](int rc) {
-    dev_free(c, staging);
-    dev_free(c, salt_staging);
-    dev_free(c, b->coeffs);
-    dev_free(c, b->lde);
-    dev_free(c, b->levels);
-    delete b;
-    return rc;
-  };
-  int rc;
-  if ((rc = dev_alloc(c, (size_t)ncols * n * 8, &b->coeffs)) != QPZK_OK) return cleanup(rc);
-  if ((rc = dev_alloc(c, (size_t)width * N * 8, &b->lde)) != QPZK_OK) return cleanup(rc);
-  if ((rc = dev_alloc(c, (size_t)N * 2 * 32, &b->levels)) != QPZK_OK) return cleanup(rc);
+  b->leaf0 = leaf0;
+  b->leaf1 = leaf1;
+  DevBuf staging(c), salt_staging(c);
+  QP(dev_alloc(c, (size_t)ncols * n * 8, &b->coeffs));
+  const u64 nown = leaf1 - leaf0;
+  QP(dev_alloc(c, (size_t)width * nown * 8, &b->lde_alloc));
+  b->lde = b->lde_alloc - leaf0;
+  b->lde_stride = nown;
+  QP(dev_alloc(c, (size_t)N * 2 * 32, &b->levels));
 
   cudaEvent_t* ev = c->ev;
-  CU(cudaEventRecord(ev[0], c->stream));
+  if (sync) CU(cudaEventRecord(ev[0], c->stream));
   const u64* src = in;
   if (in_is_host) {
-    u64* dstp = is_coeffs ? b->coeffs : nullptr;
+    u64* dstp = b->coeffs;
     if (!is_coeffs) {
-      if ((rc = dev_alloc(c, (size_t)ncols * n * 8, &staging)) != QPZK_OK) return cleanup(rc);
-      dstp = staging;
+      QP(staging.alloc((size_t)ncols * n * 8));
+      dstp = staging.p;
     }
     CU(cudaMemcpyAsync(dstp, in, (size_t)ncols * n * 8, cudaMemcpyHostToDevice, c->stream));
     src = dstp;
@@ -739,63 +809,74 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
   }
   const u64* salt_src = salts;
   if (salt_cols && salts_host) {
-    if ((rc = dev_alloc(c, (size_t)salt_cols * N * 8, &salt_staging)) != QPZK_OK) return cleanup(rc);
-    CU(cudaMemcpyAsync(salt_staging, salts, (size_t)salt_cols * N * 8, cudaMemcpyHostToDevice, c->stream));
-    salt_src = salt_staging;
+    QP(salt_staging.alloc((size_t)salt_cols * N * 8));
+    CU(cudaMemcpyAsync(salt_staging.p, salts, (size_t)salt_cols * N * 8, cudaMemcpyHostToDevice, c->stream));
+    salt_src = salt_staging.p;
   }
-  CU(cudaEventRecord(ev[1], c->stream));
-  if (!is_coeffs) {
-    if ((rc = launch_ifft(c, src, n, b->coeffs, n, ncols, (int)k)) != QPZK_OK) return cleanup(rc);
-  }
-  CU(cudaEventRecord(ev[2], c->stream));
-  if (sharded) CU(cudaMemsetAsync(b->levels, 0, (size_t)N * 2 * 32, c->stream));  // foreign digests / cap read as zero
-  if ((rc = launch_lde(c, b->coeffs, n, b->lde, N, ncols, (int)k, (int)r, blk0, nblk)) != QPZK_OK) return cleanup(rc);
+  if (sync) CU(cudaEventRecord(ev[1], c->stream));
+  if (!is_coeffs) QP(launch_ifft(c, src, n, b->coeffs, n, ncols, (int)k));
+  if (sync) CU(cudaEventRecord(ev[2], c->stream));
+  // foreign digests and cap entries of a shard read as zero (the caller all-gathers the subtree roots)
+  if (sharded) CU(cudaMemsetAsync(b->levels, 0, (size_t)N * 2 * 32, c->stream));
+  QP(launch_lde(c, b->coeffs, n, b->lde, nown, ncols, (int)k, (int)r, blk0, nblk));
   if (salt_cols) {
-    k_bitrev_rows<<<dim3((unsigned)((N + 255) / 256), salt_cols), 256, 0, c->stream>>>(
-        salt_src, b->lde + (size_t)ncols * N, (int)(k + r), salt_cols);
+    k_bitrev_rows<<<dim3((unsigned)((nown + 255) / 256), salt_cols), 256, 0, c->stream>>>(
+        salt_src, b->lde + (size_t)ncols * nown, nown, leaf0, nown, (int)(k + r), salt_cols);
     c->launches++;
   }
-  CU(cudaEventRecord(ev[3], c->stream));
-  if ((rc = build_tree(c, b->lde, 1, N, width, k + r, cap_height, b->levels, ev[4], leaf0, leaf1 - leaf0)) != QPZK_OK)
-    return cleanup(rc);
-  CU(cudaEventRecord(ev[5], c->stream));
-  dev_free(c, staging);
-  dev_free(c, salt_staging);
-  staging = salt_staging = nullptr;
-  CU(ctx_wait(c));
-  for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
-  c->stage_ms[QPZK_STAGE_D2H] = 0;
-  *out = b;
+  if (sync) CU(cudaEventRecord(ev[3], c->stream));
+  QP(build_tree(c, b->lde, 1, nown, width, k + r, cap_height, b->levels, sync ? ev[4] : nullptr, leaf0, nown));
+  if (sync) {
+    CU(cudaEventRecord(ev[5], c->stream));
+    CU(ctx_wait(c));
+    for (int i = 0; i < 5; i++) cudaEventElapsedTime(&c->stage_ms[i], ev[i], ev[i + 1]);
+    c->stage_ms[QPZK_STAGE_D2H] = 0;
+  }
+  *out = b.release();
   return QPZK_OK;
 }
+
+extern "C" {
 
 int qpzk_batch_from_values(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts, uint32_t salt_cols,
                            qpzk_batch** out) {
-  return commit_impl(c, values, true, false, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out);
+  return guarded([&] { return commit_impl(c, values, true, false, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out); });
 }
 int qpzk_batch_from_coeffs(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts, uint32_t salt_cols,
                            qpzk_batch** out) {
-  return commit_impl(c, coeffs, true, true, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out);
+  return guarded([&] { return commit_impl(c, coeffs, true, true, ncols, degree_bits, rate_bits, cap_height, salts, true, salt_cols, out); });
 }
 int qpzk_batch_from_values_dev(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
                                uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
                                uint32_t salt_cols, qpzk_batch** out) {
-  return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out);
+  return guarded([&] { return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out); });
 }
 int qpzk_batch_from_coeffs_dev(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
                                uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
                                uint32_t salt_cols, qpzk_batch** out) {
-  return commit_impl(c, coeffs, false, true, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out);
+  return guarded([&] { return commit_impl(c, coeffs, false, true, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out); });
 }
 int qpzk_batch_from_values_shard_dev(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
                                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
                                      uint32_t salt_cols, uint32_t subtree_begin, uint32_t subtree_end,
                                      qpzk_batch** out) {
   if (subtree_end == 0) return fail(QPZK_ERR_BAD_ARG, "empty subtree range");
-  return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out,
-                     subtree_begin, subtree_end);
+  return guarded([&] {
+    return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out,
+                       subtree_begin, subtree_end);
+  });
+}
+int qpzk_batch_from_coeffs_shard_dev(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
+                                     uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                                     uint32_t salt_cols, uint32_t subtree_begin, uint32_t subtree_end,
+                                     qpzk_batch** out) {
+  if (subtree_end == 0) return fail(QPZK_ERR_BAD_ARG, "empty subtree range");
+  return guarded([&] {
+    return commit_impl(c, coeffs, false, true, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out,
+                       subtree_begin, subtree_end);
+  });
 }
 int qpzk_batch_set_cap(qpzk_batch* b, const uint64_t* cap) {
   if (!b || !cap) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
@@ -836,31 +917,34 @@ int qpzk_batch_get_lde_rows(const qpzk_batch* b, const uint32_t* idx, uint32_t n
   if (!nidx) return QPZK_OK;
   qpzk_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
-  u64 N = (u64)1 << b->log_N();
-  for (uint32_t i = 0; i < nidx; i++)
-    if ((u64)idx[i] * step >= N) return fail(QPZK_ERR_BAD_ARG, "index*step out of range");
-  u64 *didx, *dout;
-  QP(dev_alloc(c, (size_t)nidx * 4, &didx));
-  QP(dev_alloc(c, (size_t)nidx * b->ncols * 8, &dout));
-  CU(cudaMemcpyAsync(didx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream));
-  k_gather_rows<<<nidx, 128, 0, c->stream>>>(b->lde, (int)b->log_N(), (const u32*)didx, nidx, step, b->ncols, dout);
+  const u32 lb = b->log_N();
+  const u64 N = (u64)1 << lb;
+  for (uint32_t i = 0; i < nidx; i++) {
+    const u64 nat = (u64)idx[i] * step;
+    if (nat >= N) return fail(QPZK_ERR_BAD_ARG, "index*step out of range");
+    if (lb && !b->owns(glh_bitrev(nat, lb))) return fail(QPZK_ERR_BAD_ARG, "row belongs to another rank's shard");
+  }
+  DevBuf didx(c), dout(c);
+  QP(didx.alloc((size_t)nidx * 4));
+  QP(dout.alloc((size_t)nidx * b->ncols * 8));
+  CU(cudaMemcpyAsync(didx.p, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream));
+  k_gather_rows<<<nidx, 128, 0, c->stream>>>(b->lde, b->lde_stride, (int)lb, (const u32*)didx.p, nidx, step, b->ncols, dout.p);
   c->launches++;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, dout, (size_t)nidx * b->ncols * 8, cudaMemcpyDeviceToHost, c->stream));
-  dev_free(c, didx);
-  dev_free(c, dout);
+  CU(cudaMemcpyAsync(out, dout.p, (size_t)nidx * b->ncols * 8, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
 int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out, uint64_t* siblings_out) {
   if (!b) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   if (leaf_index >> b->log_N()) return fail(QPZK_ERR_BAD_ARG, "leaf_index out of range");
+  if (!b->owns(leaf_index)) return fail(QPZK_ERR_BAD_ARG, "leaf belongs to another rank's shard");
   qpzk_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
   if (leaf_out) {
     if (b->width() > 4096) return fail(QPZK_ERR_UNSUPPORTED, "row too wide");
     u64* row = c->scratch_path + 64 * 4;
-    k_gather_leaf<<<1, 128, 0, c->stream>>>(b->lde, (u64)1 << b->log_N(), leaf_index, b->width(), row);
+    k_gather_leaf<<<1, 128, 0, c->stream>>>(b->lde, b->lde_stride, leaf_index, b->width(), row);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaf_out, row, (size_t)b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -871,18 +955,18 @@ int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out
 }
 int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests) {
   if (!b) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (b->sharded()) return fail(QPZK_ERR_UNSUPPORTED, "a shard holds only its own leaves: export the unsharded batch");
   qpzk_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
   u64 N = (u64)1 << b->log_N();
   if (leaves) {
-    u64* rows;
-    QP(dev_alloc(c, (size_t)N * b->width() * 8, &rows));
+    DevBuf rows(c);
+    QP(rows.alloc((size_t)N * b->width() * 8));
     dim3 grid((unsigned)((N + 31) / 32), (b->width() + 31) / 32);
-    k_transpose_to_rows<<<grid, dim3(32, 8), 0, c->stream>>>(b->lde, rows, N, b->width());
+    k_transpose_to_rows<<<grid, dim3(32, 8), 0, c->stream>>>(b->lde, rows.p, N, b->width());
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(leaves, rows, (size_t)N * b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
-    dev_free(c, rows);
+    CU(cudaMemcpyAsync(leaves, rows.p, (size_t)N * b->width() * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(ctx_wait(c));
   }
   if (digests) return export_digests(c, b->levels, b->log_N(), b->cap_height, digests);
@@ -894,26 +978,23 @@ uint32_t qpzk_batch_degree_bits(const qpzk_batch* b) { return b ? b->degree_bits
 void qpzk_batch_free(qpzk_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
-  dev_free(b->ctx, b->coeffs);
-  dev_free(b->ctx, b->lde);
-  dev_free(b->ctx, b->levels);
   delete b;
 }
 
 int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
   if (!c || !out_ops_per_s) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   CU(cudaSetDevice(c->device));
-  u64* d;
-  QP(dev_alloc(c, 64, &d));
+  DevBuf d(c);
+  QP(d.alloc(64));
   const int iters = 1024, threads = 256;
   const int blocks = c->sm_count * 8;
   float best = 1e30f;
   for (int rep = 0; rep < 5; rep++) {
     CU(cudaEventRecord(c->ev[0], c->stream));
     if (kind == 0)
-      k_imad_peak<0><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep, 17u, 15u, 41u, 16u);
+      k_imad_peak<0><<<blocks, threads, 0, c->stream>>>(d.p, iters, 12345u + rep, 17u, 15u, 41u, 16u);
     else
-      k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d, iters, 12345u + rep, 17u, 15u, 41u, 16u);
+      k_imad_peak<1><<<blocks, threads, 0, c->stream>>>(d.p, iters, 12345u + rep, 17u, 15u, 41u, 16u);
     c->launches++;
     CU(cudaEventRecord(c->ev[1], c->stream));
     CU(ctx_wait(c));
@@ -921,7 +1002,6 @@ int qpzk_measure_imad_peak(qpzk_ctx* c, int kind, double* out_ops_per_s) {
     CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
     if (rep > 0 && ms < best) best = ms;
   }
-  dev_free(c, d);
   double ops = (double)blocks * threads * iters * 64;
   *out_ops_per_s = ops / (best * 1e-3);
   return QPZK_OK;

@@ -1,0 +1,141 @@
+// Device-resident Fiat-Shamir transcript for sm_100a: the duplex-sponge `Challenger` of qp-plonky2 1.1.1
+// (iop/challenger.rs, un-vendored; driven by `prove()` reached from
+// /root/reference/wormhole/prover/src/lib.rs:233-237) kept in HBM next to the challenges it produces, so
+// that a whole proof is ONE stream-ordered enqueue: every kernel that needs a challenge reads it from
+// `TranscriptDev`, nothing travels to the host between stages and the proving thread waits once, at the end.
+//
+// Semantics (pinned by the shipped proofs through tests/test_oracle_verifier.py):
+//   observe(x): the output buffer is dropped; x joins the input buffer; 8 buffered inputs trigger a duplex.
+//   duplex    : state[0..len) = inputs (OVERWRITE mode), permute, the 8 outputs are state[0..8).
+//   get()     : duplex first if inputs are pending or no output is left; outputs are popped from the END.
+// Inputs overwrite their state word as soon as they are observed (nothing reads the state between an
+// observation and the duplex that follows it), so the sponge is 12 words plus two counters.
+//
+// One 16-lane group runs the sponge (poseidon_permute_coop: one state word per lane).
+#pragma once
+#include "poseidon.cuh"
+
+namespace qpzk {
+
+#define QPZK_MAX_CHALLENGES 4
+#define QPZK_MAX_FRI_ROUNDS 16
+#define QPZK_MAX_QUERIES 128
+
+struct Challenges {
+  u64 beta[QPZK_MAX_CHALLENGES], gamma[QPZK_MAX_CHALLENGES], alpha[QPZK_MAX_CHALLENGES];
+};
+
+// Everything Fiat-Shamir produces for one proof, in the order the prover needs it. Lives in device memory;
+// copied back once with the proof pieces (the parity tests read the challenges from it).
+struct TranscriptDev {
+  u64 state[12];
+  u32 in_len, out_len;
+  u64 pi_hash[4];
+  Challenges ch;
+  u64 zeta[2], zeta_next[2];
+  u64 fri_alpha[2];
+  u64 fri_beta[QPZK_MAX_FRI_ROUNDS][2];
+  u64 pow_witness, pow_resp;
+  u64 xidx[QPZK_MAX_QUERIES];
+};
+// word offsets into TranscriptDev for the squeeze destination of k_transcript_step
+#define QPZK_TR_OFF(field) ((u32)(offsetof(TranscriptDev, field) / 8))
+
+struct TranscriptInit {  // the sponge after the host has observed circuit_digest | H(public_inputs)
+  u64 state[12];
+  u64 pi_hash[4];
+};
+
+__global__ void __launch_bounds__(32) k_transcript_init(TranscriptDev* __restrict__ T, TranscriptInit init) {
+  const u32 t = threadIdx.x;
+  if (t < 12) T->state[t] = init.state[t];
+  if (t < 4) T->pi_hash[t] = init.pi_hash[t];
+  if (t == 0) {
+    T->in_len = 0;
+    T->out_len = 8;  // eight observations = one duplex: its outputs are available
+    T->pow_witness = ~0ull;
+  }
+}
+
+// Per-lane view of the sponge (lane < 12 holds state[lane]); in_len / out_len are uniform.
+struct CoopSponge {
+  u64 s;
+  u32 in_len, out_len;
+};
+GL_DEV void sponge_duplex(CoopSponge& sp, u32 lane, u64* xch) {
+  sp.s = gl_canon(poseidon_permute_coop(sp.s, lane, xch, 0xffffu));
+  sp.in_len = 0;
+  sp.out_len = 8;
+}
+// src_mode 0: element i at src[i]; 1: extension coefficients stored SoA [2][m] observed interleaved
+// (element i = src[(i & 1) * m + (i >> 1)]). Observed values are also written, canonical, to `copy` (may be null).
+GL_DEV void sponge_observe(CoopSponge& sp, u32 lane, u64* xch, const u64* __restrict__ src, u32 n, u32 src_mode, u64 m,
+                           u64* __restrict__ copy) {
+  u32 i = 0;
+  while (i < n) {
+    const u32 room = 8 - sp.in_len, take = n - i < room ? n - i : room;
+    if (lane >= sp.in_len && lane < sp.in_len + take) {
+      const u32 e = i + lane - sp.in_len;
+      u64 v = src_mode ? src[(u64)(e & 1) * m + (e >> 1)] : src[e];
+      v = gl_canon(v);
+      sp.s = v;
+      if (copy) copy[e] = v;
+    }
+    sp.in_len += take;
+    sp.out_len = 0;
+    i += take;
+    if (sp.in_len == 8) sponge_duplex(sp, lane, xch);
+  }
+}
+GL_DEV u64 sponge_get(CoopSponge& sp, u32 lane, u64* xch) {
+  if (sp.in_len != 0 || sp.out_len == 0) sponge_duplex(sp, lane, xch);
+  sp.out_len--;
+  const u32 lo = __shfl_sync(0xffffu, (u32)sp.s, sp.out_len, 16), hi = __shfl_sync(0xffffu, (u32)(sp.s >> 32), sp.out_len, 16);
+  return ((u64)hi << 32) | lo;
+}
+
+// One transcript step: observe n elements, then squeeze nsq1 challenges into the words
+// ((u64*)T)[dst1 + j] and nsq2 more into ((u64*)T)[dst2 + j] (betas then gammas share one step).
+// post: 0 nothing; 1: also T->zeta_next = squeezed (zeta) * aux (aux = w_n, the generator of the trace
+// subgroup); 2: squeezed words j >= 1 are masked with aux (query indices after the PoW response).
+__global__ void __launch_bounds__(16)
+k_transcript_step(TranscriptDev* __restrict__ T, const u64* __restrict__ src, u32 n, u32 src_mode, u64 m,
+                  u64* __restrict__ copy, u32 nsq1, u32 dst1, u32 nsq2, u32 dst2, u32 post, u64 aux) {
+  __shared__ u64 xch[COOP_XCH_WORDS];
+  const u32 lane = threadIdx.x;
+  CoopSponge sp;
+  sp.s = lane < 12 ? T->state[lane] : 0;
+  sp.in_len = T->in_len;
+  sp.out_len = T->out_len;
+  sponge_observe(sp, lane, xch, src, n, src_mode, m, copy);
+  u64* words = reinterpret_cast<u64*>(T);
+  for (u32 j = 0; j < nsq1 + nsq2; j++) {
+    u64 v = sponge_get(sp, lane, xch);  // every lane holds the value
+    if (post == 2 && j >= 1) v &= aux;
+    if (lane == 0) words[j < nsq1 ? dst1 + j : dst2 + (j - nsq1)] = v;
+    if (post == 1 && j < 2 && lane == 1) T->zeta_next[j] = gl_canon(gl_mul(v, aux));
+  }
+  if (lane < 12) T->state[lane] = sp.s;
+  if (lane == 0) {
+    T->in_len = sp.in_len;
+    T->out_len = sp.out_len;
+  }
+}
+
+// alpha_c^t for t < stride: the table the quotient kernel reduces constraint terms with (prover.cuh AlphaAcc).
+__global__ void __launch_bounds__(256) k_alpha_powers(const TranscriptDev* __restrict__ T, u32 stride, u64* __restrict__ apw) {
+  const u32 c = blockIdx.x;
+  const u64 a = T->ch.alpha[c];
+  for (u32 t = threadIdx.x; t < stride; t += blockDim.x) apw[c * stride + t] = gl_canon(gl_pow(a, t));
+}
+
+// Small host values into device words without a host-to-device copy (a pageable cudaMemcpyAsync
+// synchronises the stream): the per-stage hooks place caller-provided challenges this way.
+struct Words16 {
+  u64 w[16];
+};
+__global__ void k_set_words(u64* __restrict__ dst, Words16 v, u32 n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = v.w[threadIdx.x];
+}
+
+}  // namespace qpzk

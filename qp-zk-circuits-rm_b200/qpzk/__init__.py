@@ -86,12 +86,18 @@ def load_library():
         "qpzk_batch_degree_bits": (u32, [_vp]),
         "qpzk_batch_free": (None, [_vp]),
         "qpzk_measure_imad_peak": (i, [_vp, i, ctypes.POINTER(ctypes.c_double)]),
-        "qpzk_circuit_create": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, _vp, ctypes.POINTER(_vp)]),
-        "qpzk_circuit_cap": (i, [_vp, _u64p]),
+        "qpzk_batch_from_coeffs_shard_dev": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, u32, u32,
+                                                 ctypes.POINTER(_vp)]),
+        "qpzk_circuit_create": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, _vp, ctypes.c_size_t,
+                                    ctypes.POINTER(_vp)]),
+        "qpzk_circuit_cap": (i, [_vp, _u64p, ctypes.c_size_t]),
+        "qpzk_circuit_info": (i, [_vp, _u32p]),
         "qpzk_circuit_verifier_only": (ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
         "qpzk_circuit_free": (None, [_vp]),
-        "qpzk_prove": (i, [_vp, _vp, _u64p, u32, _vp, _vp, _vp, u32, ctypes.c_char_p, ctypes.c_size_t,
-                           ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_prove": (i, [_vp, _vp, ctypes.c_size_t, _u64p, u32, _vp, _vp, _vp, ctypes.c_size_t, u32, ctypes.c_char_p,
+                           ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_prove_begin": (i, [_vp, _vp, ctypes.c_size_t, _u64p, u32, _vp, _vp, _vp, ctypes.c_size_t, u32]),
+        "qpzk_prove_end": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
         "qpzk_zs_partial_products": (i, [_vp, _vp, _u64p, _u64p, _u64p]),
         "qpzk_quotient": (i, [_vp, _vp, _vp, _u64p, _u64p, _u64p, _u64p, _u64p]),
         "qpzk_fri_begin": (i, [_vp, _vp, _vp, _vp, _u64p, _u64p, ctypes.POINTER(_vp)]),
@@ -472,7 +478,12 @@ PROVE_STAGES = ("commit_wires", "zs_partial_products_commit", "quotient_commit",
 class Circuit:
     """Prover-side circuit data (`ProverCircuitData` after `build()`): the constants|sigmas batch is
     committed once here and stays on the device; `prove(wires, public_inputs)` then mirrors
-    `ProverCircuitData::prove` after witness generation and returns `ProofWithPublicInputs` bytes."""
+    `ProverCircuitData::prove` after witness generation and returns `ProofWithPublicInputs` bytes.
+    One proof at a time per Circuit; `prove_begin` / `prove_end` split the call so that one host thread can
+    keep several contexts busy."""
+
+    INFO = ("degree_bits", "rate_bits", "cap_height", "num_wires", "num_routed", "num_challenges", "salt_cols",
+            "num_public_inputs")
 
     def __init__(self, ctx, common_bytes, circuit_digest, constants_sigmas):
         L = load_library()
@@ -480,54 +491,71 @@ class Circuit:
         dg = _arr(circuit_digest)
         h = _vp()
         cb = bytes(common_bytes)
-        _check(L.qpzk_circuit_create(ctx._h, cb, len(cb), _ptr(dg), cs.ctypes.data_as(_vp), ctypes.byref(h)))
+        _check(L.qpzk_circuit_create(ctx._h, cb, len(cb), _ptr(dg), cs.ctypes.data_as(_vp), cs.size, ctypes.byref(h)))
         self.ctx, self._h, self.common = ctx, h, cb
-        self.n = cs.shape[1]
+        info = (ctypes.c_uint32 * 8)()
+        _check(L.qpzk_circuit_info(h, info))
+        self.info = dict(zip(self.INFO, [int(x) for x in info]))
+        self.n = 1 << self.info["degree_bits"]
+        self.wires_words = self.info["num_wires"] * self.n
+        self.salt_words = SALT_SIZE << (self.info["degree_bits"] + self.info["rate_bits"])
+        self._keep = None
+        self._buf = ctypes.create_string_buffer(1 << 20)
 
     @property
     def constants_sigmas_cap(self):
-        out = np.zeros((16, 4), np.uint64)
-        buf = np.zeros(4096, np.uint64)
-        _check(load_library().qpzk_circuit_cap(self._h, _ptr(buf)))
-        vo = self.verifier_only_bytes()
-        ncap = (len(vo) - 8 - 32) // 32
-        return buf[:4 * ncap].reshape(ncap, 4).copy()
+        ncap = 1 << self.info["cap_height"]
+        out = np.zeros((ncap, 4), np.uint64)
+        _check(load_library().qpzk_circuit_cap(self._h, _ptr(out), out.size))
+        return out
 
     def verifier_only_bytes(self):
         L = load_library()
-        buf = ctypes.create_string_buffer(1 << 16)
-        k = L.qpzk_circuit_verifier_only(self._h, buf, 1 << 16)
+        need = L.qpzk_circuit_verifier_only(self._h, None, 0)
+        buf = ctypes.create_string_buffer(max(need, 1))
+        k = L.qpzk_circuit_verifier_only(self._h, buf, need)
         return buf.raw[:k]
 
-    def prove(self, wires, public_inputs, salts=None, trace=False):
-        L = load_library()
+    def _host_args(self, wires, public_inputs, salts):
         w = _arr(wires)
         pi = _arr(public_inputs)
-        sp = [None, None, None]
-        keep = []
+        sp, keep, salt_words = [None, None, None], [w, pi], 0
         if salts is not None:
             for j in range(3):
                 a = _arr(salts[j])
                 keep.append(a)
                 sp[j] = a.ctypes.data_as(_vp)
-        cap = 1 << 20
-        buf = ctypes.create_string_buffer(cap)
-        ln = ctypes.c_size_t(0)
-        _check(L.qpzk_prove(self._h, w.ctypes.data_as(_vp), _ptr(pi), pi.size, sp[0], sp[1], sp[2],
-                            1 if trace else 0, buf, cap, ctypes.byref(ln)))
-        return buf.raw[:ln.value]
+                salt_words = a.size
+        return w.ctypes.data_as(_vp), w.size, pi, sp, salt_words, keep
+
+    def prove(self, wires, public_inputs, salts=None, trace=False):
+        self.prove_begin(wires, public_inputs, salts, trace=trace)
+        return self.prove_end()
 
     def prove_dev(self, wires_dev, public_inputs, salts_dev=None):
         """Same as prove() with the witness matrix (and salts) already resident on the device."""
-        L = load_library()
+        self.prove_begin_dev(wires_dev, public_inputs, salts_dev)
+        return self.prove_end()
+
+    def prove_begin(self, wires, public_inputs, salts=None, trace=False):
+        """Enqueue one proof (qpzk_prove_begin); the host arrays must stay alive until prove_end()."""
+        wp, wn, pi, sp, sn, keep = self._host_args(wires, public_inputs, salts)
+        _check(load_library().qpzk_prove_begin(self._h, wp, wn, _ptr(pi), pi.size, sp[0], sp[1], sp[2], sn,
+                                               1 if trace else 0))
+        self._keep = keep
+
+    def prove_begin_dev(self, wires_dev, public_inputs, salts_dev=None):
         pi = _arr(public_inputs)
         sp = [None, None, None] if salts_dev is None else [_vp(x) for x in salts_dev]
-        cap = 1 << 20
-        buf = ctypes.create_string_buffer(cap)
+        _check(load_library().qpzk_prove_begin(self._h, _vp(wires_dev), self.wires_words, _ptr(pi), pi.size, sp[0], sp[1],
+                                               sp[2], self.salt_words if salts_dev is not None else 0, 2))
+        self._keep = [pi]
+
+    def prove_end(self):
         ln = ctypes.c_size_t(0)
-        _check(L.qpzk_prove(self._h, _vp(wires_dev), _ptr(pi), pi.size, sp[0], sp[1], sp[2], 2, buf, cap,
-                            ctypes.byref(ln)))
-        return buf.raw[:ln.value]
+        _check(load_library().qpzk_prove_end(self._h, self._buf, len(self._buf), ctypes.byref(ln)))
+        self._keep = None
+        return self._buf.raw[:ln.value]
 
     def zs_partial_products(self, wires, betas, gammas, nch=2, npp=9):
         """H8 as a stand-alone stage: [nch*(1+npp)][n]."""

@@ -52,6 +52,7 @@ extern "C" {
     pub fn qpzk_batch_from_values_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_from_coeffs_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_from_values_shard_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_batch_from_coeffs_shard_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_cap(b: *const qpzk_batch, out_: *mut u64) -> c_int;
     pub fn qpzk_batch_cap_dev(b: *mut qpzk_batch) -> *mut u64;
     pub fn qpzk_batch_set_cap(b: *mut qpzk_batch, cap: *const u64) -> c_int;
@@ -60,16 +61,18 @@ extern "C" {
     pub fn qpzk_batch_open(b: *const qpzk_batch, leaf_index: u64, leaf_out: *mut u64, siblings_out: *mut u64) -> c_int;
     pub fn qpzk_batch_export(b: *const qpzk_batch, leaves: *mut u64, digests: *mut u64) -> c_int;
     pub fn qpzk_batch_eval_ext(b: *const qpzk_batch, point: *const u64, out_: *mut u64) -> c_int;
-    pub fn qpzk_fri_pow(ctx: *mut qpzk_ctx, sponge_state: *const u64, input_pos: u32, min_leading_zeros: u32, witness_out: *mut u64) -> c_int;
     pub fn qpzk_batch_ncols(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_width(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_degree_bits(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_free(b: *mut qpzk_batch);
-    pub fn qpzk_circuit_create(ctx: *mut qpzk_ctx, common_bytes: *const u8, common_len: usize, circuit_digest: *const u64, constants_sigmas: *const u64, out_: *mut *mut qpzk_circuit) -> c_int;
-    pub fn qpzk_circuit_cap(c: *const qpzk_circuit, out_: *mut u64) -> c_int;
+    pub fn qpzk_circuit_create(ctx: *mut qpzk_ctx, common_bytes: *const u8, common_len: usize, circuit_digest: *const u64, constants_sigmas: *const u64, constants_sigmas_words: usize, out_: *mut *mut qpzk_circuit) -> c_int;
+    pub fn qpzk_circuit_cap(c: *const qpzk_circuit, out_: *mut u64, cap_words: usize) -> c_int;
+    pub fn qpzk_circuit_info(c: *const qpzk_circuit, out_: *mut u32) -> c_int;
     pub fn qpzk_circuit_verifier_only(c: *const qpzk_circuit, out_: *mut u8, cap: usize) -> usize;
     pub fn qpzk_circuit_free(c: *mut qpzk_circuit);
-    pub fn qpzk_prove(c: *mut qpzk_circuit, wires: *const u64, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+    pub fn qpzk_prove(c: *mut qpzk_circuit, wires: *const u64, wires_words: usize, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, salt_words: usize, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+    pub fn qpzk_prove_begin(c: *mut qpzk_circuit, wires: *const u64, wires_words: usize, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, salt_words: usize, flags: u32) -> c_int;
+    pub fn qpzk_prove_end(c: *mut qpzk_circuit, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn qpzk_zs_partial_products(c: *mut qpzk_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out_: *mut u64) -> c_int;
     pub fn qpzk_quotient(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, pi_hash: *const u64, betas: *const u64, gammas: *const u64, alphas: *const u64, out_chunks: *mut u64) -> c_int;
     pub fn qpzk_fri_begin(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, quotient_batch: *const qpzk_batch, zeta: *const u64, alpha: *const u64, out_: *mut *mut qpzk_fri) -> c_int;
@@ -81,5 +84,6 @@ extern "C" {
     pub fn qpzk_fri_free(f: *mut qpzk_fri);
     pub fn qpzk_prove_trace(c: *const qpzk_circuit, which: c_int, out_: *mut u64) -> usize;
     pub fn qpzk_prove_stage_ms(c: *const qpzk_circuit, out16: *mut f32) -> c_int;
+    pub fn qpzk_fri_pow(ctx: *mut qpzk_ctx, sponge_state: *const u64, input_pos: u32, min_leading_zeros: u32, witness_out: *mut u64) -> c_int;
     pub fn qpzk_measure_imad_peak(ctx: *mut qpzk_ctx, kind: c_int, out_ops_per_s: *mut f64) -> c_int;
 }

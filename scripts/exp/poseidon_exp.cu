@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "../../qp-zk-circuits-rm_b200/csrc/poseidon.cuh"
-#include "../../qp-zk-circuits-rm_b200/csrc/poseidon_tables.hpp"
+#include "../../qp-zk-circuits-rm_b200/csrc/poseidon_upload.cuh"
 
 using namespace qpzk;
 
@@ -68,34 +68,7 @@ int main(int argc, char** argv) {
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { printf("host KAT ok; no GPU\n"); return 0; }
-  CK(cudaMemcpyToSymbol(c_rc, T->rc, sizeof T->rc));
-  CK(cudaMemcpyToSymbol(c_fast_first, T->fast_first, sizeof T->fast_first));
-  CK(cudaMemcpyToSymbol(c_fast_rc, T->fast_rc, sizeof T->fast_rc));
-  CK(cudaMemcpyToSymbol(c_fast_init, T->fast_init, sizeof T->fast_init));
-  CK(cudaMemcpyToSymbol(c_fast_w_hat, T->fast_w_hat, sizeof T->fast_w_hat));
-  CK(cudaMemcpyToSymbol(c_fast_v, T->fast_v, sizeof T->fast_v));
-  CK(cudaMemcpyToSymbol(c_h_rc, T->h_rc, sizeof T->h_rc));
-  CK(cudaMemcpyToSymbol(c_h_init, T->h_init, sizeof T->h_init));
-  CK(cudaMemcpyToSymbol(c_h_w_hat, T->h_w_hat, sizeof T->h_w_hat));
-  CK(cudaMemcpyToSymbol(c_h_v, T->h_v, sizeof T->h_v));
-  u32 circ[12];
-  for (int i = 0; i < 12; i++) circ[i] = (u32)kMdsCirc[i];
-  u32 diag0 = (u32)kMdsDiag0;
-  CK(cudaMemcpyToSymbol(c_mds_circ, circ, sizeof circ));
-  CK(cudaMemcpyToSymbol(c_mds_diag0, &diag0, sizeof diag0));
-#if PV_MDS_F64
-  {
-    double cd[12];
-    for (int i = 0; i < 12; i++) cd[i] = (double)kMdsCirc[i];
-    CK(cudaMemcpyToSymbol(c_mds_circ_d, cd, sizeof cd));
-    static double next_rc[QPZK_MDS_LAYERS_MAX][2][12];
-    poseidon_next_rc_f64(*T, next_rc, PV_MDS_SPLIT != 0);
-      static double half_d[12];
-      poseidon_mds_half_f64(half_d);
-      CK(cudaMemcpyToSymbol(c_mds_half_d, half_d, sizeof half_d));
-    CK(cudaMemcpyToSymbol(c_mds_next_rc_d, next_rc, sizeof next_rc));
-  }
-#endif
+  CK(poseidon_upload_tables(*T));
   const u64 n = 1 << 19;
   const int reps = argc > 1 ? atoi(argv[1]) : 17;
   std::vector<u64> h((size_t)reps * 8 * n);
