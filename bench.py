@@ -322,12 +322,13 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     S = max(1, args.streams)
-    # a spinning proving thread occupies a host core while its stream works: once threads x ranks exceed the
-    # cores the threads poll and yield instead
+    HT = max(1, min(args.host_threads, S))
+    # a proof is one stream-ordered enqueue (qpzk_prove_begin) and one wait (qpzk_prove_end), so HT host
+    # threads keep S proofs in flight; a waiting thread spins on a core unless threads x ranks exceed the cores
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sync = args.sync
     if sync == "auto":
-        sync = "spin" if S * max(1, world) <= cores else "yield"
+        sync = "spin" if HT * max(1, world) <= cores else "yield"
     ctxs = [qpzk.Context(local_rank, blocking_sync=sync == "blocking", yield_sync=sync == "yield") for _ in range(S)]
     ctx0 = ctxs[0]
 
@@ -361,21 +362,30 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    results = [None] * S
+    results = [None] * HT
 
-    def worker(s, count, resident):
-        out = None
-        for _ in range(count):
-            if resident:
-                out = circuits[s].prove_dev(dev_w[s], circ["public_inputs"], dev_s[s])
-            else:
-                out = circuits[s].prove(pinned_w[s].array, circ["public_inputs"], [a.array for a in pinned_s[s]])
-        results[s] = out
+    def worker(t, count, resident):
+        """Host thread t keeps its streams (t, t + HT, ...) full: begin on every idle stream, then end on the
+        oldest proof in flight."""
+        mine = list(range(t, S, HT))
+        inflight, issued, done, out = [], 0, 0, None
+        while done < count:
+            while issued < count and len(inflight) < len(mine):
+                s = mine[issued % len(mine)]
+                if resident:
+                    circuits[s].prove_begin_dev(dev_w[s], circ["public_inputs"], dev_s[s])
+                else:
+                    circuits[s].prove_begin(pinned_w[s].array, circ["public_inputs"], [a.array for a in pinned_s[s]])
+                inflight.append(s)
+                issued += 1
+            out = circuits[inflight.pop(0)].prove_end()
+            done += 1
+        results[t] = out
 
     def run_round(total, resident):
-        # exactly `total` proofs, spread over the S streams
-        th = [threading.Thread(target=worker, args=(s, total // S + (1 if s < total % S else 0), resident))
-              for s in range(S)]
+        # exactly `total` proofs, spread over the HT host threads (and through them over the S streams)
+        th = [threading.Thread(target=worker, args=(t, total // HT + (1 if t < total % HT else 0), resident))
+              for t in range(HT)]
         for t in th:
             t.start()
         for t in th:
@@ -398,11 +408,12 @@ def run_gpu(args, rank, local_rank, world):
             ms = float(t.item())
         return ms
 
-    steps_total = args.steps
+    # a step = one proof on every stream of this GPU (S proofs): the timed region is steps x S proofs per GPU
+    steps_total = args.steps * S
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    run_round(max(args.warmup, S), True)
+    run_round(args.warmup * S, True)     # W warm-up steps
     run_round(S, False)
     if rank == 0:
         sampler.wait_first()
@@ -541,16 +552,17 @@ def run_gpu(args, rank, local_rank, world):
         h2d = int(circ["wires"].nbytes + sum(s.nbytes for s in circ["salts"]))
         line = {
             "metric": METRIC, "value": total / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": steps_total, "warmup": args.warmup, "ms_per_step": ms_res / steps_total,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "degree_bits": PROOF_K, "zero_knowledge": PROOF_ZK,
-                       "streams_per_gpu": S, "host_wait": sync, "host_cores": cores,
+                       "proofs_per_step": S * world, "step": "one proof on each of the %d streams of every GPU" % S,
+                       "streams_per_gpu": S, "host_threads_per_gpu": HT, "host_wait": sync, "host_cores": cores,
                        "l2": "each proof streams ~0.3 GB of LDE/digest buffers through HBM (> 126 MB L2); "
                              "the commit microbench rotates 4 distinct 70.8 MB traces",
                        "parallelism": "independent proofs, %d stream(s) per GPU, no collective" % S},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps_total,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(proof)},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d * S, "d2h_bytes_per_step": len(proof) * S},
             "gpu_launches": int(launches),
             "single_proof_latency_ms": latency_ms,
             "proof_stage_ms": proof_stages,
@@ -609,10 +621,12 @@ def run_gpu(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=16, help="a step = one proof on every stream of every GPU")
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--streams", type=int, default=8,
                     help="proofs in flight per GPU (measured at 128 steps: 6: 204, 8: 207, 12: 208 proofs/s; 8 divides the default step count)")
+    ap.add_argument("--host-threads", type=int, default=1,
+                    help="host threads per GPU driving the streams through qpzk_prove_begin / qpzk_prove_end")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sync", default="auto", choices=["auto", "spin", "yield", "blocking"],
@@ -632,7 +646,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--streams", str(args.streams), "--sync", args.sync]
+               "--streams", str(args.streams), "--sync", args.sync, "--host-threads", str(args.host_threads)]
         cmd += ["--no-cpu"] * args.no_cpu + ["--no-aggregator"] * args.no_aggregator
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)

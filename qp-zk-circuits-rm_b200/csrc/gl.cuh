@@ -64,9 +64,32 @@ GL_DEV u64 gl_fold_mul(u64 lo, u32 r2, u64 h) {
   asm("mad.hi.u32 %0, %1, 2, %0;" : "+r"(rh) : "r"(k));  // ... so give the 2^32 back: hi += k >> 31
   return ((u64)rh << 32) | rl;
 }
+// Third spelling: r2*EPS rides on ONE multiply-add whose addend is lo (IMAD.WIDE with carry-out), -h is a
+// two-word subtract, the carry and the borrow meet in k = C - B and the usual single correction follows:
+// 7-8 instructions, one of them on the multiplier pipe.
+GL_DEV u64 gl_fold_mad(u64 lo, u32 r2, u64 h) {
+  u32 t0 = (u32)lo, t1 = (u32)(lo >> 32), h0 = (u32)h, h1 = (u32)(h >> 32), k, sx;
+  asm("{\n\t.reg .u32 c;\n\t"
+      "mad.lo.cc.u32 %0, %4, 0xffffffff, %0;\n\t"
+      "madc.hi.cc.u32 %1, %4, 0xffffffff, %1;\n\t"
+      "addc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, %5;\n\t"
+      "subc.cc.u32 %1, %1, %6;\n\t"
+      "subc.u32 %2, c, 0;\n\t"           // k = carry - borrow: 0, 1 or 0xffffffff
+      "shr.s32 %3, %2, 31;\n\t"
+      "sub.cc.u32 %0, %0, %2;\n\t"       // + k*EPS = + (k << 32) - k
+      "subc.u32 %1, %1, %3;\n\t"
+      "add.u32 %1, %1, %2;\n\t"
+      "}"
+      : "+r"(t0), "+r"(t1), "=&r"(k), "=&r"(sx)
+      : "r"(r2), "r"(h0), "r"(h1));
+  return ((u64)t1 << 32) | t0;
+}
 GL_DEV u64 gl_fold(u64 lo, u32 r2, u64 h) {
-#if GL_FOLD_ALU
+#if GL_FOLD_ALU == 1
   return gl_fold_alu(lo, r2, h);
+#elif GL_FOLD_ALU == 2
+  return gl_fold_mad(lo, r2, h);
 #else
   return gl_fold_mul(lo, r2, h);
 #endif

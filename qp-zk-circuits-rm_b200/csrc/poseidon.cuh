@@ -425,10 +425,13 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
 // round is executed in the textbook form (constants, s-box on all lanes or on lane 0, MDS) - the same
 // permutation as the sparse partial-round form, so results are bit-identical.
 __device__ u64 g_rc[372];  // lane-indexed reads: global/L1, not the constant bank (divergent index); 12 zeros appended
-#define COOP_XCH_WORDS 24
+#define COOP_XCH_WORDS 48
 
 // s: this lane's state word (lanes 12..15 of the group carry garbage and must be ignored by the caller).
-// xch: COOP_XCH_WORDS u64 of shared memory private to the 16-lane group (double buffer).
+// xch: COOP_XCH_WORDS u64 of shared memory private to the 16-lane group: two buffers of 24 words. Every
+// lane stores its word TWICE, at [lane] and [lane + 12], so that the circulant row of lane l is the 12
+// consecutive words [l, l + 12): one base address and immediate offsets instead of a compare-and-wrap per
+// load (25 of the ~185 instructions of a round, all of them on the dependent chain of a single warp).
 // mask: the lanes that execute this call together (__syncwarp mask) - the whole warp when both 16-lane
 // groups of a warp run in lockstep, one half when they may diverge (tree climbing, merkle.cuh).
 // The constants of round r + 1 enter as the initial value of round r's MDS accumulators (their 32-bit halves
@@ -445,16 +448,17 @@ GL_DEV u64 poseidon_permute_coop(u64 s, u32 lane, u64* xch, u32 mask = 0xfffffff
     rc_next = __ldg(&g_rc[(r < 28 ? r + 2 : 30) * 12 + li]);  // the last two trips read the zero padding
     const bool full = r < 4 || r >= 26;
     if (full || lane == 0) s = sbox7(s);
-    u64* buf = xch + (r & 1) * 12;
-    if (act) buf[lane] = s;
+    u64* buf = xch + (r & 1) * 24;
+    if (act) {
+      buf[lane] = s;
+      buf[lane + 12] = s;
+    }
     __syncwarp(mask);
+    const u64* row = buf + li;
     u32 al0 = (u32)rc, al1 = 0, ah0 = (u32)(rc >> 32), ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
 #pragma unroll
     for (int i = 0; i < 12; i += 2) {
-      u32 j0 = li + i, j1 = li + i + 1;
-      j0 = j0 >= 12 ? j0 - 12 : j0;
-      j1 = j1 >= 12 ? j1 - 12 : j1;
-      const u64 v0 = buf[j0], v1 = buf[j1];
+      const u64 v0 = row[i], v1 = row[i + 1];
       mad_wide(al0, al1, (u32)v0, c_mds_circ[i]);
       mad_wide(ah0, ah1, (u32)(v0 >> 32), c_mds_circ[i]);
       mad_wide(bl0, bl1, (u32)v1, c_mds_circ[i + 1]);

@@ -314,7 +314,10 @@ static bool validate_common(const CommonHost& c, std::string* err) {
 struct ByteWriter {
   std::vector<uint8_t> b;
   void u(u64 v, size_t bytes) { for (size_t i = 0; i < bytes; i++) b.push_back((uint8_t)(v >> (8 * i))); }
-  void felts(const u64* x, size_t n) { for (size_t i = 0; i < n; i++) u(x[i], 8); }
+  void felts(const u64* x, size_t n) {  // little-endian host (x86-64 / aarch64): the words are the bytes
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(x);
+    b.insert(b.end(), p, p + 8 * n);
+  }
 };
 
 }  // namespace qpzk
