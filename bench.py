@@ -47,9 +47,9 @@ WORKLOAD = ("wormhole single-proof generation, bench-data shape (2^14 x 135 wire
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture per kernel
-# profiles/r1_ntt_v2_ncu_full.txt: k_ntt_pass_a<0>, k_ntt_pass_b_transpose, k_ntt_pass_a<1>, k_ntt_pass_b_rows
-NTT_DRAM_BYTES_PER_COMMIT = int((71.430912 + 28.294144 + 70.869504 + 25.209344 +
-                                 75.717888 + 509.248000 + 566.322176 + 506.380288) * 1e6)
+# IFFT (two passes): profiles/r1_ntt_v2_ncu_full.txt k_ntt_pass_a<0>, k_ntt_pass_b_transpose;
+# LDE (one pass, cluster kernel): profiles/r2_ntt_cluster_2p16_ncu_full.txt
+NTT_DRAM_BYTES_PER_COMMIT = int((71.430912 + 28.294144 + 70.869504 + 25.209344 + 75.771648 + 512.583936) * 1e6)
 LEAF_HASH_DRAM_BYTES_PER_COMMIT = int((566.815232 + 17.787392) * 1e6)   # profiles/r1_leaf_hash_v5_twoplane_ncu_full.txt
 
 
@@ -569,13 +569,14 @@ def run_gpu(args, rank, local_rank, world):
             "circuit_constants_sigmas_commit_ms": circuit_commit_ms,
             "commit_microbench": {"workload": "PolynomialBatch::from_values 2^16 x 135, rate_bits=3, cap_height=4 "
                                               "(BASELINE configs[2])", "ms": sum(micro.values()), "stage_ms": micro},
-            "roofline": {"bound": "hbm", "kernel": "commit microbench: IFFT + coset-LDE NTT passes "
-                                                   "(k_ntt_pass_a / k_ntt_pass_b_*)",
+            "roofline": {"bound": "hbm", "kernel": "commit microbench: IFFT (k_ntt_pass_a / k_ntt_pass_b_transpose) + "
+                                                   "coset LDE (k_ntt_cluster)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of the four NTT launches of one commit
-                         # (two passes over HBM: 2.9x the algorithmic bytes - the second pass re-reads and
-                         # re-writes the LDE; the kernels are integer-issue-bound, not HBM-bound)
-                         "traffic": NTT_DRAM_BYTES_PER_COMMIT, "traffic_source": "profiles/r1_ntt_v2_ncu_full.txt",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the three NTT launches of one commit: the
+                         # LDE is one pass over HBM (cluster kernel, tile in distributed shared memory), the IFFT
+                         # two; the kernels are integer-issue-bound, not HBM-bound
+                         "traffic": NTT_DRAM_BYTES_PER_COMMIT,
+                         "traffic_source": "profiles/r1_ntt_v2_ncu_full.txt (IFFT) + profiles/r2_ntt_cluster_2p16_ncu_full.txt (LDE)",
                          "peak_source": peak_src, "algorithmic_bytes": alg["ntt_bytes"],
                          "stage_ms": ntt_ms,
                          "note": "the north star's split: HBM roofline for the NTT/transpose stages (integer-issue-bound "

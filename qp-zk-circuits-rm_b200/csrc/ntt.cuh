@@ -19,9 +19,12 @@
 //    rows. Every global access is a full 128-byte line.
 //  * Twiddles come from two-level tables (w^e = lo[e & m] * hi[e >> lk]) that stay L1/L2 resident.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "gl.cuh"
 
 namespace qpzk {
+namespace cg = cooperative_groups;
 
 struct RootTab {
   const u64* lo;  // [2^lk]      root^e
@@ -291,6 +294,78 @@ k_ntt_small(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, 
     if (scale != 1) v = gl_mul(v, scale);
     d[q] = gl_canon(v);
   }
+}
+
+// ---- one pass over HBM for 2^15 and 2^16 points: a thread-block CLUSTER holds the (column, coset) tile ----
+// Above 2^14 points a tile no longer fits one SM's shared memory and the two-pass kernels below write the
+// half-transformed data to HBM and read it back (DRAM traffic 2.9x the algorithmic bytes at 2^16 x 135,
+// profiles/r1_ntt_v2_ncu_full.txt). Eight CTAs of a cluster have 8 x 227 KB between them: with n = R * B,
+// R = 2^A1 (8 or 16),
+//   phase 1  CTA c takes the columns j2 in [c*B/8, (c+1)*B/8) of the [R][B] view: R coalesced loads per thread
+//            (coset pre-multiplier applied), an R-point DFT in registers (w_16 = 2^12: shifts only), the
+//            twiddle w_n^(j2*k1), and each result goes straight into the shared memory of the CTA that owns its
+//            row - the row at DIF position p = rev(k1) lives in CTA p / (R/8) - as a distributed-shared-memory
+//            store;
+//   phase 2  after one cluster barrier every CTA holds R/8 complete rows: B-point DIFs in its own shared memory
+//            (three radix-16 stages at B = 2^12), written to the contiguous block [p*B, (p+1)*B) of the
+//            bit-reversed output.
+// The coefficients are read once and the evaluations written once. Three CTAs per SM (launch bounds) so that
+// the CTAs of other clusters run while one waits at its barrier.
+#define QPZK_NTT_CLUSTER 8
+template <int A1, int THREADS>
+__global__ void __cluster_dims__(QPZK_NTT_CLUSTER, 1, 1) __launch_bounds__(THREADS, 3)
+k_ntt_cluster(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst, u64 dst_stride,
+              const u64* __restrict__ pm, RootTab tabB, const u64* __restrict__ tw1, const u64* __restrict__ twc,
+              int k, int r, u32 blk0) {
+  constexpr int R = 1 << A1;
+  constexpr int RPC = R / QPZK_NTT_CLUSTER;           // rows per CTA
+  constexpr u32 RPC_LOG = A1 - 3;
+  extern __shared__ u64 smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lb = k - A1;                               // log2 B
+  const u32 B = 1u << lb;
+  const u32 pitch = tile_pitch(B);
+  u64* x = smem;                                       // [RPC][pitch]
+  u64* tw = smem + RPC * pitch;
+  const u32 rank = cluster.block_rank();
+  const u32 col = blockIdx.z, blk = blk0 + blockIdx.y, t = brev(blk, r);
+  // twiddles of the local transform, then make sure every CTA of the cluster is running before its shared
+  // memory is written from outside
+  TwFill{tw, tabB, tw1 ? B >> 4 : B, tw1 ? 4 : 0}();
+  cluster.sync();
+  {
+    const u64* s = src + (u64)col * src_stride;
+    const u64* pmt = pm ? pm + ((u64)t << k) : nullptr;
+    u64* remote[QPZK_NTT_CLUSTER];
+#pragma unroll
+    for (int c = 0; c < QPZK_NTT_CLUSTER; c++) remote[c] = cluster.map_shared_rank(x, c);
+    const u32 per = B >> 3;  // columns j2 of this CTA
+    for (u32 i = threadIdx.x; i < per; i += THREADS) {
+      const u32 j2 = rank * per + i;
+      u64 v[R];
+#pragma unroll
+      for (int j1 = 0; j1 < R; j1++) v[j1] = s[((u64)j1 << lb) + j2];
+      if (pmt) {
+#pragma unroll
+        for (int j1 = 0; j1 < R; j1++) v[j1] = gl_mul(v[j1], pmt[((u64)j1 << lb) + j2]);
+      }
+      dft_regs<A1, false>(v);
+      const u32 pos = j2 + (j2 >> 4);
+#pragma unroll
+      for (int p = 0; p < R; p++) {
+        const u32 k1 = __brev((u32)p) >> (32 - A1);
+        u64 e = v[p];
+        if (p != 0) e = gl_mul(e, twc[((u64)k1 << lb) + j2]);
+        remote[p >> RPC_LOG][(p & (RPC - 1)) * pitch + pos] = e;
+      }
+    }
+  }
+  cluster.sync();
+  tile_dif<false, false>(x, tw, tw1, lb, RPC_LOG, pitch, TileLd<false>{x, RPC_LOG, pitch}, TileSt<false>{x, RPC_LOG, pitch},
+                         NoPre());
+  u64* d = dst + (u64)col * dst_stride + ((u64)blk << k) + ((u64)(rank * RPC) << lb);
+  for (u32 q = threadIdx.x; q < RPC * B; q += THREADS)
+    d[q] = gl_canon(x[tile_pos<false>(q >> lb, q & (B - 1), 0, pitch)]);
 }
 
 // ---- pass A: strided n1-point DIF + inter-pass twiddle ----

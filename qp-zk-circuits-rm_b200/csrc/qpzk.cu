@@ -253,6 +253,14 @@ static int get_coset_pm(qpzk_ctx* c, int k, int r, u64 shift, const u64** out) {
 static const int kSmallMaxLog = 14;
 static const int kSmallTableLog = 12;  // up to here the full twiddle table fits next to the tile
 static const int kSmallSmemBytes = 148 * 1024;
+static const int kClusterMaxLog = 16;  // 8 CTAs x 2 rows of 2^12 points
+static bool ntt_cluster_enabled() {    // QPZK_NTT_CLUSTER=0: the two-pass kernels (A/B measurements)
+  static const bool on = [] {
+    const char* e = getenv("QPZK_NTT_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 // (Tried and dropped: running the two passes of a long transform per group of columns small enough for
 // pass A's output to stay in the 126 MB L2 until pass B overwrites it in place. The kernels are
@@ -290,6 +298,24 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
   u32 ncosets = nblk;
   if (k <= kSmallMaxLog) return launch_small<false>(c, coeffs, src_stride, lde, dst_stride, pm, tab, ncols, ncosets, k, r, 1, blk0);
   if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
+  if (k <= kClusterMaxLog && ntt_cluster_enabled()) {  // 2^15, 2^16 points: one pass, the tile spread over a cluster
+    const int a1 = k - 12, lb = 12;                    // n = 2^a1 rows of 2^12 points: radix-8 / radix-16 across the cluster
+    RootTab tab_b;
+    QP(get_root_tab(c, lb, false, &tab_b));
+    const u64 *tw1, *twc;
+    QP(get_tw_matrix(c, lb, 4, false, &tw1));
+    QP(get_tw_matrix(c, k, a1, false, &twc));
+    const u32 B = 1u << lb;
+    const size_t smem = ((size_t)tile_pitch(B) * ((1u << a1) / QPZK_NTT_CLUSTER) + (B >> 4)) * 8;
+    const dim3 grid(QPZK_NTT_CLUSTER, ncosets, ncols);
+    if (a1 == 4)
+      k_ntt_cluster<4, 256><<<grid, 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride, pm, tab_b, tw1, twc, k, r, blk0);
+    else
+      k_ntt_cluster<3, 256><<<grid, 256, smem, c->stream>>>(coeffs, src_stride, lde, dst_stride, pm, tab_b, tw1, twc, k, r, blk0);
+    c->launches++;
+    CU(cudaGetLastError());
+    return QPZK_OK;
+  }
   int a = (k + 1) / 2;
   if (a > 8) a = 8;
   int b = k - a;
@@ -490,6 +516,8 @@ static int device_init_once(int device) {
   CU(cudaFuncSetAttribute(k_ntt_small<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
   CU(cudaFuncSetAttribute(k_ntt_small<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
   CU(cudaFuncSetAttribute(k_ntt_small<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_cluster<3, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
+  CU(cudaFuncSetAttribute(k_ntt_cluster<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallSmemBytes));
   CU(cudaFuncSetAttribute(k_ntt_pass_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   CU(cudaFuncSetAttribute(k_ntt_pass_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
   CU(cudaFuncSetAttribute(k_ntt_pass_b_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
