@@ -242,6 +242,39 @@ int qpzk_prove_begin(qpzk_circuit* c, const uint64_t* wires, size_t wires_words,
                      uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
                      const uint64_t* salts_quotient, size_t salt_words, uint32_t flags);
 int qpzk_prove_end(qpzk_circuit* c, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+/* ONE proof over several GPUs (BASELINE configs[4]: an aggregation proof of 2^17-2^18 rows on 8 B200;
+ * SURVEY.md 8(e)). Every rank holds the circuit and the whole witness and calls the same sequence on its own
+ * context with its own range of cap subtrees - whole LDE cosets, as for qpzk_batch_from_values_shard_dev:
+ *
+ *   qpzk_sprove_begin(.., subtree_begin, subtree_end, &s)        commit the wires shard
+ *   loop:  for i = 0, 1, ..: qpzk_sprove_exchange(s, i, ..)       what to exchange now (kind 0: nothing more)
+ *          qpzk_sprove_next(s)                                    next phase
+ *   until qpzk_sprove_phase(s) == 6;  qpzk_sprove_end(s, ..)      wait once, ProofWithPublicInputs bytes
+ *
+ * Phases and what follows them (all stream-ordered on the context's stream, no host synchronisation):
+ *   1 wires commit, 2 Z/partial products + commit, 4 quotient commit: QPZK_EXCHANGE_ALLGATHER of the
+ *     2^cap_height subtree roots, in place on the device cap (each rank owns words [own_begin, own_end));
+ *   3 quotient values on the rank's own points: all-gather of one contiguous block per challenge;
+ *   5 openings, FRI, proof of work, queries (replicated; rows of the sharded oracles are served by their
+ *     owner, zeros elsewhere): QPZK_EXCHANGE_SUM over the ranks (u64 wrap-around add);
+ *   6 the proof pieces are on their way to the host.
+ * The Fiat-Shamir transcript runs replicated on every device, so every rank ends with the same bytes, equal
+ * to the single-GPU proof. With the full range [0, 2^cap_height) nothing is exchanged and the sequence is
+ * qpzk_prove in steps. Needs quotient_degree_factor == 2^rate_bits (every standard configuration). */
+typedef struct qpzk_sprove qpzk_sprove;
+#define QPZK_EXCHANGE_ALLGATHER 1u
+#define QPZK_EXCHANGE_SUM 2u
+int qpzk_sprove_begin(qpzk_circuit* c, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+                      uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+                      const uint64_t* salts_quotient, size_t salt_words, uint32_t flags, uint32_t subtree_begin,
+                      uint32_t subtree_end, qpzk_sprove** out);
+int qpzk_sprove_next(qpzk_sprove* s);
+uint32_t qpzk_sprove_phase(const qpzk_sprove* s);
+int qpzk_sprove_exchange(const qpzk_sprove* s, uint32_t index, uint64_t** dev_ptr, uint64_t* words,
+                         uint64_t* own_begin, uint64_t* own_end, uint32_t* kind);
+/* Waits for the proof, writes the bytes and releases s (also when it fails). */
+int qpzk_sprove_end(qpzk_sprove* s, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* Per-stage hooks for a fork that keeps plonky2's own `prove()` loop and transcript (integration depth (b),
  * INTEGRATION.md): the same device code qpzk_prove runs.
  * qpzk_zs_partial_products = `all_wires_permutation_partial_products` + the running product (qp-plonky2

@@ -448,11 +448,11 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
            CircuitDesc d, const Challenges* __restrict__ chp, const u64* __restrict__ pi_hash, const u64* __restrict__ zh /*[2^qdb]*/,
            const u64* __restrict__ zh_inv, const u64* __restrict__ apw /* alpha powers [2][QPZK_APW_STRIDE] */,
            const u64* __restrict__ l0_den_inv /* [2^lb]: 1 / (n (x_i - 1)) */, RootTab tab /* size degree_bits + qdb */,
-           u64* __restrict__ out) {
+           u64 q_begin, u64 q_end /* positions to evaluate */, u32 out_bitrev, u64* __restrict__ out) {
   const u32 lb = d.degree_bits + d.quotient_degree_bits;  // quotient domain bits
   const u64 lde = (u64)1 << lb;
-  u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;     // position in the bit-reversed quotient domain
-  if (q >= lde) return;
+  u64 q = q_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;  // position in the bit-reversed quotient domain
+  if (q >= q_end) return;
   const u64 i = __brevll(q) >> (64 - lb);                  // natural index on g*<w_lde>
   // position inside the committed LDE (rate_bits >= qdb): natural index i*step -> leaf rev(i*step)
   const u32 full_bits = d.degree_bits + d.rate_bits;
@@ -611,7 +611,7 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
     aa_gate_end(a, filter);
   }
   const u64 zi = zh_inv[i & (((u64)1 << d.quotient_degree_bits) - 1)];
-  for (u32 c = 0; c < nch; c++) out[(u64)c * lde + i] = gl_canon(gl_mul(acc_reduce(a.acc[c]), zi));
+  for (u32 c = 0; c < nch; c++) out[(u64)c * lde + (out_bitrev ? q : i)] = gl_canon(gl_mul(acc_reduce(a.acc[c]), zi));
 }
 
 // data[c][m] *= base^m via a two-level power table (coset (i)fft shift removal).
@@ -837,13 +837,20 @@ k_pow_grind_dev(TranscriptDev* __restrict__ T, u32 min_lz) {
 // H14  batched openings: for each query q: salted row (column-major source) + Merkle path
 // ---------------------------------------------------------------------------------------------
 // grid = nq blocks. out[q] = [width felts][L*4 felts]
+// A multi-GPU shard serves the leaves [leaf0, leaf1) it holds and writes ZEROS for the others: the ranks'
+// outputs are then summed.
 __global__ void k_gather_openings(const u64* __restrict__ lde, u64 row_stride, u64 col_stride, u32 width,
                                   const u64* __restrict__ levels, u32 log_n, u32 cap_height,
-                                  const u64* __restrict__ leaf_idx, u32 shift_bits, u64* __restrict__ out) {
+                                  const u64* __restrict__ leaf_idx, u32 shift_bits, u64 leaf0, u64 leaf1,
+                                  u64* __restrict__ out) {
   const u32 q = blockIdx.x;
   const u64 leaf = leaf_idx[q] >> shift_bits;
   const u32 L = log_n - cap_height;
   u64* o = out + (u64)q * (width + 4 * L);
+  if (leaf < leaf0 || leaf >= leaf1) {
+    for (u32 e = threadIdx.x; e < width + 4 * L; e += blockDim.x) o[e] = 0;
+    return;
+  }
   for (u32 c = threadIdx.x; c < width; c += blockDim.x) o[c] = lde[leaf * row_stride + (u64)c * col_stride];
   const u64 twoN = (u64)2 << log_n;
   for (u32 e = threadIdx.x; e < 4 * L; e += blockDim.x) {

@@ -769,7 +769,8 @@ static int fri_queries(qpzk_fri* F, const u64* xidx_dev, u32 nq, u64* const* ini
   const u32 h = (u32)F->q->common.cap_height, lb = d.degree_bits + d.rate_bits;
   for (int o = 0; o < 4; o++) {
     const qpzk_batch* b = F->oracles[o];
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(b->lde, 1, b->lde_stride, b->width(), b->levels, lb, h, xidx_dev, 0, init_out[o]);
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(b->lde, 1, b->lde_stride, b->width(), b->levels, lb, h, xidx_dev, 0, b->leaf0,
+                                                 b->leaf1, init_out[o]);
     c->launches++;
   }
   u32 sh = 0;
@@ -777,7 +778,8 @@ static int fri_queries(qpzk_fri* F, const u64* xidx_dev, u32 nq, u64* const* ini
     const FriTree& t = F->trees[s];
     sh += t.arity_bits;
     const u32 width = 2u << t.arity_bits;
-    k_gather_openings<<<nq, 128, 0, c->stream>>>(t.leaves, width, 1, width, t.levels, t.log_n, h, xidx_dev, sh, step_out[s]);
+    k_gather_openings<<<nq, 128, 0, c->stream>>>(t.leaves, width, 1, width, t.levels, t.log_n, h, xidx_dev, sh, 0,
+                                                 1ull << t.log_n, step_out[s]);
     c->launches++;
   }
   CU(cudaGetLastError());
@@ -809,41 +811,74 @@ static int compute_zs_partial_products(qpzk_circuit* q, const u64* wires_dev, co
 }
 
 // ---- H9: compute_quotient_polys: vanishing(x)/Z_H(x) on the quotient coset from the three committed
-// oracles, coset IFFT, coefficients [nch][qdf*n] (= nch*qdf chunks of n). apw_dev: alpha powers
-// [nch][QPZK_APW_STRIDE] (k_alpha_powers); chal_dev / pi_hash_dev: device pointers ----
-static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash_dev,
-                                   const Challenges* chal_dev, const u64* apw_dev, DevBuf* qcoeffs) {
+// oracles -> values [nch][2^(k+qdb)]; then coset IFFT -> coefficients [nch][qdf*n] (= nch*qdf chunks of n).
+// apw_dev: alpha powers [nch][QPZK_APW_STRIDE] (k_alpha_powers); chal_dev / pi_hash_dev: device pointers.
+// Whole proof: the kernel writes natural order, ready for the IFFT. One rank of a sharded proof evaluates only
+// the points it holds - leaf positions [leaf0, leaf1) of the batches - and writes BIT-REVERSED order, so that
+// its part is one contiguous block per challenge for the all-gather; quotient_values_to_chunks undoes the
+// permutation. (Sharding needs the quotient domain to be the whole LDE domain: quotient_degree_bits ==
+// rate_bits, as in every standard configuration.) ----
+static int compute_quotient_values(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash_dev,
+                                   const Challenges* chal_dev, const u64* apw_dev, bool sharded, DevBuf* qvals) {
   qpzk_ctx* c = q->ctx;
   const CommonHost& cm = q->common;
   const CircuitDesc& d = q->desc;
   const u32 k = d.degree_bits, r = d.rate_bits, nch = d.num_challenges, qdb = d.quotient_degree_bits;
   const u32 qlb = k + qdb;
   const u64 qlde = 1ull << qlb;
-  DevBuf qvals(c);
-  QP(qvals.alloc((size_t)nch * qlde * 8));
-  QP(qcoeffs->alloc((size_t)nch * qlde * 8));
+  u64 q0 = 0, q1 = qlde;
+  if (sharded) {
+    if (qdb != r) return fail(QPZK_ERR_UNSUPPORTED, "a sharded proof needs quotient_degree_factor == 2^rate_bits");
+    q0 = wires_b->leaf0;
+    q1 = wires_b->leaf1;
+    if (zs_b->leaf0 != q0 || zs_b->leaf1 != q1) return fail(QPZK_ERR_BAD_ARG, "oracle shards differ");
+  }
+  QP(qvals->alloc((size_t)nch * qlde * 8));
   RootTab tab_q;
   QP(get_root_tab(c, (int)qlb, false, &tab_q));
   const u64* zh = q->zh_dev;
   const u64* zh_inv = q->zh_dev + (1u << qdb);
+  const unsigned grid = (unsigned)((q1 - q0 + 127) / 128);
   if (cm.recursion)
-    k_quotient<true><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+    k_quotient<true><<<grid, 128, 0, c->stream>>>(
         q->cs_batch->lde, wires_b->lde, zs_b->lde, q->cs_batch->lde_stride, wires_b->lde_stride, zs_b->lde_stride, r - qdb,
-        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, qvals.p);
+        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, q0, q1, sharded ? 1u : 0u, qvals->p);
   else
-    k_quotient<false><<<(unsigned)((qlde + 127) / 128), 128, 0, c->stream>>>(
+    k_quotient<false><<<grid, 128, 0, c->stream>>>(
         q->cs_batch->lde, wires_b->lde, zs_b->lde, q->cs_batch->lde_stride, wires_b->lde_stride, zs_b->lde_stride, r - qdb,
-        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, qvals.p);
+        q->k_is_dev, d, chal_dev, pi_hash_dev, zh, zh_inv, apw_dev, q->l0_den_inv_dev, tab_q, q0, q1, sharded ? 1u : 0u, qvals->p);
   c->launches++;
   CU(cudaGetLastError());
+  return QPZK_OK;
+}
+static int quotient_values_to_chunks(qpzk_circuit* q, DevBuf* qvals, bool bitrev_in, DevBuf* qcoeffs) {
+  qpzk_ctx* c = q->ctx;
+  const CircuitDesc& d = q->desc;
+  const u32 nch = d.num_challenges, qlb = d.degree_bits + d.quotient_degree_bits;
+  const u64 qlde = 1ull << qlb;
+  QP(qcoeffs->alloc((size_t)nch * qlde * 8));
+  const u64* vals = qvals->p;
+  DevBuf nat(c);
+  if (bitrev_in) {  // gathered shards arrive in leaf (bit-reversed) order
+    QP(nat.alloc((size_t)nch * qlde * 8));
+    k_bitrev_rows<<<dim3((unsigned)((qlde + 255) / 256), nch), 256, 0, c->stream>>>(qvals->p, nat.p, qlde, 0, qlde, (int)qlb, nch);
+    c->launches++;
+    vals = nat.p;
+  }
   // coset IFFT: values on g*<w> -> coefficients; then split into qdf chunks of n (contiguous already)
-  QP(launch_ifft(c, qvals.p, qlde, qcoeffs->p, qlde, nch, (int)qlb));
+  QP(launch_ifft(c, vals, qlde, qcoeffs->p, qlde, nch, (int)qlb));
   RootTab tab_ginv;
   QP(get_pow_tab(c, glh::inv(GL_GEN), (int)qlb, &tab_ginv));
   k_scale_by_powers<<<dim3((unsigned)((qlde + 255) / 256), nch), 256, 0, c->stream>>>(qcoeffs->p, qlde, tab_ginv);
   c->launches++;
   CU(cudaGetLastError());
   return QPZK_OK;
+}
+static int compute_quotient_chunks(qpzk_circuit* q, const qpzk_batch* wires_b, const qpzk_batch* zs_b, const u64* pi_hash_dev,
+                                   const Challenges* chal_dev, const u64* apw_dev, DevBuf* qcoeffs) {
+  DevBuf qvals(q->ctx);
+  QP(compute_quotient_values(q, wires_b, zs_b, pi_hash_dev, chal_dev, apw_dev, false, &qvals));
+  return quotient_values_to_chunks(q, &qvals, false, qcoeffs);
 }
 
 static inline void tr_step(qpzk_ctx* c, TranscriptDev* T, const u64* src, u32 n, u32 src_mode, u64 m, u64* copy, u32 nsq1,
@@ -852,158 +887,242 @@ static inline void tr_step(qpzk_ctx* c, TranscriptDev* T, const u64* src, u32 n,
   c->launches++;
 }
 
-// One proof, enqueued: the order of operations of `prove()` with NO host synchronisation. Everything lands
-// in the circuit's arena; prove_finish waits once and serialises.
+}  // namespace qpzk
+
+// One proof being enqueued, phase by phase: the order of operations of `prove()` with NO host
+// synchronisation; everything lands in the circuit's arena and prove_finish waits once and serialises.
+//
+// A whole proof runs the five phases back to back. One rank of a multi-GPU proof runs the same
+// phases on its range of cap subtrees [sub_begin, sub_end) - whole LDE cosets - and the caller exchanges, on
+// the context's stream between phases,
+//   after wires / zs / quotient_commit : all-gather of the 2^cap_height subtree roots, in place on cap_dev(i)
+//   after quotient_eval                : all-gather of the quotient values, in place on qvals (bit-reversed
+//                                        order: a rank's leaves are one contiguous block per challenge)
+//   after fri                          : sum (all-reduce) of the opened rows of the three sharded oracles - a
+//                                        rank writes zeros for leaves it does not hold.
+// IFFTs, Z / partial products, openings and FRI are replicated: every rank holds every coefficient, runs the
+// identical transcript on its own device and ends with the identical arena.
+struct qpzk_sprove {
+  qpzk_circuit* q = nullptr;
+  u32 sub_begin = 0, sub_end = 0, flags = 0;
+  bool sharded = false;
+  int phase = 0;
+  const u64 *salt_w = nullptr, *salt_z = nullptr, *salt_q = nullptr;
+  const u64* wires_dev = nullptr;
+  DevBuf wires_up, zs_vals, apw, qvals, qcoeffs;
+  std::unique_ptr<qpzk_batch> wires_b, zs_b, q_b;
+  qpzk_fri F;
+  explicit qpzk_sprove(qpzk_circuit* q_)
+      : q(q_), wires_up(q_->ctx), zs_vals(q_->ctx), apw(q_->ctx), qvals(q_->ctx), qcoeffs(q_->ctx) {}
+
+  int commit(const u64* in, bool is_coeffs, u32 ncols, const u64* salts, std::unique_ptr<qpzk_batch>* out) {
+    const CommonHost& cm = q->common;
+    const u32 salt_cols = cm.hiding ? QPZK_SALT_SIZE : 0;
+    const bool on_device = flags & 2;
+    qpzk_batch* raw = nullptr;
+    QP(commit_impl(q->ctx, in, false, is_coeffs, ncols, q->desc.degree_bits, q->desc.rate_bits, (u32)cm.cap_height,
+                   cm.hiding ? salts : nullptr, !on_device, salt_cols, &raw, sub_begin, sub_end, false));
+    out->reset(raw);
+    return QPZK_OK;
+  }
+
+  // ---- transcript start + (2) commit wires ----
+  int phase_wires(const u64* wires_in, const u64* pis, u32 npi) {
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    const u64 n = 1ull << d.degree_bits;
+    TranscriptDev* T = q->transcript();
+    // the transcript up to the first commitment is host work on inputs only: circuit digest | H(public inputs)
+    TranscriptInit init;
+    {
+      host_hash_no_pad(pis, npi, init.pi_hash);
+      HostChallenger ch;
+      ch.observe_n(q->digest, 4);
+      ch.observe_n(init.pi_hash, 4);   // the eighth observation runs the duplex
+      memcpy(init.state, ch.state, sizeof init.state);
+    }
+    q->pis.assign(npi, 0);
+    for (u32 i = 0; i < npi; i++) q->pis[i] = pis[i] >= GL_P ? pis[i] - GL_P : pis[i];
+    q->want_trace = flags & 1;
+    memset(q->stage_ms, 0, sizeof q->stage_ms);
+    k_transcript_init<<<1, 32, 0, c->stream>>>(T, init);
+    c->launches++;
+    CU(cudaEventRecord(q->ev[0], c->stream));
+    wires_dev = wires_in;
+    if (!(flags & 2)) {
+      QP(wires_up.alloc((size_t)d.num_wires * n * 8));
+      CU(cudaMemcpyAsync(wires_up.p, wires_in, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
+      wires_dev = wires_up.p;
+    }
+    QP(commit(wires_dev, false, d.num_wires, salt_w, &wires_b));
+    phase = 1;
+    return QPZK_OK;
+  }
+
+  // ---- observe the wires cap; (4,5) Z + partial products, commit ----
+  int phase_zs() {
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    const ArenaLayout& L = q->lay;
+    const u32 k = d.degree_bits, r = d.rate_bits, h = (u32)q->common.cap_height, nch = d.num_challenges;
+    const u64 n = 1ull << k;
+    TranscriptDev* T = q->transcript();
+    u64* A = q->arena_dev;
+    tr_step(c, T, cap_ptr(wires_b->levels, k + r, h), L.capw, 0, 0, A + L.caps, nch, QPZK_TR_OFF(ch.beta), nch,
+            QPZK_TR_OFF(ch.gamma), 0, 0);
+    CU(cudaEventRecord(q->ev[1], c->stream));  // stage 0: wires commit
+    const u32 nzs = nch * (1 + d.num_partial_products);
+    QP(compute_zs_partial_products(q, wires_dev, &T->ch, &zs_vals));
+    QP(commit(zs_vals.p, false, nzs, salt_z, &zs_b));
+    if (q->want_trace) {
+      q->tr_zs_pp.resize((size_t)nzs * n);
+      CU(cudaMemcpyAsync(q->tr_zs_pp.data(), zs_vals.p, (size_t)nzs * n * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(ctx_wait(c));
+    }
+    phase = 2;
+    return QPZK_OK;
+  }
+
+  // ---- observe the zs cap; (6) quotient values on this rank's points ----
+  int phase_quotient_eval() {
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    const ArenaLayout& L = q->lay;
+    const u32 k = d.degree_bits, r = d.rate_bits, h = (u32)q->common.cap_height, nch = d.num_challenges;
+    TranscriptDev* T = q->transcript();
+    u64* A = q->arena_dev;
+    tr_step(c, T, cap_ptr(zs_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + L.capw, nch, QPZK_TR_OFF(ch.alpha), 0, 0, 0, 0);
+    CU(cudaEventRecord(q->ev[2], c->stream));  // stage 1: Z/pp + commit
+    QP(apw.alloc((size_t)2 * QPZK_APW_STRIDE * 8));
+    k_alpha_powers<<<nch, 256, 0, c->stream>>>(T, QPZK_APW_STRIDE, apw.p);
+    c->launches++;
+    QP(compute_quotient_values(q, wires_b.get(), zs_b.get(), T->pi_hash, &T->ch, apw.p, sharded, &qvals));
+    phase = 3;
+    return QPZK_OK;
+  }
+
+  // ---- (6,7) quotient coefficients and their commitment ----
+  int phase_quotient_commit() {
+    qpzk_ctx* c = q->ctx;
+    const CircuitDesc& d = q->desc;
+    const u32 nch = d.num_challenges, qlb = d.degree_bits + d.quotient_degree_bits;
+    const u64 qlde = 1ull << qlb;
+    QP(quotient_values_to_chunks(q, &qvals, sharded, &qcoeffs));
+    QP(commit(qcoeffs.p, true, nch * d.qdf, salt_q, &q_b));
+    if (q->want_trace) {
+      q->tr_quotient.resize((size_t)nch * qlde);
+      CU(cudaMemcpyAsync(q->tr_quotient.data(), qcoeffs.p, (size_t)nch * qlde * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(ctx_wait(c));
+    }
+    phase = 4;
+    return QPZK_OK;
+  }
+
+  // ---- observe the quotient cap; (8) openings; (9) FRI: combine, commit phase, proof of work, queries ----
+  int phase_fri() {
+    qpzk_ctx* c = q->ctx;
+    const CommonHost& cm = q->common;
+    const CircuitDesc& d = q->desc;
+    const ArenaLayout& L = q->lay;
+    const u32 k = d.degree_bits, r = d.rate_bits, h = (u32)cm.cap_height, nch = d.num_challenges;
+    const u64 n = 1ull << k, N = n << r;
+    TranscriptDev* T = q->transcript();
+    u64* A = q->arena_dev;
+    tr_step(c, T, cap_ptr(q_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + 2 * (size_t)L.capw, 2, QPZK_TR_OFF(zeta), 0, 0, 1,
+            glh::root_of_unity(k));
+    CU(cudaEventRecord(q->ev[3], c->stream));  // stage 2: quotient + commit
+
+    // openings: observe order constants, sigmas, wires, zs, partial_products, quotient (= oracle order), then zs_next
+    const qpzk_batch* oracles[4] = {q->cs_batch, wires_b.get(), zs_b.get(), q_b.get()};
+    const u32 total_polys = L.total_polys;
+    {
+      DevBuf zpow(c), zpow_next(c);
+      QP(zpow.alloc(n * 16));
+      QP(zpow_next.alloc(n * 16));
+      u64* open_dev = A + L.opens;
+      k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta, n, zpow.p);
+      k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta_next, n, zpow_next.p);
+      c->launches += 2;
+      u32 off = 0;
+      for (auto* b : oracles) {
+        k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, open_dev + 2ull * off);
+        off += b->ncols;
+        c->launches++;
+      }
+      k_eval_at_ext<<<nch, 256, 0, c->stream>>>(zs_b->coeffs, n, zpow_next.p, open_dev + 2ull * off);
+      c->launches++;
+      CU(cudaGetLastError());
+      tr_step(c, T, open_dev, 2 * (total_polys + nch), 0, 0, nullptr, 2, QPZK_TR_OFF(fri_alpha), 0, 0, 0, 0);
+    }
+    CU(cudaEventRecord(q->ev[4], c->stream));  // stage 3: openings
+
+    QP(fri_begin(q, oracles, T->zeta, T->zeta_next, T->fri_alpha, &F));
+    if (q->want_trace) {
+      std::vector<u64> soa(2 * n);
+      CU(cudaMemcpyAsync(soa.data(), F.fpoly, n * 16, cudaMemcpyDeviceToHost, c->stream));
+      CU(ctx_wait(c));
+      q->tr_final_poly.resize(2 * n);
+      for (u64 m = 0; m < n; m++) {
+        q->tr_final_poly[2 * m] = soa[m];
+        q->tr_final_poly[2 * m + 1] = soa[n + m];
+      }
+    }
+    CU(cudaEventRecord(q->ev[5], c->stream));  // stage 4: FRI combine
+
+    for (size_t round = 0; round < cm.arities.size(); round++) {
+      const u64* cap_dev = nullptr;
+      QP(fri_commit_round(&F, &cap_dev));
+      tr_step(c, T, cap_dev, L.capw, 0, 0, A + L.fri_caps + round * (size_t)L.capw, 2, QPZK_TR_OFF(fri_beta) + 2 * (u32)round, 0,
+              0, 0, 0);
+      QP(fri_fold(&F, T->fri_beta[round]));
+    }
+    // the polynomial left after the last fold, observed (and stored) as interleaved extension coefficients
+    tr_step(c, T, F.coeffs_cur, 2 * (u32)F.cur_n, 1, F.cur_n, A + L.final_poly, 0, 0, 0, 0, 0, 0);
+    CU(cudaEventRecord(q->ev[6], c->stream));  // stage 5: FRI commit phase
+
+    // proof of work, then the response and the query indices
+    k_pow_grind_dev<<<pow_grid_blocks(cm.pow_bits), 128, 0, c->stream>>>(T, cm.pow_bits);
+    c->launches++;
+    const u32 nq = (u32)cm.num_queries;
+    tr_step(c, T, &T->pow_witness, 1, 0, 0, nullptr, 1 + nq, QPZK_TR_OFF(pow_resp), 0, 0, 2, N - 1);
+    CU(cudaEventRecord(q->ev[7], c->stream));  // stage 6: PoW
+
+    u64* init_out[4];
+    u64* step_out[QPZK_MAX_FRI_ROUNDS];
+    for (int o = 0; o < 4; o++) init_out[o] = A + L.init_open[o];
+    for (size_t s = 0; s < cm.arities.size(); s++) step_out[s] = A + L.step_open[s];
+    QP(fri_queries(&F, T->xidx, nq, init_out, step_out));
+    CU(cudaEventRecord(q->ev[8], c->stream));  // stage 7: queries
+    phase = 5;
+    return QPZK_OK;
+  }
+
+  // ---- the arena goes back to the host ----
+  int phase_download() {
+    qpzk_ctx* c = q->ctx;
+    CU(cudaMemcpyAsync(q->arena_host, q->arena_dev, q->lay.total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(q->done, c->stream));
+    phase = 6;
+    return QPZK_OK;
+  }
+};
+
+namespace qpzk {
+
 static int prove_enqueue(qpzk_circuit* q, const u64* wires_in, const u64* pis, u32 npi, const u64* salt_w,
                          const u64* salt_z, const u64* salt_q, u32 flags) {
-  qpzk_ctx* c = q->ctx;
-  const CommonHost& cm = q->common;
-  const CircuitDesc& d = q->desc;
-  const ArenaLayout& L = q->lay;
-  const u32 k = d.degree_bits, r = d.rate_bits, h = (u32)cm.cap_height, nch = d.num_challenges;
-  const u32 npp = d.num_partial_products, nw = d.num_wires, qdf = d.qdf, qdb = d.quotient_degree_bits;
-  const u64 n = 1ull << k, N = n << r;
-  const u32 salt_cols = cm.hiding ? QPZK_SALT_SIZE : 0;
-  const bool want_trace = flags & 1;
-  const bool on_device = flags & 2;  // wires / salts are device pointers (HBM-resident witness)
-  TranscriptDev* T = q->transcript();
-  u64* A = q->arena_dev;
-
-  // the transcript up to the first commitment is host work on inputs only: circuit digest | H(public inputs)
-  TranscriptInit init;
-  {
-    host_hash_no_pad(pis, npi, init.pi_hash);
-    HostChallenger ch;
-    ch.observe_n(q->digest, 4);
-    ch.observe_n(init.pi_hash, 4);   // the eighth observation runs the duplex
-    memcpy(init.state, ch.state, sizeof init.state);
-  }
-  q->pis.assign(npi, 0);
-  for (u32 i = 0; i < npi; i++) q->pis[i] = pis[i] >= GL_P ? pis[i] - GL_P : pis[i];
-  q->want_trace = want_trace;
-  memset(q->stage_ms, 0, sizeof q->stage_ms);
-  k_transcript_init<<<1, 32, 0, c->stream>>>(T, init);
-  c->launches++;
-
-  // ---- (2) commit wires ----
-  CU(cudaEventRecord(q->ev[0], c->stream));
-  DevBuf wires_up(c);
-  const u64* wires_dev = wires_in;
-  if (!on_device) {
-    QP(wires_up.alloc((size_t)nw * n * 8));
-    CU(cudaMemcpyAsync(wires_up.p, wires_in, (size_t)nw * n * 8, cudaMemcpyHostToDevice, c->stream));
-    wires_dev = wires_up.p;
-  }
-  qpzk_batch* raw = nullptr;
-  QP(commit_impl(c, wires_dev, false, false, nw, k, r, h, cm.hiding ? salt_w : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
-  std::unique_ptr<qpzk_batch> wires_b(raw);
-  tr_step(c, T, cap_ptr(wires_b->levels, k + r, h), L.capw, 0, 0, A + L.caps, nch, QPZK_TR_OFF(ch.beta), nch,
-          QPZK_TR_OFF(ch.gamma), 0, 0);
-  CU(cudaEventRecord(q->ev[1], c->stream));  // stage 0: wires commit
-
-  // ---- (4,5) Z + partial products, commit ----
-  const u32 nzs = nch * (1 + npp);
-  DevBuf zs_vals(c);
-  QP(compute_zs_partial_products(q, wires_dev, &T->ch, &zs_vals));
-  QP(commit_impl(c, zs_vals.p, false, false, nzs, k, r, h, cm.hiding ? salt_z : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
-  std::unique_ptr<qpzk_batch> zs_b(raw);
-  tr_step(c, T, cap_ptr(zs_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + L.capw, nch, QPZK_TR_OFF(ch.alpha), 0, 0, 0, 0);
-  CU(cudaEventRecord(q->ev[2], c->stream));  // stage 1: Z/pp + commit
-  if (want_trace) {
-    q->tr_zs_pp.resize((size_t)nzs * n);
-    CU(cudaMemcpyAsync(q->tr_zs_pp.data(), zs_vals.p, (size_t)nzs * n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(ctx_wait(c));
-  }
-
-  // ---- (6,7) quotient ----
-  const u32 qlb = k + qdb;
-  const u64 qlde = 1ull << qlb;
-  DevBuf qcoeffs(c), apw(c);
-  QP(apw.alloc((size_t)2 * QPZK_APW_STRIDE * 8));
-  k_alpha_powers<<<nch, 256, 0, c->stream>>>(T, QPZK_APW_STRIDE, apw.p);
-  c->launches++;
-  QP(compute_quotient_chunks(q, wires_b.get(), zs_b.get(), T->pi_hash, &T->ch, apw.p, &qcoeffs));
-  QP(commit_impl(c, qcoeffs.p, false, true, nch * qdf, k, r, h, cm.hiding ? salt_q : nullptr, !on_device, salt_cols, &raw, 0, 0, false));
-  std::unique_ptr<qpzk_batch> q_b(raw);
-  tr_step(c, T, cap_ptr(q_b->levels, k + r, h), L.capw, 0, 0, A + L.caps + 2 * (size_t)L.capw, 2, QPZK_TR_OFF(zeta), 0, 0, 1,
-          glh::root_of_unity(k));
-  CU(cudaEventRecord(q->ev[3], c->stream));  // stage 2: quotient + commit
-  if (want_trace) {
-    q->tr_quotient.resize((size_t)nch * qlde);
-    CU(cudaMemcpyAsync(q->tr_quotient.data(), qcoeffs.p, (size_t)nch * qlde * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(ctx_wait(c));
-  }
-
-  // ---- (8) openings: observe order constants, sigmas, wires, zs, partial_products, quotient (= oracle
-  // order), then zs_next ----
-  const qpzk_batch* oracles[4] = {q->cs_batch, wires_b.get(), zs_b.get(), q_b.get()};
-  const u32 total_polys = L.total_polys;
-  DevBuf zpow(c), zpow_next(c);
-  QP(zpow.alloc(n * 16));
-  QP(zpow_next.alloc(n * 16));
-  u64* open_dev = A + L.opens;
-  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta, n, zpow.p);
-  k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(T->zeta_next, n, zpow_next.p);
-  c->launches += 2;
-  {
-    u32 off = 0;
-    for (auto* b : oracles) {
-      k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, open_dev + 2ull * off);
-      off += b->ncols;
-      c->launches++;
-    }
-    k_eval_at_ext<<<nch, 256, 0, c->stream>>>(zs_b->coeffs, n, zpow_next.p, open_dev + 2ull * off);
-    c->launches++;
-  }
-  CU(cudaGetLastError());
-  tr_step(c, T, open_dev, 2 * (total_polys + nch), 0, 0, nullptr, 2, QPZK_TR_OFF(fri_alpha), 0, 0, 0, 0);
-  CU(cudaEventRecord(q->ev[4], c->stream));  // stage 3: openings
-
-  // ---- (9) FRI: batch combine ----
-  qpzk_fri F;
-  QP(fri_begin(q, oracles, T->zeta, T->zeta_next, T->fri_alpha, &F));
-  if (want_trace) {
-    std::vector<u64> soa(2 * n);
-    CU(cudaMemcpyAsync(soa.data(), F.fpoly, n * 16, cudaMemcpyDeviceToHost, c->stream));
-    CU(ctx_wait(c));
-    q->tr_final_poly.resize(2 * n);
-    for (u64 m = 0; m < n; m++) {
-      q->tr_final_poly[2 * m] = soa[m];
-      q->tr_final_poly[2 * m + 1] = soa[n + m];
-    }
-  }
-  CU(cudaEventRecord(q->ev[5], c->stream));  // stage 4: FRI combine
-
-  // ---- (9) FRI: commit phase ----
-  for (size_t round = 0; round < cm.arities.size(); round++) {
-    const u64* cap_dev = nullptr;
-    QP(fri_commit_round(&F, &cap_dev));
-    tr_step(c, T, cap_dev, L.capw, 0, 0, A + L.fri_caps + round * (size_t)L.capw, 2, QPZK_TR_OFF(fri_beta) + 2 * (u32)round, 0, 0,
-            0, 0);
-    QP(fri_fold(&F, T->fri_beta[round]));
-  }
-  // the polynomial left after the last fold, observed (and stored) as interleaved extension coefficients
-  tr_step(c, T, F.coeffs_cur, 2 * (u32)F.cur_n, 1, F.cur_n, A + L.final_poly, 0, 0, 0, 0, 0, 0);
-  CU(cudaEventRecord(q->ev[6], c->stream));  // stage 5: FRI commit phase
-
-  // ---- (9) proof of work, then the response and the query indices ----
-  k_pow_grind_dev<<<pow_grid_blocks(cm.pow_bits), 128, 0, c->stream>>>(T, cm.pow_bits);
-  c->launches++;
-  const u32 nq = (u32)cm.num_queries;
-  tr_step(c, T, &T->pow_witness, 1, 0, 0, nullptr, 1 + nq, QPZK_TR_OFF(pow_resp), 0, 0, 2, N - 1);
-  CU(cudaEventRecord(q->ev[7], c->stream));  // stage 6: PoW
-
-  // ---- (9) query rounds ----
-  u64* init_out[4];
-  u64* step_out[QPZK_MAX_FRI_ROUNDS];
-  for (int o = 0; o < 4; o++) init_out[o] = A + L.init_open[o];
-  for (size_t s = 0; s < cm.arities.size(); s++) step_out[s] = A + L.step_open[s];
-  QP(fri_queries(&F, T->xidx, nq, init_out, step_out));
-  CU(cudaEventRecord(q->ev[8], c->stream));  // stage 7: queries
-
-  CU(cudaMemcpyAsync(q->arena_host, q->arena_dev, L.total * 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaEventRecord(q->done, c->stream));
-  // F, the three batches and every scratch buffer are released here in stream order
+  qpzk_sprove run(q);
+  run.flags = flags;
+  run.salt_w = salt_w;
+  run.salt_z = salt_z;
+  run.salt_q = salt_q;
+  QP(run.phase_wires(wires_in, pis, npi));
+  QP(run.phase_zs());
+  QP(run.phase_quotient_eval());
+  QP(run.phase_quotient_commit());
+  QP(run.phase_fri());
+  QP(run.phase_download());
+  // the FRI state, the three batches and every scratch buffer are released here in stream order
   return QPZK_OK;
 }
 
@@ -1326,6 +1445,121 @@ int qpzk_prove_end(qpzk_circuit* q, uint8_t* proof_out, size_t proof_cap, size_t
     }
     return QPZK_OK;
   });
+}
+
+// ---- one proof over several GPUs: every rank runs the phases on its cap subtrees, the caller exchanges
+// between them (qpzk_sprove in this file; include/qpzk.h) ----
+int qpzk_sprove_begin(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
+                      uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
+                      const uint64_t* salts_quotient, size_t salt_words, uint32_t flags, uint32_t subtree_begin,
+                      uint32_t subtree_end, qpzk_sprove** out) {
+  return guarded([&]() -> int {
+    if (!out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words));
+    const u32 ncap = 1u << q->common.cap_height;
+    if (subtree_begin >= subtree_end || subtree_end > ncap) return fail(QPZK_ERR_BAD_ARG, "bad subtree range");
+    if (flags & 1) return fail(QPZK_ERR_UNSUPPORTED, "the parity trace is not kept for sharded proofs");
+    CU(cudaSetDevice(q->ctx->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (q->in_flight) return fail(QPZK_ERR_BAD_ARG, "a proof is already in flight on this circuit handle");
+    std::unique_ptr<qpzk_sprove> s(new qpzk_sprove(q));
+    s->flags = flags;
+    s->sub_begin = subtree_begin;
+    s->sub_end = subtree_end;
+    s->sharded = subtree_begin != 0 || subtree_end != ncap;
+    s->salt_w = salts_wires;
+    s->salt_z = salts_zs;
+    s->salt_q = salts_quotient;
+    int rc = s->phase_wires(wires, public_inputs, num_public_inputs);
+    if (rc != QPZK_OK) {
+      ctx_wait(q->ctx);
+      return rc;
+    }
+    q->in_flight = true;
+    *out = s.release();
+    return QPZK_OK;
+  });
+}
+
+int qpzk_sprove_next(qpzk_sprove* s) {
+  return guarded([&]() -> int {
+    if (!s) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(s->q->ctx->device));
+    std::lock_guard<std::mutex> lk(s->q->mu);
+    switch (s->phase) {
+      case 1: return s->phase_zs();
+      case 2: return s->phase_quotient_eval();
+      case 3: return s->phase_quotient_commit();
+      case 4: return s->phase_fri();
+      case 5: return s->phase_download();
+      default: return fail(QPZK_ERR_BAD_ARG, "no phase left: call qpzk_sprove_end");
+    }
+  });
+}
+
+uint32_t qpzk_sprove_phase(const qpzk_sprove* s) { return s ? (uint32_t)s->phase : 0; }
+
+int qpzk_sprove_exchange(const qpzk_sprove* s, uint32_t index, uint64_t** dev_ptr, uint64_t* words, uint64_t* own_begin,
+                         uint64_t* own_end, uint32_t* kind) {
+  if (!s || !dev_ptr || !words || !own_begin || !own_end || !kind) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  const qpzk_circuit* q = s->q;
+  const CircuitDesc& d = q->desc;
+  const ArenaLayout& L = q->lay;
+  const u32 lb = d.degree_bits + d.rate_bits, h = (u32)q->common.cap_height;
+  *kind = 0;
+  *dev_ptr = nullptr;
+  *words = *own_begin = *own_end = 0;
+  if (!s->sharded) return QPZK_OK;
+  const qpzk_batch* capb = s->phase == 1 ? s->wires_b.get() : s->phase == 2 ? s->zs_b.get() : s->phase == 4 ? s->q_b.get() : nullptr;
+  if (capb) {
+    if (index > 0) return QPZK_OK;
+    *kind = QPZK_EXCHANGE_ALLGATHER;
+    *dev_ptr = const_cast<u64*>(cap_ptr(capb->levels, lb, h));
+    *words = L.capw;
+    *own_begin = 4ull * s->sub_begin;
+    *own_end = 4ull * s->sub_end;
+  } else if (s->phase == 3) {
+    if (index >= d.num_challenges) return QPZK_OK;
+    const u64 qlde = 1ull << (d.degree_bits + d.quotient_degree_bits);
+    *kind = QPZK_EXCHANGE_ALLGATHER;
+    *dev_ptr = s->qvals.p + (size_t)index * qlde;
+    *words = qlde;
+    *own_begin = s->wires_b->leaf0;
+    *own_end = s->wires_b->leaf1;
+  } else if (s->phase == 5) {
+    if (index > 0) return QPZK_OK;
+    const u64 nq = q->common.num_queries;
+    *kind = QPZK_EXCHANGE_SUM;
+    *dev_ptr = q->arena_dev + L.init_open[1];
+    *words = L.init_open[3] + nq * (L.width[3] + 4ull * L.L0) - L.init_open[1];
+    *own_end = *words;
+  }
+  return QPZK_OK;
+}
+
+int qpzk_sprove_end(qpzk_sprove* s, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!s) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  qpzk_circuit* q = s->q;
+  int rc = guarded([&]() -> int {
+    CU(cudaSetDevice(q->ctx->device));
+    std::lock_guard<std::mutex> lk(q->mu);
+    q->in_flight = false;
+    if (s->phase != 6) {
+      ctx_wait(q->ctx);
+      return fail(QPZK_ERR_BAD_ARG, "proof abandoned before its last phase");
+    }
+    if (!proof_len) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    std::vector<uint8_t> bytes;
+    QP(prove_finish(q, &bytes));
+    *proof_len = bytes.size();
+    if (proof_out) {
+      if (bytes.size() > proof_cap) return fail(QPZK_ERR_BAD_ARG, "proof buffer too small");
+      memcpy(proof_out, bytes.data(), bytes.size());
+    }
+    return QPZK_OK;
+  });
+  delete s;
+  return rc;
 }
 
 int qpzk_prove(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,

@@ -98,6 +98,13 @@ def load_library():
                            ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
         "qpzk_prove_begin": (i, [_vp, _vp, ctypes.c_size_t, _u64p, u32, _vp, _vp, _vp, ctypes.c_size_t, u32]),
         "qpzk_prove_end": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+        "qpzk_sprove_begin": (i, [_vp, _vp, ctypes.c_size_t, _u64p, u32, _vp, _vp, _vp, ctypes.c_size_t, u32, u32, u32,
+                                  ctypes.POINTER(_vp)]),
+        "qpzk_sprove_next": (i, [_vp]),
+        "qpzk_sprove_phase": (u32, [_vp]),
+        "qpzk_sprove_exchange": (i, [_vp, u32, ctypes.POINTER(_vp), ctypes.POINTER(u64), ctypes.POINTER(u64),
+                                     ctypes.POINTER(u64), ctypes.POINTER(u32)]),
+        "qpzk_sprove_end": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
         "qpzk_zs_partial_products": (i, [_vp, _vp, _u64p, _u64p, _u64p]),
         "qpzk_quotient": (i, [_vp, _vp, _vp, _u64p, _u64p, _u64p, _u64p, _u64p]),
         "qpzk_fri_begin": (i, [_vp, _vp, _vp, _vp, _u64p, _u64p, ctypes.POINTER(_vp)]),
@@ -471,6 +478,46 @@ class Fri:
             pass
 
 
+class ShardedProof:
+    """One rank's part of a proof spread over several GPUs (include/qpzk.h, qpzk_sprove_*): run `next()` until
+    `phase == 6`, performing the exchanges `exchanges()` lists between phases (qpzk.dist has the NCCL and the
+    in-process spellings), then `end()`."""
+
+    ALLGATHER, SUM = 1, 2
+
+    def __init__(self, circuit, handle, keep):
+        self.circuit, self._h, self._keep = circuit, handle, keep
+
+    @property
+    def phase(self):
+        return int(load_library().qpzk_sprove_phase(self._h))
+
+    def exchanges(self):
+        """[(kind, device pointer, words, own_begin, own_end)] due after the phase just run."""
+        L = load_library()
+        out = []
+        idx = 0
+        while True:
+            p, w, b, e, k = _vp(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32()
+            _check(L.qpzk_sprove_exchange(self._h, idx, ctypes.byref(p), ctypes.byref(w), ctypes.byref(b), ctypes.byref(e),
+                                          ctypes.byref(k)))
+            if k.value == 0:
+                return out
+            out.append((k.value, p.value, w.value, b.value, e.value))
+            idx += 1
+
+    def next(self):
+        _check(load_library().qpzk_sprove_next(self._h))
+
+    def end(self):
+        buf = self.circuit._buf
+        ln = ctypes.c_size_t(0)
+        h, self._h = self._h, None
+        _check(load_library().qpzk_sprove_end(h, buf, len(buf), ctypes.byref(ln)))
+        self._keep = None
+        return buf.raw[:ln.value]
+
+
 PROVE_STAGES = ("commit_wires", "zs_partial_products_commit", "quotient_commit", "openings", "fri_combine",
                 "fri_commit_phase", "proof_of_work", "queries")
 
@@ -556,6 +603,20 @@ class Circuit:
         _check(load_library().qpzk_prove_end(self._h, self._buf, len(self._buf), ctypes.byref(ln)))
         self._keep = None
         return self._buf.raw[:ln.value]
+
+    def sprove_begin(self, wires, public_inputs, salts, subtree_begin, subtree_end, on_device=False):
+        """First phase of one rank's part of a multi-GPU proof (qpzk_sprove_begin); returns a ShardedProof."""
+        if on_device:
+            pi = _arr(public_inputs)
+            wp, wn, keep = _vp(wires), self.wires_words, [pi]
+            sp = [None, None, None] if salts is None else [_vp(x) for x in salts]
+            sn = self.salt_words if salts is not None else 0
+        else:
+            wp, wn, pi, sp, sn, keep = self._host_args(wires, public_inputs, salts)
+        h = _vp()
+        _check(load_library().qpzk_sprove_begin(self._h, wp, wn, _ptr(pi), pi.size, sp[0], sp[1], sp[2], sn,
+                                                2 if on_device else 0, subtree_begin, subtree_end, ctypes.byref(h)))
+        return ShardedProof(self, h, keep)
 
     def zs_partial_products(self, wires, betas, gammas, nch=2, npp=9):
         """H8 as a stand-alone stage: [nch*(1+npp)][n]."""

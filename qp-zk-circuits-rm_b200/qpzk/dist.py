@@ -62,3 +62,72 @@ def allgather_cap_host(cap_local, subtrees, group=None):
     parts = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return torch.cat(parts, 0).numpy().view(np.uint64)
+
+
+# ---- one proof over several GPUs (include/qpzk.h qpzk_sprove_*, BASELINE configs[4]) ----
+def _stream_ctx(ctx):
+    """torch stream context over the qpzk context's own CUDA stream, so that a collective is ordered after the
+    phase just enqueued and before the next one without any host synchronisation."""
+    import torch
+    return torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device)))
+
+
+def exchange_nccl(proof, group=None):
+    """Perform the exchanges due after the current phase of `proof` (a qpzk.ShardedProof) with NCCL, in place on
+    the device buffers and on the context's stream: all-gather of subtree roots / quotient values, sum of the
+    opened rows."""
+    import torch
+    import torch.distributed as dist
+
+    ctx = proof.circuit.ctx
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    with _stream_ctx(ctx):
+        for kind, ptr, words, b, e in proof.exchanges():
+            t = torch.as_tensor(_DevArray(ptr, words), device=dev)
+            if kind == proof.ALLGATHER:
+                per = words // world
+                if (b, e) != (rank * per, (rank + 1) * per):
+                    raise ValueError("shard does not match the rank's slot in the all-gather")
+                dist.all_gather_into_tensor(t, t[b:e], group=group)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def exchange_local(proofs):
+    """The same exchanges between `proofs` that live in ONE process (one context each, any device): copies through
+    the host. This is how the sharding logic is tested on a single GPU."""
+    lists = [p.exchanges() for p in proofs]
+    for items in zip(*lists):
+        kind, words = items[0][0], items[0][2]
+        bufs = []
+        for p, (_, ptr, w, b, e) in zip(proofs, items):
+            a = np.zeros(w, np.uint64)
+            p.circuit.ctx.d2h(a, ptr)
+            bufs.append(a)
+        if kind == 1:
+            full = np.zeros(words, np.uint64)
+            for a, (_, _, _, b, e) in zip(bufs, items):
+                full[b:e] = a[b:e]
+        else:
+            full = np.zeros(words, np.uint64)
+            with np.errstate(over="ignore"):
+                for a in bufs:
+                    full = full + a
+        for p, (_, ptr, _, _, _) in zip(proofs, items):
+            p.circuit.ctx.h2d(ptr, full)
+
+
+def prove_sharded_nccl(circuit, wires, public_inputs, salts, cap_height, rate_bits, on_device=False, group=None):
+    """One proof over the ranks of `group`: every rank calls this with the same circuit and witness on its own
+    context; returns the proof bytes (identical on every rank, equal to the single-GPU proof)."""
+    import torch.distributed as dist
+
+    b, e = shard_subtrees(dist.get_rank(group), dist.get_world_size(group), cap_height, rate_bits)
+    proof = circuit.sprove_begin(wires, public_inputs, salts, b, e, on_device=on_device)
+    while True:
+        exchange_nccl(proof, group)
+        if proof.phase == 6:
+            break
+        proof.next()
+    return proof.end()

@@ -18,12 +18,15 @@ pub const QPZK_ERR_UNSUPPORTED: c_int = -5;
 pub const QPZK_SALT_SIZE: usize = 4;
 pub const QPZK_CTX_BLOCKING_SYNC: u32 = 1;
 pub const QPZK_CTX_YIELD_SYNC: u32 = 2;
+pub const QPZK_EXCHANGE_ALLGATHER: u32 = 1;
+pub const QPZK_EXCHANGE_SUM: u32 = 2;
 
 #[repr(C)] pub struct qpzk_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_tree { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_circuit { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_fri { _p: [u8; 0] }
+#[repr(C)] pub struct qpzk_sprove { _p: [u8; 0] }
 
 extern "C" {
     pub fn qpzk_ctx_create(device: c_int, flags: u32, out_: *mut *mut qpzk_ctx) -> c_int;
@@ -73,6 +76,11 @@ extern "C" {
     pub fn qpzk_prove(c: *mut qpzk_circuit, wires: *const u64, wires_words: usize, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, salt_words: usize, flags: u32, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn qpzk_prove_begin(c: *mut qpzk_circuit, wires: *const u64, wires_words: usize, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, salt_words: usize, flags: u32) -> c_int;
     pub fn qpzk_prove_end(c: *mut qpzk_circuit, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
+    pub fn qpzk_sprove_begin(c: *mut qpzk_circuit, wires: *const u64, wires_words: usize, public_inputs: *const u64, num_public_inputs: u32, salts_wires: *const u64, salts_zs: *const u64, salts_quotient: *const u64, salt_words: usize, flags: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_sprove) -> c_int;
+    pub fn qpzk_sprove_next(s: *mut qpzk_sprove) -> c_int;
+    pub fn qpzk_sprove_phase(s: *const qpzk_sprove) -> u32;
+    pub fn qpzk_sprove_exchange(s: *const qpzk_sprove, index: u32, dev_ptr: *mut *mut u64, words: *mut u64, own_begin: *mut u64, own_end: *mut u64, kind: *mut u32) -> c_int;
+    pub fn qpzk_sprove_end(s: *mut qpzk_sprove, proof_out: *mut u8, proof_cap: usize, proof_len: *mut usize) -> c_int;
     pub fn qpzk_zs_partial_products(c: *mut qpzk_circuit, wires: *const u64, betas: *const u64, gammas: *const u64, out_: *mut u64) -> c_int;
     pub fn qpzk_quotient(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, pi_hash: *const u64, betas: *const u64, gammas: *const u64, alphas: *const u64, out_chunks: *mut u64) -> c_int;
     pub fn qpzk_fri_begin(c: *mut qpzk_circuit, wires_batch: *const qpzk_batch, zs_batch: *const qpzk_batch, quotient_batch: *const qpzk_batch, zeta: *const u64, alpha: *const u64, out_: *mut *mut qpzk_fri) -> c_int;

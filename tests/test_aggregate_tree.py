@@ -1,0 +1,86 @@
+"""The aggregator's tree schedule (/root/reference/wormhole/aggregator/src/circuits/tree.rs:55-103) dealt over
+ranks: level structure, dependency order, and the world_size-2 gloo run in which each rank proves only its own
+nodes and the per-level all-gather hands the children to whichever rank proves the parent. CPU only: the "node
+proof" here is a hash of the children, so the result is checkable against a single-process run."""
+import hashlib
+import os
+import socket
+
+import pytest
+
+from qpzk import aggregate as agg
+
+
+def _node(level, index, children):
+    h = hashlib.sha256(b"%d:%d" % (level, index))
+    for c in children:
+        h.update(c)
+    return h.digest() * 4          # fixed-length "proof"
+
+
+def _run(rank, world, gather):
+    order = []
+
+    def begin(level, index, children, slot):
+        order.append((level, index, slot))
+        return (level, index, list(children))
+
+    root, levels = agg.aggregate_tree([bytes([i]) * 128 for i in range(8)], 2, begin, lambda h: _node(*h), rank, world, gather)
+    return root, levels, order
+
+
+def test_levels_match_the_reference_defaults():
+    assert agg.tree_levels(8, 2) == [4, 2, 1]           # tree.rs:17-20 defaults: 7 node proofs
+    assert agg.tree_levels(16, 2) == [8, 4, 2, 1]
+    assert agg.tree_levels(8, 8) == [1]                 # a flat 8-ary node
+    assert agg.tree_levels(9, 4) == [3, 1]
+    assert agg.tree_levels(1, 2) == []
+    with pytest.raises(ValueError):
+        agg.tree_levels(8, 1)
+
+
+def test_single_rank_order_and_root():
+    root, levels, order = _run(0, 1, None)
+    assert [len(l) for l in levels] == [4, 2, 1]
+    assert [o[0] for o in order] == [0, 0, 0, 0, 1, 1, 2]        # a level only after the one below it
+    want1 = [_node(0, i, [bytes([2 * i]) * 128, bytes([2 * i + 1]) * 128]) for i in range(4)]
+    assert levels[0] == want1
+    assert root == _node(2, 0, [_node(1, 0, want1[:2]), _node(1, 1, want1[2:])])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        root, levels, order = _run(rank, world, agg.torch_all_gather(128))
+        q.put((rank, root, [o[:2] for o in order]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_tree():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(30)
+    want_root, _, _ = _run(0, 1, None)
+    assert res[0][1] == want_root and res[1][1] == want_root
+    # nodes are dealt round-robin: rank 0 proves the even nodes of every level (and the root), rank 1 the odd ones
+    assert res[0][2] == [(0, 0), (0, 2), (1, 0), (2, 0)]
+    assert res[1][2] == [(0, 1), (0, 3), (1, 1)]
