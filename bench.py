@@ -309,6 +309,110 @@ def sharded_commit_bench(ctx, qpzk, torch, dist, rank, world, steps, warmup):
             "cap_equals_unsharded": ok}
 
 
+def sharded_proof_bench(ctx, qpzk, torch, dist, rank, world, k, reps=3):
+    """BASELINE configs[4] on N GPUs: ONE recursion-shaped (aggregation) proof of 2^k rows, every rank working on
+    its cap subtrees (qpzk_sprove_*, NCCL exchanges on the context's stream), witness resident in HBM on every
+    rank. Device time from the first enqueue to the proof bytes, max over ranks. Rank 0 also proves it alone: the
+    bytes must be equal."""
+    from qpzk import dist as qdist
+    from qpzk import synth
+    bc = synth.build_recursion(k, zk=True, seed=10, provider=synth.GpuProvider(ctx))
+    circ = qpzk.Circuit(ctx, bc["common"], bc["digest"], bc["constants_sigmas"])
+    dw = ctx.dev_alloc(bc["wires"].nbytes)
+    ctx.h2d(dw, bc["wires"])
+    ds = []
+    for sa in bc["salts"]:
+        p = ctx.dev_alloc(sa.nbytes)
+        ctx.h2d(p, sa)
+        ds.append(p)
+    times, proof = [], None
+    for i in range(reps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = qdist.prove_sharded_nccl(circ, dw, bc["public_inputs"], ds, CAP_HEIGHT, RATE_BITS, on_device=True)
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if i:
+            times.append(float(ms.item()))
+    stages = circ.stage_ms()
+    out = None
+    if rank == 0:
+        lat = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            alone = circ.prove_dev(dw, bc["public_inputs"], ds)
+            if i:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        if alone != proof:
+            raise SystemExit("bench: %d-GPU sharded proof bytes != single-GPU proof bytes" % world)
+        from oracle import oracle as orc  # the checker: the restated plonky2 verifier
+        rc, _ = orc.verify(bc["common"], circ.verifier_only_bytes(), proof)
+        if rc != 0:
+            raise SystemExit("bench: sharded proof rejected by the restated verifier (rc %d)" % rc)
+        out = {"workload": "one aggregation-shaped proof: 2^%d rows x 135 wires, 14-gate recursion set, ZK, witness "
+                           "resident in HBM on every rank" % k,
+               "n_gpus": world, "latency_ms_median": float(np.median(times)), "latency_ms_min": float(np.min(times)),
+               "single_gpu_latency_ms": float(np.median(lat)), "speedup": float(np.median(lat) / np.median(times)),
+               "bytes_equal_single_gpu_proof": True, "verifier_accepts": True, "proof_bytes": len(proof),
+               "stage_ms_rank0": stages,
+               "exchange": "NCCL on the context's stream: 3 all-gathers of 16 x 32 B subtree roots, all-gather of the "
+                           "quotient values (2 x 2^%d x 8 B), all-reduce of 28 x 3 opened rows" % (k + 3)}
+    dist.barrier()
+    for p in [dw] + ds:
+        ctx.dev_free(p)
+    circ.free()
+    return out
+
+
+def tree_schedule_bench(ctxs, qpzk, torch, dist, rank, world, reps=3):
+    """The reference aggregator's default tree (8 leaves, branching factor 2: 4 + 2 + 1 dependent node proofs,
+    /root/reference/wormhole/aggregator/src/circuits/tree.rs:17-20,55-103) dealt over the ranks: every node is a
+    2^13-row recursion-shaped proof, the nodes of a level run concurrently (one per GPU, or per stream on one
+    GPU), the node proofs are all-gathered after each level. Wall time from the leaf proofs to the root proof,
+    max over ranks."""
+    from qpzk import aggregate as agg
+    from qpzk import synth
+    ak = 13
+    ac = synth.build_recursion(ak, zk=True, seed=9, provider=synth.GpuProvider(ctxs[0]))
+    slots = min(len(ctxs), 4)
+    circs = [qpzk.Circuit(c, ac["common"], ac["digest"], ac["constants_sigmas"]) for c in ctxs[:slots]]
+    pw = qpzk.PinnedBuffer(ac["wires"].shape)
+    pw.array[...] = ac["wires"]
+    ps = [qpzk.PinnedBuffer(sa.shape) for sa in ac["salts"]]
+    for a, sa in zip(ps, ac["salts"]):
+        a.array[...] = sa
+    node_len = len(circs[0].prove(pw.array, ac["public_inputs"], [a.array for a in ps]))
+    leaves = [bytes([i]) * node_len for i in range(8)]
+
+    def begin(level, index, children, slot):
+        # building the node circuit and its witness from `children` is host work outside this backend
+        circs[slot].prove_begin(pw.array, ac["public_inputs"], [a.array for a in ps])
+        return slot
+
+    gather = agg.torch_all_gather(node_len, device=torch.device("cuda", ctxs[0].device)) if world > 1 else None
+    times = []
+    for i in range(reps + 1):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        root, levels = agg.aggregate_tree(leaves, 2, begin, lambda slot: circs[slot].prove_end(), rank, world, gather)
+        ms = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        if i:
+            times.append(ms)
+    for q in circs:
+        q.free()
+    return {"workload": "aggregation tree of 8 leaf proofs, branching factor 2: 4 + 2 + 1 dependent node proofs of 2^%d "
+                        "rows (recursion gate set, ZK, host buffers), node proofs all-gathered per level" % ak,
+            "n_gpus": world, "latency_ms_median": float(np.median(times)), "latency_ms_min": float(np.min(times)),
+            "node_proofs": 7, "node_proof_bytes": node_len, "root_proof_bytes": len(root)}
+
+
 def run_gpu(args, rank, local_rank, world):
     import torch
     import qpzk
@@ -427,6 +531,33 @@ def run_gpu(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     proof = results[0]
 
+    # ---- everything that needs all ranks comes first; then ranks > 0 are released (they used to spin in a
+    # barrier at ~60 % "GPU busy" while rank 0 ran its single-GPU extras) ----
+    sharded = sharded_proof = None
+    tree = None
+    if dist is not None:
+        if (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
+            sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
+            if not args.no_aggregator:
+                sharded_proof = sharded_proof_bench(ctx0, qpzk, torch, dist, rank, world, args.shard_k)
+        if not args.no_aggregator:
+            tree = tree_schedule_bench(ctxs, qpzk, torch, dist, rank, world)
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
+        if rank != 0:
+            for c, d, ds in zip(ctxs, dev_w, dev_s):
+                c.dev_free(d)
+                for p in ds:
+                    c.dev_free(p)
+            for q in circuits:
+                q.free()
+            for c in ctxs:
+                c.close()
+            return
+    elif not args.no_aggregator:
+        tree = tree_schedule_bench(ctxs, qpzk, torch, None, 0, 1)
+
     # single-proof latency and stage breakdown (one stream, nothing else in flight)
     t0 = time.perf_counter()
     circuits[0].prove_dev(dev_w[0], circ["public_inputs"], dev_s[0])
@@ -497,26 +628,27 @@ def run_gpu(args, rank, local_rank, world):
         # a flat 16-ary aggregation node is ~2^16 rows, BASELINE configs[4] quotes ~2^17-2^18:
         # single-proof latency at 2^16, 2^17 and 2^18 rows, each proof accepted by the restated verifier
         from oracle import oracle as orc  # the checker: the restated plonky2 verifier
-        for bk in (16, 17, 18):
+        for bk in ((16, 17, 18) if world == 1 else ()):   # at N > 1 the 2^18-row proof is the sharded one above
             bc = synth.build_recursion(bk, zk=True, seed=10, provider=synth.GpuProvider(ctx0))
             bcirc = qpzk.Circuit(ctx0, bc["common"], bc["digest"], bc["constants_sigmas"])
-            blat = []
-            for i in range(4):
+            blat, bst = [], []
+            for i in range(5):     # first run warms the memory pool up to this proof size; the other four are reported
                 t0 = time.perf_counter()
                 bproof = bcirc.prove(bc["wires"], bc["public_inputs"], bc["salts"])
                 if i:
                     blat.append((time.perf_counter() - t0) * 1e3)
+                    bst.append(bcirc.stage_ms())
             rc, _ = orc.verify(bc["common"], bcirc.verifier_only_bytes(), bproof)
             if rc != 0:
                 raise SystemExit("2^%d-row recursion-shaped proof rejected by the restated verifier (rc %d)" % (bk, rc))
-            aggregator["flat_node_2^%d_rows" % bk] = {"latency_ms_median": float(np.median(blat)), "proof_bytes": len(bproof),
-                                                      "verifier_accepts": True, "stage_ms": bcirc.stage_ms()}
+            aggregator["flat_node_2^%d_rows" % bk] = {
+                "latency_ms_median": float(np.median(blat)), "latency_ms_all": [float(x) for x in blat],
+                "proof_bytes": len(bproof), "verifier_accepts": True,
+                "stage_ms_median": {kk: float(np.median([st[kk] for st in bst])) for kk in bst[0]},
+                "stage_ms_max": {kk: float(np.max([st[kk] for st in bst])) for kk in bst[0]}}
             bcirc.free()
             del bc
 
-    sharded = None
-    if dist is not None and (1 << min(CAP_HEIGHT, RATE_BITS)) % world == 0:
-        sharded = sharded_commit_bench(ctx0, qpzk, torch, dist, rank, world, 5, 3)
     micro = commit_microbench(ctx0, qpzk, 5, 3, rank) if rank == 0 else None
     sweep = commit_sweep(ctx0, qpzk) if rank == 0 else None
     imad_wide = ctx0.measure_imad_peak(1)
@@ -597,14 +729,19 @@ def run_gpu(args, rank, local_rank, world):
             "clocks": clocks,
         }
         line["commit_microbench"]["ms_at_2^k_rows"] = sweep
-        if sharded is not None:
-            line["commit_microbench"]["sharded"] = sharded
         if voting is not None:
             line["voting_single_proof"] = voting
         if aggregator is not None:
             line["aggregator_node_proof"] = aggregator
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        # the multi-GPU results go LAST so that a tail of the line keeps them
+        if tree is not None:
+            line["aggregation_tree"] = tree
+        if sharded is not None:
+            line["commit_microbench_sharded"] = sharded
+        if sharded_proof is not None:
+            line["aggregation_proof_sharded"] = sharded_proof
         print(json.dumps(line), flush=True)
 
     for c, d, ds in zip(ctxs, dev_w, dev_s):
@@ -615,8 +752,6 @@ def run_gpu(args, rank, local_rank, world):
         q.free()
     for c in ctxs:
         c.close()
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 def main():
@@ -634,7 +769,8 @@ def main():
                     help="how a proving thread waits for its stream: spin on a core, poll + sched_yield "
                          "(QPZK_CTX_YIELD_SYNC) or sleep on a blocking-sync event (QPZK_CTX_BLOCKING_SYNC); "
                          "auto = spin while streams x ranks fit the host cores, else yield")
-    ap.add_argument("--no-aggregator", action="store_true", help="skip the aggregation-node proof (configs[4])")
+    ap.add_argument("--no-aggregator", action="store_true", help="skip the aggregation proofs (configs[4])")
+    ap.add_argument("--shard-k", type=int, default=18, help="log2 rows of the aggregation proof sharded over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -647,7 +783,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--streams", str(args.streams), "--sync", args.sync, "--host-threads", str(args.host_threads)]
+               "--streams", str(args.streams), "--sync", args.sync, "--host-threads", str(args.host_threads),
+               "--shard-k", str(args.shard_k)]
         cmd += ["--no-cpu"] * args.no_cpu + ["--no-aggregator"] * args.no_aggregator
         sys.exit(subprocess.call(cmd))
     run_gpu(args, rank, local_rank, world)
