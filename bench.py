@@ -198,6 +198,12 @@ def run_reference(args, rank, world):
     rc, _ = orc.verify(circ["common"], oc.verifier_only_bytes(), proof)
     if rc != 0:
         raise SystemExit("reference arm: oracle proof not accepted by the oracle verifier")
+    # the port's hashing rate, for scale: MerkleTree::new over 2^15 rows of 139 elements (19 permutations per row)
+    rng = np.random.default_rng(1)
+    lv = rng.integers(0, 0xFFFFFFFF00000001, size=(1 << 15, 139), dtype=np.uint64)
+    t0 = time.perf_counter()
+    orc.merkle_new(lv, 4, threads=threads)
+    mperm = (1 << 15) * 19 / (time.perf_counter() - t0) / 1e6
     frac = float(1 << k) / float(1 << PROOF_K)
     dt = dt / frac          # scaled to the full 2^14-row proof (prover work is ~linear in rows)
     value = 1.0 / dt
@@ -208,10 +214,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of qp-plonky2's prove() (the Rust reference "
-                   "cannot be built here: no cargo, crates un-vendored); scalar C++, %d host threads, no AVX" % threads},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": sample},
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port of qp-plonky2's prove() (the Rust reference cannot be "
+                   "built here: no cargo, crates un-vendored); C++, %d host threads, AVX-512 where the CPU has it (8-way "
+                   "Poseidon for Merkle hashing and proof of work, vectorised NTT butterflies), scalar otherwise" % threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "avx512": bool(orc.have_avx512()), "poseidon_Mperm_per_s": mperm},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -662,9 +669,9 @@ def run_gpu(args, rank, local_rank, world):
         t0 = time.perf_counter()
         want = oc.prove(circ["wires"], circ["public_inputs"], circ["salts"])
         dt = time.perf_counter() - t0
-        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "one full proof of the same circuit and witness with the oracle port (scalar C++, %d threads): "
-                         "%.2f s" % (threads, dt)}
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port", "avx512": bool(orc.have_avx512()),
+               "sample": "one full proof of the same circuit and witness with the oracle port (C++, %d threads, AVX-512 "
+                         "Poseidon / NTT where available): %.2f s" % (threads, dt)}
         # parity gate inside the bench: the timed GPU path must emit the very bytes the oracle does,
         # and the restated verifier must accept them
         if proof != want:

@@ -325,4 +325,5 @@ void orc_trace_final_poly(void* h, u64* out) {  // [n][2]
   }
 }
 
+int orc_have_avx512(void) { return orc::have_avx512() ? 1 : 0; }
 }  // extern "C"

@@ -76,9 +76,13 @@ static inline unsigned log2_strict(size_t n) {
   return k;
 }
 static inline size_t bitrev(size_t x, unsigned bits) {
-  size_t r = 0;
-  for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
-  return r;
+  if (bits == 0) return 0;
+  u64 v = (u64)x;
+  v = ((v >> 1) & 0x5555555555555555ULL) | ((v & 0x5555555555555555ULL) << 1);
+  v = ((v >> 2) & 0x3333333333333333ULL) | ((v & 0x3333333333333333ULL) << 2);
+  v = ((v >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((v & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  v = __builtin_bswap64(v);
+  return (size_t)(v >> (64 - bits));
 }
 
 // Quadratic extension, W = 7.

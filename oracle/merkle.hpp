@@ -14,6 +14,7 @@
 
 #include "ntt.hpp"
 #include "poseidon.hpp"
+#include "poseidon_avx512.hpp"
 
 namespace orc {
 
@@ -42,6 +43,27 @@ static inline Hash fill_subtree(Hash* buf, size_t buflen, const u64* leaves, siz
 
 static inline void parallel_for(size_t n, unsigned threads, const std::function<void(size_t)>& f);
 
+// The same subtree level by level, eight permutations per call (poseidon_avx512.hpp): leaf digests, then each
+// level's nodes, every digest stored where the recursive rule above puts it - sibling pair q of level i at
+// 2 * ((q << (i + 1)) + (1 << i) - 1) + {0, 1}. Used when the CPU has AVX-512 (run-time check); results are
+// identical to fill_subtree.
+static inline Hash fill_subtree_x8(Hash* buf, size_t buflen, const u64* leaves, size_t nleaves, size_t leaf_len) {
+  if (nleaves < 8 || !have_avx512()) return fill_subtree(buf, buflen, leaves, nleaves, leaf_len);
+  std::vector<Hash> cur(nleaves), next;
+  for (size_t j = 0; j < nleaves; j += 8) hash_or_noop_x8(leaves + j * leaf_len, leaf_len, leaf_len, &cur[j]);
+  for (unsigned i = 0; cur.size() > 1; i++) {
+    const size_t count = cur.size();
+    for (size_t j = 0; j < count; j++) buf[2 * (((j >> 1) << (i + 1)) + ((size_t)1 << i) - 1) + (j & 1)] = cur[j];
+    next.resize(count / 2);
+    size_t j = 0;
+    for (; j + 8 <= count / 2; j += 8) two_to_one_x8(&cur[2 * j], &next[j]);
+    for (; j < count / 2; j++) next[j] = two_to_one(cur[2 * j], cur[2 * j + 1]);
+    cur.swap(next);
+  }
+  (void)buflen;
+  return cur[0];
+}
+
 static inline MerkleTree merkle_new(std::vector<u64> leaves, size_t nleaves, size_t leaf_len,
                                     unsigned cap_height, unsigned threads = 1) {
   MerkleTree t;
@@ -61,8 +83,8 @@ static inline MerkleTree merkle_new(std::vector<u64> leaves, size_t nleaves, siz
   size_t parts = (size_t)1 << split;
   if (split == 0) {
     parallel_for(ncap, threads, [&](size_t s) {
-      t.cap[s] = fill_subtree(t.digests.data() + s * sub_digests, sub_digests,
-                              t.leaves.data() + s * sub_leaves * leaf_len, sub_leaves, leaf_len);
+      t.cap[s] = fill_subtree_x8(t.digests.data() + s * sub_digests, sub_digests,
+                                 t.leaves.data() + s * sub_leaves * leaf_len, sub_leaves, leaf_len);
     });
     return t;
   }
@@ -86,7 +108,7 @@ static inline MerkleTree merkle_new(std::vector<u64> leaves, size_t nleaves, siz
     plan(s, t.digests.data() + s * sub_digests, sub_digests,
          t.leaves.data() + s * sub_leaves * leaf_len, sub_leaves, 0);
   parallel_for(jobs.size(), threads, [&](size_t j) {
-    jobs[j].out = fill_subtree(jobs[j].buf, jobs[j].buflen, jobs[j].lv, jobs[j].nl, leaf_len);
+    jobs[j].out = fill_subtree_x8(jobs[j].buf, jobs[j].buflen, jobs[j].lv, jobs[j].nl, leaf_len);
   });
   std::function<Hash(size_t, size_t&, Hash*, size_t, unsigned)> finish =
       [&](size_t s, size_t& next, Hash* buf, size_t buflen, unsigned depth) -> Hash {
@@ -179,8 +201,9 @@ static inline PolyBatch batch_from_coeffs(std::vector<std::vector<u64>> coeffs, 
     std::vector<u64> v = coset_fft(lde(coeffs[c], rate_bits), GEN);
     for (size_t i = 0; i < N; i++) leaves[bitrev(i, lb) * width + c] = v[i];
   });
-  for (size_t s = 0; s < b.salt_cols; s++)
+  parallel_for(b.salt_cols, threads, [&](size_t s) {
     for (size_t i = 0; i < N; i++) leaves[bitrev(i, lb) * width + b.ncols + s] = salts[s * N + i];
+  });
   b.coeffs = std::move(coeffs);
   b.tree = merkle_new(std::move(leaves), N, width, cap_height, threads);
   return b;

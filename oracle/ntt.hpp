@@ -9,11 +9,43 @@
 // /root/reference/wormhole/circuit/src/circuit.rs:98-108 (build). Plain iterative radix-2; a naive
 // O(n^2) DFT is kept as an independent cross-check for small n.
 #pragma once
+#include <mutex>
 #include <vector>
 
 #include "gl.hpp"
+#include "poseidon_avx512.hpp"
 
 namespace orc {
+
+// Twiddles of one butterfly stage, w_m^j for j < m/2 (m = 2^s): they depend on the stage only, so they are
+// built once per process.
+static inline const std::vector<u64>& stage_twiddles(unsigned s) {
+  static std::vector<u64> tabs[40];
+  static std::once_flag once[40];
+  std::call_once(once[s], [s] {
+    size_t half = (size_t)1 << (s - 1);
+    std::vector<u64> tw(half);
+    u64 wm = root_of_unity(s);
+    tw[0] = 1;
+    for (size_t j = 1; j < half; j++) tw[j] = mul(tw[j - 1], wm);
+    tabs[s] = std::move(tw);
+  });
+  return tabs[s];
+}
+
+// One stage over the whole array, eight butterflies per instruction (poseidon_avx512.hpp arithmetic); half >= 8.
+ORC_AVX512_FN static void fft_stage_x8(u64* a, size_t n, size_t half, const u64* tw) {
+  const v8 p = v8_set1(P);
+  for (size_t base = 0; base < n; base += 2 * half)
+    for (size_t j = 0; j < half; j += 8) {
+      v8 u = _mm512_loadu_si512((const void*)(a + base + j));
+      v8 t = v8_mul(_mm512_loadu_si512((const void*)(tw + j)), _mm512_loadu_si512((const void*)(a + base + j + half)));
+      _mm512_storeu_si512((void*)(a + base + j), v8_add(u, t));
+      v8 d = _mm512_sub_epi64(u, t);
+      __mmask8 borrow = _mm512_cmplt_epu64_mask(u, t);
+      _mm512_storeu_si512((void*)(a + base + j + half), _mm512_mask_add_epi64(d, borrow, d, p));
+    }
+}
 
 // In-place forward DFT: out[i] = sum_j a[j] * w^(i*j), natural order in and out.
 static inline void fft_inplace(std::vector<u64>& a) {
@@ -24,12 +56,14 @@ static inline void fft_inplace(std::vector<u64>& a) {
     size_t j = bitrev(i, k);
     if (i < j) std::swap(a[i], a[j]);
   }
+  const bool vec = have_avx512();
   for (unsigned s = 1; s <= k; s++) {
     size_t m = (size_t)1 << s, half = m >> 1;
-    u64 wm = root_of_unity(s);
-    std::vector<u64> tw(half);
-    tw[0] = 1;
-    for (size_t j = 1; j < half; j++) tw[j] = mul(tw[j - 1], wm);
+    const std::vector<u64>& tw = stage_twiddles(s);
+    if (vec && half >= 8) {
+      fft_stage_x8(a.data(), n, half, tw.data());
+      continue;
+    }
     for (size_t base = 0; base < n; base += m)
       for (size_t j = 0; j < half; j++) {
         u64 t = mul(tw[j], a[base + j + half]);

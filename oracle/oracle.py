@@ -138,6 +138,11 @@ def naive_coset_eval(coeffs, npoints, shift):
     return out
 
 
+def have_avx512():
+    """True when the batched AVX-512 Poseidon / NTT paths are in use on this CPU."""
+    return bool(lib().orc_have_avx512())
+
+
 def merkle_new(leaves, cap_height, threads=1):
     """leaves: [nleaves][leaf_len] row-major. Returns (digests[.,4] plonky2 layout, cap[2^h,4])."""
     lv = _a(leaves)

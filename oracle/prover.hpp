@@ -12,6 +12,9 @@
 // Everything this prover emits is accepted or rejected by verifier.hpp, which is itself pinned by
 // the reference's shipped proof.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "challenger.hpp"
@@ -58,7 +61,7 @@ static inline std::vector<u64> batch_inverse(const std::vector<u64>& x) {
 // H8: [Z_0.., pp_0[0..npp), pp_1[..) ...] as value vectors on H (the zs_partial_products batch).
 static inline std::vector<std::vector<u64>> compute_zs_partial_products(
     const CircuitProverData& d, const std::vector<std::vector<u64>>& wires,
-    const std::vector<u64>& betas, const std::vector<u64>& gammas) {
+    const std::vector<u64>& betas, const std::vector<u64>& gammas, unsigned threads = 1) {
   const CommonData& c = d.common;
   size_t n = (size_t)1 << c.degree_bits, nr = c.num_routed_wires, npp = c.num_partial_products;
   size_t nch = c.num_challenges, chunk = c.quotient_degree_factor;
@@ -66,26 +69,39 @@ static inline std::vector<std::vector<u64>> compute_zs_partial_products(
   if (nchunks != npp + 1) throw std::runtime_error("partial product count mismatch");
   std::vector<std::vector<u64>> zs(nch, std::vector<u64>(n)), pps(nch * npp, std::vector<u64>(n));
   u64 w = root_of_unity(c.degree_bits);
+  // pass 1 (rows in parallel, as plonky2's par_iter): the chunk quotients of every row; pass 2: the running
+  // product over the rows, which is sequential
+  std::vector<std::vector<u64>> quot(nch * nchunks, std::vector<u64>(n));
+  const size_t rows_per_task = 256, ntasks = (n + rows_per_task - 1) / rows_per_task;
   for (size_t ch = 0; ch < nch; ch++) {
-    u64 z = 1, x = 1;
-    for (size_t i = 0; i < n; i++) {
+    parallel_for(ntasks, threads, [&](size_t task) {
+      size_t i0 = task * rows_per_task, i1 = i0 + rows_per_task < n ? i0 + rows_per_task : n;
+      u64 x = pow(w, i0);
       std::vector<u64> num(nr), den(nr);
-      for (size_t j = 0; j < nr; j++) {
-        u64 wv = wires[j][i];
-        num[j] = add(add(wv, mul(betas[ch], mul(c.k_is[j], x))), gammas[ch]);
-        den[j] = add(add(wv, mul(betas[ch], d.constants_sigmas[c.num_constants + j][i])), gammas[ch]);
+      for (size_t i = i0; i < i1; i++) {
+        for (size_t j = 0; j < nr; j++) {
+          u64 wv = wires[j][i];
+          num[j] = add(add(wv, mul(betas[ch], mul(c.k_is[j], x))), gammas[ch]);
+          den[j] = add(add(wv, mul(betas[ch], d.constants_sigmas[c.num_constants + j][i])), gammas[ch]);
+        }
+        std::vector<u64> di = batch_inverse(den);
+        for (size_t k = 0; k < nchunks; k++) {
+          u64 prod = 1;
+          for (size_t j = k * chunk; j < (k + 1) * chunk && j < nr; j++) prod = mul(prod, mul(num[j], di[j]));
+          quot[ch * nchunks + k][i] = prod;
+        }
+        x = mul(x, w);
       }
-      std::vector<u64> di = batch_inverse(den);
+    });
+    u64 z = 1;
+    for (size_t i = 0; i < n; i++) {
       zs[ch][i] = z;
       u64 acc = z;
       for (size_t k = 0; k < nchunks; k++) {
-        u64 prod = 1;
-        for (size_t j = k * chunk; j < (k + 1) * chunk && j < nr; j++) prod = mul(prod, mul(num[j], di[j]));
-        acc = mul(acc, prod);
+        acc = mul(acc, quot[ch * nchunks + k][i]);
         if (k < npp) pps[ch * npp + k][i] = acc;
       }
       z = acc;  // Z(g x)
-      x = mul(x, w);
     }
   }
   std::vector<std::vector<u64>> out;
@@ -204,6 +220,18 @@ struct ProveTrace {  // intermediate values exposed for stage-by-stage parity te
   std::vector<E2> final_poly_coeffs_initial;  // the polynomial that enters FRI (n coefficients)
 };
 
+// ORC_TIMING=1: per-stage wall time of prove() on stderr (where the CPU baseline spends its time)
+struct StageTimer {
+  bool on = getenv("ORC_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "  [orc] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 static inline Proof prove(const CircuitProverData& d, const std::vector<std::vector<u64>>& wires,
                           const std::vector<u64>& public_inputs, const ProverSalts& salts,
                           unsigned threads, ProveTrace* trace = nullptr) {
@@ -216,9 +244,11 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
   Proof pf;
   pf.public_inputs = public_inputs;
   Hash pih = hash_no_pad(public_inputs.data(), public_inputs.size());
+  StageTimer tm;
 
   PolyBatch wires_b = batch_from_values(wires, c.rate_bits, c.cap_height, c.hiding ? salts.wires : nullptr,
                                         salt_cols, threads);
+  tm.lap("commit wires");
   Challenger ch;
   ch.observe_hash(d.circuit_digest);
   ch.observe_hash(pih);
@@ -227,16 +257,20 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
   for (size_t i = 0; i < nch; i++) betas.push_back(ch.get_challenge());
   for (size_t i = 0; i < nch; i++) gammas.push_back(ch.get_challenge());
 
-  std::vector<std::vector<u64>> zs_pp = compute_zs_partial_products(d, wires, betas, gammas);
+  std::vector<std::vector<u64>> zs_pp = compute_zs_partial_products(d, wires, betas, gammas, threads);
+  tm.lap("zs / partial products");
   PolyBatch zs_b = batch_from_values(zs_pp, c.rate_bits, c.cap_height, c.hiding ? salts.zs_pp : nullptr,
                                      salt_cols, threads);
+  tm.lap("commit zs");
   ch.observe_cap(zs_b.tree.cap);
   for (size_t i = 0; i < nch; i++) alphas.push_back(ch.get_challenge());
 
   std::vector<std::vector<u64>> qchunks =
       compute_quotient_chunks(d, wires_b, zs_b, pih.e, betas, gammas, alphas, threads);
+  tm.lap("quotient");
   PolyBatch q_b = batch_from_coeffs(qchunks, c.rate_bits, c.cap_height, c.hiding ? salts.quotient : nullptr,
                                     salt_cols, threads);
+  tm.lap("commit quotient");
   ch.observe_cap(q_b.tree.cap);
   E2 zeta = ch.get_ext_challenge();
   if (e2pow(zeta, n) == e2(1)) throw std::runtime_error("Opening point is in the subgroup.");
@@ -244,7 +278,9 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
   // H10 openings
   const PolyBatch* oracles[4] = {&d.cs_batch, &wires_b, &zs_b, &q_b};
   auto eval_all = [&](const PolyBatch& b, size_t from, size_t to, E2 x, std::vector<E2>& out) {
-    for (size_t j = from; j < to; j++) out.push_back(eval_base_poly_at_e2(b.coeffs[j].data(), n, x));
+    size_t base = out.size();
+    out.resize(base + (to - from));
+    parallel_for(to - from, threads, [&](size_t j) { out[base + j] = eval_base_poly_at_e2(b.coeffs[from + j].data(), n, x); });
   };
   E2 zeta_next = scale(zeta, root_of_unity(c.degree_bits));
   eval_all(d.cs_batch, 0, c.num_constants, zeta, pf.constants);
@@ -258,6 +294,7 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
     for (E2 e : *v) ch.observe_ext(e);
   for (E2 e : pf.zs_next) ch.observe_ext(e);
 
+  tm.lap("openings");
   // H11 prove_openings: final_poly = sum_batches alpha^(..) (F_b(X) - F_b(z_b)) / (X - z_b)
   E2 alpha = ch.get_ext_challenge();
   std::vector<E2> final_poly(n, e2(0));
@@ -291,6 +328,7 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
   }
   if (trace) trace->final_poly_coeffs_initial = final_poly;
 
+  tm.lap("fri combine");
   // H12 commit phase
   unsigned lde_bits = c.lde_bits();
   std::vector<E2> coeffs = final_poly;  // logical length n; LDE padding is implicit
@@ -338,19 +376,41 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
   pf.final_poly = coeffs;  // already truncated to len >> rate_bits (the padding was implicit)
   for (E2 e : pf.final_poly) ch.observe_ext(e);
 
+  tm.lap("fri commit phase");
   // H13 proof of work: smallest witness whose response has >= pow_bits leading zeros
   {
     State st = ch.state;
     size_t pos = ch.in.size();
     for (size_t i = 0; i < pos; i++) st[i] = ch.in[i];
+    // plonky2 searches (0..p) with rayon find_any; here windows of candidates are tried in parallel (eight per
+    // permutation call where AVX-512 is available) and the SMALLEST witness of the first window with a hit is
+    // kept, so that the result stays deterministic
     u64 wv = 0;
-    for (;; wv++) {
-      State s2 = st;
-      s2[pos] = wv;
-      poseidon(s2);
-      u64 resp = s2[7];
-      unsigned lz = resp ? (unsigned)__builtin_clzll(resp) : 64;
-      if (lz >= c.pow_bits) break;
+    const u64 per_task = 512, tasks = 4 * (u64)(threads ? threads : 1);
+    for (u64 start = 0;; start += per_task * tasks) {
+      std::vector<u64> found(tasks, ~0ull);
+      parallel_for(tasks, threads, [&](size_t t) {
+        u64 lo = start + t * per_task;
+        u64 w8[8];
+        for (u64 cand = lo; cand < lo + per_task; cand += 8) {
+          for (int j = 0; j < 8; j++) w8[j] = cand + j;
+          u64 resp[8];
+          pow_responses_x8(st, pos, w8, resp);
+          for (int j = 0; j < 8; j++) {
+            unsigned lz = resp[j] ? (unsigned)__builtin_clzll(resp[j]) : 64;
+            if (lz >= c.pow_bits) {
+              found[t] = w8[j];
+              return;
+            }
+          }
+        }
+      });
+      u64 best = ~0ull;
+      for (u64 f : found) best = f < best ? f : best;
+      if (best != ~0ull) {
+        wv = best;
+        break;
+      }
     }
     pf.pow_witness = wv;
     ch.observe(wv);
@@ -359,6 +419,7 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
     if (lz < c.pow_bits) throw std::runtime_error("pow response mismatch");
   }
 
+  tm.lap("proof of work");
   // H14 query rounds
   size_t lde_size = (size_t)1 << lde_bits;
   for (u64 q = 0; q < c.num_query_rounds; q++) {
@@ -380,6 +441,7 @@ static inline Proof prove(const CircuitProverData& d, const std::vector<std::vec
     }
     pf.queries.push_back(std::move(qr));
   }
+  tm.lap("queries");
   pf.wires_cap = wires_b.tree.cap;
   pf.zs_cap = zs_b.tree.cap;
   pf.quotient_cap = q_b.tree.cap;

@@ -254,6 +254,14 @@ static const int kSmallMaxLog = 14;
 static const int kSmallTableLog = 12;  // up to here the full twiddle table fits next to the tile
 static const int kSmallSmemBytes = 148 * 1024;
 static const int kClusterMaxLog = 16;  // 8 CTAs x 2 rows of 2^12 points
+static int ntt_cluster_min() {  // QPZK_NTT_CLUSTER_MIN=13|14: also take 2^13 / 2^14-point transforms (experiment)
+  static const int v = [] {
+    const char* e = getenv("QPZK_NTT_CLUSTER_MIN");
+    int x = e ? atoi(e) : 15;
+    return x < 9 ? 9 : x;
+  }();
+  return v;
+}
 static bool ntt_cluster_enabled() {    // QPZK_NTT_CLUSTER=0: the two-pass kernels (A/B measurements)
   static const bool on = [] {
     const char* e = getenv("QPZK_NTT_CLUSTER");
@@ -296,10 +304,10 @@ static int launch_lde_shift(qpzk_ctx* c, const u64* coeffs, u64 src_stride, u64*
   const u64* pm;
   QP(get_coset_pm(c, k, r, shift, &pm));
   u32 ncosets = nblk;
-  if (k <= kSmallMaxLog) return launch_small<false>(c, coeffs, src_stride, lde, dst_stride, pm, tab, ncols, ncosets, k, r, 1, blk0);
+  if (k <= kSmallMaxLog && k < ntt_cluster_min()) return launch_small<false>(c, coeffs, src_stride, lde, dst_stride, pm, tab, ncols, ncosets, k, r, 1, blk0);
   if (k > 20) return fail(QPZK_ERR_UNSUPPORTED, "degree_bits > 20 not supported");
   if (k <= kClusterMaxLog && ntt_cluster_enabled()) {  // 2^15, 2^16 points: one pass, the tile spread over a cluster
-    const int a1 = k - 12, lb = 12;                    // n = 2^a1 rows of 2^12 points: radix-8 / radix-16 across the cluster
+    const int a1 = k == 15 ? 3 : 4, lb = k - a1;       // n = 2^a1 rows of 2^lb points: radix-8 / radix-16 across the cluster
     RootTab tab_b;
     QP(get_root_tab(c, lb, false, &tab_b));
     const u64 *tw1, *twc;
