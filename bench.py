@@ -39,6 +39,7 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 PROOF_K, PROOF_ZK = 14, True
+SALT_SEED = np.array([0x5EED0003, 0x0123456789ABCDEF, 0xFEDCBA9876543210, 0x0F1E2D3C4B5A6978], np.uint64)
 DEGREE_BITS, NCOLS, RATE_BITS, CAP_HEIGHT = 16, 135, 3, 4
 METRIC = "wormhole proofs/s (bench-data shape: 2^14 rows x 135 wires, ZK, rate_bits=3, cap_height=4, 28 queries)"
 UNIT = "proofs/s"
@@ -226,8 +227,9 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def commit_microbench(ctx, qpzk, steps, warmup, rank):
-    """BASELINE configs[2]: per-stage device times of PolynomialBatch::from_values, 2^16 x 135."""
+def commit_microbench(ctx, qpzk, steps, warmup, rank, blinding=False):
+    """BASELINE configs[2]: per-stage device times of PolynomialBatch::from_values, 2^16 x 135; with
+    blinding = True, 4 salt columns from SplitMix64 seed 0x5eed0002 join every leaf."""
     n = 1 << DEGREE_BITS
     nrot = 4  # 4 x 70.8 MB distinct traces > 126 MB L2
     dev = []
@@ -236,15 +238,23 @@ def commit_microbench(ctx, qpzk, steps, warmup, rank):
         d = ctx.dev_alloc(tr.nbytes)
         ctx.h2d(d, tr)
         dev.append(d)
+    salts = None
+    if blinding:
+        sa = splitmix_trace(0x5EED0002, 4, n << RATE_BITS)
+        sp = ctx.dev_alloc(sa.nbytes)
+        ctx.h2d(sp, sa)
+        salts = (sp, 4)
     stages = []
     for i in range(warmup + steps):
-        b = qpzk.PolynomialBatch.from_values_dev(ctx, dev[i % nrot], NCOLS, n, RATE_BITS, CAP_HEIGHT)
+        b = qpzk.PolynomialBatch.from_values_dev(ctx, dev[i % nrot], NCOLS, n, RATE_BITS, CAP_HEIGHT, salts=salts)
         st = ctx.stage_ms()
         b.free()
         if i >= warmup:
             stages.append(st)
     for d in dev:
         ctx.dev_free(d)
+    if salts:
+        ctx.dev_free(salts[0])
     return {k2: float(np.mean([s[k2] for s in stages])) for k2 in stages[0]}
 
 
@@ -485,8 +495,8 @@ def run_gpu(args, rank, local_rank, world):
                 s = mine[issued % len(mine)]
                 if resident:
                     circuits[s].prove_begin_dev(dev_w[s], circ["public_inputs"], dev_s[s])
-                else:
-                    circuits[s].prove_begin(pinned_w[s].array, circ["public_inputs"], [a.array for a in pinned_s[s]])
+                else:   # host witness in; the salts are drawn on the device from a seed, as the reference draws its own
+                    circuits[s].prove_begin(pinned_w[s].array, circ["public_inputs"], seed=SALT_SEED)
                 inflight.append(s)
                 issued += 1
             out = circuits[inflight.pop(0)].prove_end()
@@ -532,11 +542,12 @@ def run_gpu(args, rank, local_rank, world):
     l0 = sum(c.launch_count() for c in ctxs)
     ms_res = timed(steps_total, True)
     launches = sum(c.launch_count() for c in ctxs) - l0
+    proof = results[0]
     ms_e2e = timed(steps_total, False)
+    proof_e2e = results[0]
     if rank == 0:
         sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    proof = results[0]
 
     # ---- everything that needs all ranks comes first; then ranks > 0 are released (they used to spin in a
     # barrier at ~60 % "GPU busy" while rank 0 ran its single-GPU extras) ----
@@ -657,6 +668,7 @@ def run_gpu(args, rank, local_rank, world):
             del bc
 
     micro = commit_microbench(ctx0, qpzk, 5, 3, rank) if rank == 0 else None
+    micro_blind = commit_microbench(ctx0, qpzk, 5, 3, rank, blinding=True) if rank == 0 else None
     sweep = commit_sweep(ctx0, qpzk) if rank == 0 else None
     imad_wide = ctx0.measure_imad_peak(1)
     imad_lo = ctx0.measure_imad_peak(0)
@@ -676,6 +688,11 @@ def run_gpu(args, rank, local_rank, world):
         # and the restated verifier must accept them
         if proof != want:
             raise SystemExit("bench: GPU proof bytes != oracle proof bytes")
+        # the e2e arm drew its salts on the device: the oracle gets the same salts restated on the host
+        want_e2e = oc.prove(circ["wires"], circ["public_inputs"], [synth.seeded_salts(SALT_SEED, o, n << RATE_BITS)
+                                                                   for o in range(3)])
+        if proof_e2e != want_e2e:
+            raise SystemExit("bench: GPU proof with device-drawn salts != oracle proof with the restated salts")
         rc, _ = orc.verify(circ["common"], circuits[0].verifier_only_bytes(), proof)
         if rc != 0:
             raise SystemExit("bench: GPU proof rejected by the restated verifier (code %d)" % rc)
@@ -688,7 +705,7 @@ def run_gpu(args, rank, local_rank, world):
         achieved = alg["ntt_bytes"] / (ntt_ms * 1e-3) / 1e9
         peak = float(peaks["hbm_gbs"])
         total = steps_total * world
-        h2d = int(circ["wires"].nbytes + sum(s.nbytes for s in circ["salts"]))
+        h2d = int(circ["wires"].nbytes + SALT_SEED.nbytes)   # e2e: witness + the 32-byte salt seed
         line = {
             "metric": METRIC, "value": total / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
@@ -699,7 +716,9 @@ def run_gpu(args, rank, local_rank, world):
                        "streams_per_gpu": S, "host_threads_per_gpu": HT, "host_wait": sync, "host_cores": cores,
                        "l2": "each proof streams ~0.3 GB of LDE/digest buffers through HBM (> 126 MB L2); "
                              "the commit microbench rotates 4 distinct 70.8 MB traces",
-                       "parallelism": "independent proofs, %d stream(s) per GPU, no collective" % S},
+                       "parallelism": "independent proofs, %d stream(s) per GPU, no collective" % S,
+                       "salts": "value: three [4][2^17] salt arrays resident in HBM; e2e: drawn on the device from a "
+                                "32-byte seed (ChaCha8), as the reference draws its own from the OS RNG"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d * S, "d2h_bytes_per_step": len(proof) * S},
             "gpu_launches": int(launches),
@@ -707,7 +726,10 @@ def run_gpu(args, rank, local_rank, world):
             "proof_stage_ms": proof_stages,
             "circuit_constants_sigmas_commit_ms": circuit_commit_ms,
             "commit_microbench": {"workload": "PolynomialBatch::from_values 2^16 x 135, rate_bits=3, cap_height=4 "
-                                              "(BASELINE configs[2])", "ms": sum(micro.values()), "stage_ms": micro},
+                                              "(BASELINE configs[2])", "ms": sum(micro.values()), "stage_ms": micro,
+                                  "blinding": {"workload": "the same with blinding = true: 4 salt columns (seed "
+                                                           "0x5eed0002), 139-element leaves = 18 permutations",
+                                               "ms": sum(micro_blind.values()), "stage_ms": micro_blind}},
             "roofline": {"bound": "hbm", "kernel": "commit microbench: IFFT (k_ntt_pass_a / k_ntt_pass_b_transpose) + "
                                                    "coset LDE (k_ntt_cluster)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -731,6 +753,16 @@ def run_gpu(args, rank, local_rank, world):
                                             "algorithmic count of SURVEY 8(d) (its 2304 small-constant MDS "
                                             "multiplies now execute as DFMA on the FP64 pipe)",
                              "peak_imad_32bit": imad_lo / 1e12, "permutations": alg["perms"],
+                             # the same work charged per instruction class: the 4308 wide (32x32+64) multiplies of a
+                             # permutation against the IMAD.WIDE peak, its 2304 small-constant MDS multiplies against the
+                             # 32-bit IMAD peak they were counted as in SURVEY 8(d) (they execute as DFMA today)
+                             "frac_class_weighted": alg["perms"] * (4308.0 / imad_wide + 2304.0 / imad_lo) / (hash_ms * 1e-3),
+                             "frac_wide_multiplies_only": alg["perms"] * 4308.0 / imad_wide / (hash_ms * 1e-3),
+                             "ncu": {"source": "profiles/r1_leaf_hash_v5_twoplane_ncu_full.txt (k_leaf_hash, same kernel)",
+                                     "issue_slots_busy_pct": 60.9, "fmaheavy_pipe_pct": 75.8, "alu_pipe_pct": 49.6,
+                                     "fp64_pipe_pct": 15.7, "warp_instructions_per_permutation": 19800,
+                                     "limiter": "the FMA-heavy (integer multiply) pipe: 25.9 k pipe cycles per warp-permutation "
+                                                "(IMAD.WIDE / IMAD.HI hold it 4 cycles, other IMAD forms 2) of 33.6 k elapsed"},
                              "traffic": LEAF_HASH_DRAM_BYTES_PER_COMMIT,
                              "perms_per_s": alg["perms"] / (hash_ms * 1e-3), "stage_ms": hash_ms},
             "clocks": clocks,

@@ -53,6 +53,10 @@ typedef struct qpzk_batch qpzk_batch; /* PolynomialBatch: coefficients + LDE + M
 typedef struct qpzk_tree qpzk_tree;   /* MerkleTree over caller-provided leaves, on device */
 
 #define QPZK_SALT_SIZE 4 /* plonky2 SALT_SIZE: blinding columns appended to each hiding oracle */
+/* qpzk_prove flags */
+#define QPZK_PROVE_TRACE 1u        /* keep intermediates for qpzk_prove_trace */
+#define QPZK_PROVE_DEVICE_INPUTS 2u /* wires / salts are device pointers */
+#define QPZK_PROVE_SEEDED_SALTS 4u  /* salts drawn on the device from a 32-byte seed */
 
 /* Stage indices for qpzk_ctx_stage_ms (CUDA-event time of the last commit on this context). */
 enum {
@@ -225,6 +229,11 @@ void qpzk_circuit_free(qpzk_circuit* c);
  * smallest valid one (the reference returns whichever a rayon worker finds first; any valid witness
  * verifies). flags bit 0: keep intermediates for qpzk_prove_trace; bit 1: `wires` and the salt
  * pointers are DEVICE pointers on the context's device (HBM-resident witness).
+ * bit 2 (QPZK_PROVE_SEEDED_SALTS): the blinding salts are DRAWN ON THE DEVICE: salts_wires points to a
+ * 32-byte seed on the host (salt_words = 4), salts_zs / salts_quotient are ignored, and the salts of oracle o
+ * (0 wires, 1 Z|partial products, 2 quotient) are the ChaCha8 stream keyed by the seed with nonce o (eight
+ * salts per 64-byte block, element j = column j / N, natural row j % N, values >= p reduced by p) - what
+ * plonky2 takes from the OS RNG, reproducible, and 12.6 MB less host-to-device traffic per wormhole proof.
  * wires_words / salt_words: element counts of `wires` and of EACH salt array, checked against the circuit
  * (num_wires << degree_bits, 4 << (degree_bits + rate_bits)).
  * The whole proof is enqueued on the context's stream without a host round trip (the transcript is a

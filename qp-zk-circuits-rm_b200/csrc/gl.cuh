@@ -19,6 +19,24 @@ typedef uint32_t u32;
 #define GL_GEN 14293326489335486720ULL       // MULTIPLICATIVE_GROUP_GENERATOR == coset shift
 #define GL_ROOT_2_32 7277203076849721926ULL  // POWER_OF_TWO_GENERATOR
 
+// -DQPZK_CHECKED (make libqpzk_checked.so): every tile, level, wire and table index computed on the device is
+// range-checked and a violation traps the kernel (the context then reports an error on its next call). This is the
+// stand-in for compute-sanitizer, which the GPU pool does not allow; tests/test_gpu_checked_build.py runs the
+// small-case suite against the checked library.
+#ifdef QPZK_CHECKED
+#include <cstdio>
+#define QPZK_CHECK(cond)                                                                              \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      printf("QPZK_CHECK failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)threadIdx.x);                                                                       \
+      __trap();                                                                                       \
+    }                                                                                                 \
+  } while (0)
+#else
+#define QPZK_CHECK(cond) ((void)0)
+#endif
+
 #define GL_DEV __device__ __forceinline__
 #ifndef GL_FOLD_ALU
 #define GL_FOLD_ALU 1

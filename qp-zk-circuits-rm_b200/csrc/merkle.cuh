@@ -110,6 +110,7 @@ k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wi
   }
   for (;;) {
     u64* out = levels + (twoN - (twoN >> l) + t) * 4;
+    QPZK_CHECK(l <= log_n && t < (((u64)1 << log_n) >> l));
     if (lane < 4) out[lane] = gl_canon(s);
     if (l >= top) break;
     // publish, then pair up with the sibling subtree
@@ -118,7 +119,9 @@ k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wi
     const u32 d = l + 1 - l_start;                                   // parent's depth above the start level
     const u64 ci = 2 * count - ((2 * count) >> d) + ((t >> 1) - (first >> d));
     u32 old = 0;
+    QPZK_CHECK(ci < 2 * count && ci < 2 * QPZK_CLIMB_MAX_START);
     if (lane == 0) old = atomicAdd(&counters[ci], 1u);
+    QPZK_CHECK(lane != 0 || old < 2);
     old = __shfl_sync(mask, old, 0, 16);
     if (old == 0) break;                                             // the sibling will take the parent
     if (lane == 0) counters[ci] = 0;

@@ -129,15 +129,27 @@ GL_DEV u32 tile_pos(u32 c, u32 e, u32 cnt_log, u32 pitch) {
 // through ST; inside a pass both are the shared-memory tile, but the FIRST stage of a kernel reads
 // straight from global memory (all of a thread's loads are issued before any arithmetic, and one
 // shared-memory round trip disappears) and the LAST stage may write straight to global memory.
+// (checked build: an access must fall inside the dynamic shared memory the kernel was launched with)
+GL_DEV u32 dyn_smem_words() {
+  u32 bytes;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
+  return bytes >> 3;
+}
 template <bool INTERLEAVED>
 struct TileLd {
   const u64* sm; u32 cnt_log, pitch;
-  GL_DEV u64 operator()(u32 c, u32 e) const { return sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)]; }
+  GL_DEV u64 operator()(u32 c, u32 e) const {
+    QPZK_CHECK(tile_pos<INTERLEAVED>(c, e, cnt_log, pitch) < dyn_smem_words());
+    return sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)];
+  }
 };
 template <bool INTERLEAVED>
 struct TileSt {
   u64* sm; u32 cnt_log, pitch;
-  GL_DEV void operator()(u32 c, u32 e, u64 v) const { sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)] = v; }
+  GL_DEV void operator()(u32 c, u32 e, u64 v) const {
+    QPZK_CHECK(tile_pos<INTERLEAVED>(c, e, cnt_log, pitch) < dyn_smem_words());
+    sm[tile_pos<INTERLEAVED>(c, e, cnt_log, pitch)] = v;
+  }
 };
 struct NoPre {
   GL_DEV void operator()() const {}
@@ -148,7 +160,10 @@ struct NoPre {
 //             consecutive words
 struct TwTable {
   const u64* tw; int sh;
-  GL_DEV u64 operator()(u32 e_lo, u32 k1) const { return tw[(e_lo * k1) << sh]; }
+  GL_DEV u64 operator()(u32 e_lo, u32 k1) const {
+    QPZK_CHECK(((e_lo * k1) << sh) < dyn_smem_words());
+    return tw[(e_lo * k1) << sh];
+  }
 };
 struct TwMatrix {
   const u64* t; u32 q_log;
@@ -356,6 +371,7 @@ k_ntt_cluster(const u64* __restrict__ src, u64 src_stride, u64* __restrict__ dst
         const u32 k1 = __brev((u32)p) >> (32 - A1);
         u64 e = v[p];
         if (p != 0) e = gl_mul(e, twc[((u64)k1 << lb) + j2]);
+        QPZK_CHECK((p & (RPC - 1)) * pitch + pos < RPC * pitch);
         remote[p >> RPC_LOG][(p & (RPC - 1)) * pitch + pos] = e;
       }
     }

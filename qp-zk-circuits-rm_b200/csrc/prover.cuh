@@ -171,6 +171,7 @@ struct AlphaAcc {
   u32 nch;
 };
 GL_DEV void aa_emit(AlphaAcc& a, u64 term) {
+  QPZK_CHECK(a.t < QPZK_APW_STRIDE);
 #pragma unroll
   for (int c = 0; c < 2; c++)
     if (c < (int)a.nch) acc_mac(a.acc[c], __ldg(a.apw + c * QPZK_APW_STRIDE + a.t), term);
@@ -195,8 +196,19 @@ GL_DEV void aa_gate_end(AlphaAcc& a, u64 filter) {
 struct WireRow {  // column-major LDE accessor for one leaf position
   const u64* base;
   u64 N;
-  GL_DEV u64 operator[](u32 c) const { return __ldg(base + (u64)c * N); }
+#ifdef QPZK_CHECKED
+  u32 width;
+#endif
+  GL_DEV u64 operator[](u32 c) const {
+    QPZK_CHECK(c < width);
+    return __ldg(base + (u64)c * N);
+  }
 };
+#ifdef QPZK_CHECKED
+#define QPZK_WIRE_ROW(base, stride, width) WireRow{base, stride, width}
+#else
+#define QPZK_WIRE_ROW(base, stride, width) WireRow{base, stride}
+#endif
 
 // PoseidonGate::eval_unfiltered (123 constraints) with the fast partial rounds; emits in order.
 // The s-box input wires (29..134) are consumed in index order, a few per round, each right before a long
@@ -461,8 +473,14 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
   const u64 leaf_next = __brevll(inext << step_bits) >> (64 - full_bits);
   const u64 x = gl_mul(GL_GEN, root_pow(tab, i));
   const u32 nch = d.num_challenges, npp = d.num_partial_products;
-  WireRow cs{cs_lde + leaf, cs_stride}, w{wires_lde + leaf, wires_stride}, zs{zs_lde + leaf, zs_stride};
-  WireRow zsn{zs_lde + leaf_next, zs_stride};
+  QPZK_CHECK(leaf < ((u64)1 << full_bits) && leaf_next < ((u64)1 << full_bits));
+  QPZK_CHECK(d.num_gates <= QPZK_MAX_GATES && d.num_selectors <= QPZK_MAX_GATES && nch <= 2);
+  const u32 zs_width = nch * (1 + npp);
+  WireRow cs = QPZK_WIRE_ROW(cs_lde + leaf, cs_stride, d.num_constants + d.num_routed);
+  WireRow w = QPZK_WIRE_ROW(wires_lde + leaf, wires_stride, d.num_wires);
+  WireRow zs = QPZK_WIRE_ROW(zs_lde + leaf, zs_stride, zs_width);
+  WireRow zsn = QPZK_WIRE_ROW(zs_lde + leaf_next, zs_stride, zs_width);
+  (void)zs_width;
   const u64 zhx = zh[i & (((u64)1 << d.quotient_degree_bits) - 1)];
 
   AlphaAcc a;
@@ -536,6 +554,7 @@ k_quotient(const u64* __restrict__ cs_lde, const u64* __restrict__ wires_lde, co
   for (u32 g = 0; g < d.num_gates; g++) {
     if (d.gate_id[g] == G_NOOP) continue;
     const u32 si = d.gate_selector[g];
+    QPZK_CHECK(si < d.num_selectors && d.group_hi[si] <= d.num_gates);
     const u64 s = cs[si];
     u64 filter = 1;
     for (u32 j = d.group_lo[si]; j < d.group_hi[si]; j++)
@@ -847,6 +866,7 @@ __global__ void k_gather_openings(const u64* __restrict__ lde, u64 row_stride, u
   const u64 leaf = leaf_idx[q] >> shift_bits;
   const u32 L = log_n - cap_height;
   u64* o = out + (u64)q * (width + 4 * L);
+  QPZK_CHECK(leaf < ((u64)1 << log_n) && cap_height <= log_n);
   if (leaf < leaf0 || leaf >= leaf1) {
     for (u32 e = threadIdx.x; e < width + 4 * L; e += blockDim.x) o[e] = 0;
     return;

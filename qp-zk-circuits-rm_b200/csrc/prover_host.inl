@@ -909,19 +909,35 @@ struct qpzk_sprove {
   int phase = 0;
   const u64 *salt_w = nullptr, *salt_z = nullptr, *salt_q = nullptr;
   const u64* wires_dev = nullptr;
-  DevBuf wires_up, zs_vals, apw, qvals, qcoeffs;
+  DevBuf wires_up, zs_vals, apw, qvals, qcoeffs, salt_buf;
+  bool seeded = false;   // QPZK_PROVE_SEEDED_SALTS: the salts of every blinded oracle are drawn on the device
+  SaltSeed seed;
   std::unique_ptr<qpzk_batch> wires_b, zs_b, q_b;
   qpzk_fri F;
   explicit qpzk_sprove(qpzk_circuit* q_)
-      : q(q_), wires_up(q_->ctx), zs_vals(q_->ctx), apw(q_->ctx), qvals(q_->ctx), qcoeffs(q_->ctx) {}
+      : q(q_), wires_up(q_->ctx), zs_vals(q_->ctx), apw(q_->ctx), qvals(q_->ctx), qcoeffs(q_->ctx), salt_buf(q_->ctx) {}
 
-  int commit(const u64* in, bool is_coeffs, u32 ncols, const u64* salts, std::unique_ptr<qpzk_batch>* out) {
+  void set_seed(const u64* seed_words) {  // flags bit 2: salts_wires is a 32-byte seed on the HOST
+    seeded = (flags & 4) && q->common.hiding;
+    if (seeded) memcpy(seed.key, seed_words, sizeof seed.key);
+  }
+  int commit(const u64* in, bool is_coeffs, u32 ncols, const u64* salts, u32 oracle, std::unique_ptr<qpzk_batch>* out) {
     const CommonHost& cm = q->common;
+    qpzk_ctx* c = q->ctx;
     const u32 salt_cols = cm.hiding ? QPZK_SALT_SIZE : 0;
-    const bool on_device = flags & 2;
+    bool salts_host = !(flags & 2);
+    if (cm.hiding && seeded) {
+      const u64 count = (u64)QPZK_SALT_SIZE << (q->desc.degree_bits + q->desc.rate_bits);
+      if (!salt_buf.p) QP(salt_buf.alloc(count * 8));
+      k_salts_chacha8<<<(unsigned)((count / 8 + 127) / 128), 128, 0, c->stream>>>(seed, oracle, count, salt_buf.p);
+      c->launches++;
+      CU(cudaGetLastError());
+      salts = salt_buf.p;
+      salts_host = false;
+    }
     qpzk_batch* raw = nullptr;
-    QP(commit_impl(q->ctx, in, false, is_coeffs, ncols, q->desc.degree_bits, q->desc.rate_bits, (u32)cm.cap_height,
-                   cm.hiding ? salts : nullptr, !on_device, salt_cols, &raw, sub_begin, sub_end, false));
+    QP(commit_impl(c, in, false, is_coeffs, ncols, q->desc.degree_bits, q->desc.rate_bits, (u32)cm.cap_height,
+                   cm.hiding ? salts : nullptr, salts_host, salt_cols, &raw, sub_begin, sub_end, false));
     out->reset(raw);
     return QPZK_OK;
   }
@@ -954,7 +970,7 @@ struct qpzk_sprove {
       CU(cudaMemcpyAsync(wires_up.p, wires_in, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
       wires_dev = wires_up.p;
     }
-    QP(commit(wires_dev, false, d.num_wires, salt_w, &wires_b));
+    QP(commit(wires_dev, false, d.num_wires, salt_w, 0, &wires_b));
     phase = 1;
     return QPZK_OK;
   }
@@ -973,7 +989,7 @@ struct qpzk_sprove {
     CU(cudaEventRecord(q->ev[1], c->stream));  // stage 0: wires commit
     const u32 nzs = nch * (1 + d.num_partial_products);
     QP(compute_zs_partial_products(q, wires_dev, &T->ch, &zs_vals));
-    QP(commit(zs_vals.p, false, nzs, salt_z, &zs_b));
+    QP(commit(zs_vals.p, false, nzs, salt_z, 1, &zs_b));
     if (q->want_trace) {
       q->tr_zs_pp.resize((size_t)nzs * n);
       CU(cudaMemcpyAsync(q->tr_zs_pp.data(), zs_vals.p, (size_t)nzs * n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1008,7 +1024,7 @@ struct qpzk_sprove {
     const u32 nch = d.num_challenges, qlb = d.degree_bits + d.quotient_degree_bits;
     const u64 qlde = 1ull << qlb;
     QP(quotient_values_to_chunks(q, &qvals, sharded, &qcoeffs));
-    QP(commit(qcoeffs.p, true, nch * d.qdf, salt_q, &q_b));
+    QP(commit(qcoeffs.p, true, nch * d.qdf, salt_q, 2, &q_b));
     if (q->want_trace) {
       q->tr_quotient.resize((size_t)nch * qlde);
       CU(cudaMemcpyAsync(q->tr_quotient.data(), qcoeffs.p, (size_t)nch * qlde * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1116,6 +1132,7 @@ static int prove_enqueue(qpzk_circuit* q, const u64* wires_in, const u64* pis, u
   run.salt_w = salt_w;
   run.salt_z = salt_z;
   run.salt_q = salt_q;
+  run.set_seed(salt_w);
   QP(run.phase_wires(wires_in, pis, npi));
   QP(run.phase_zs());
   QP(run.phase_quotient_eval());
@@ -1397,13 +1414,16 @@ int qpzk_fri_query(qpzk_fri* f, uint64_t x_index, uint64_t* out, size_t cap_word
 void qpzk_fri_free(qpzk_fri* f) { delete f; }
 
 static int check_prove_args(qpzk_circuit* q, const uint64_t* wires, size_t wires_words, const uint64_t* public_inputs,
-                            uint32_t npi, const uint64_t* sw, const uint64_t* sz, const uint64_t* sq, size_t salt_words) {
+                            uint32_t npi, const uint64_t* sw, const uint64_t* sz, const uint64_t* sq, size_t salt_words,
+                            uint32_t flags = 0) {
   if (!q || !wires || (!public_inputs && npi)) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   const CommonHost& cm = q->common;
   if (npi != cm.num_public_inputs) return fail(QPZK_ERR_BAD_ARG, "public input count mismatch");
   if (wires_words != ((size_t)cm.num_wires << cm.degree_bits))
     return fail(QPZK_ERR_BAD_ARG, "wires must hold num_wires * 2^degree_bits words");
-  if (cm.hiding) {
+  if (cm.hiding && (flags & 4)) {
+    if (!sw || salt_words != 4) return fail(QPZK_ERR_BAD_ARG, "seeded salts: salts_wires must point to a 4-word seed (salt_words = 4)");
+  } else if (cm.hiding) {
     if (!(sw && sz && sq)) return fail(QPZK_ERR_BAD_ARG, "hiding circuit needs salts");
     if (salt_words != ((size_t)QPZK_SALT_SIZE << (cm.degree_bits + cm.rate_bits)))
       return fail(QPZK_ERR_BAD_ARG, "each salt array must hold 4 * 2^(degree_bits + rate_bits) words");
@@ -1415,7 +1435,7 @@ int qpzk_prove_begin(qpzk_circuit* q, const uint64_t* wires, size_t wires_words,
                      uint32_t num_public_inputs, const uint64_t* salts_wires, const uint64_t* salts_zs,
                      const uint64_t* salts_quotient, size_t salt_words, uint32_t flags) {
   return guarded([&]() -> int {
-    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words));
+    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words, flags));
     CU(cudaSetDevice(q->ctx->device));
     std::lock_guard<std::mutex> lk(q->mu);
     if (q->in_flight) return fail(QPZK_ERR_BAD_ARG, "a proof is already in flight on this circuit handle: call qpzk_prove_end first");
@@ -1455,7 +1475,7 @@ int qpzk_sprove_begin(qpzk_circuit* q, const uint64_t* wires, size_t wires_words
                       uint32_t subtree_end, qpzk_sprove** out) {
   return guarded([&]() -> int {
     if (!out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
-    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words));
+    QP(check_prove_args(q, wires, wires_words, public_inputs, num_public_inputs, salts_wires, salts_zs, salts_quotient, salt_words, flags));
     const u32 ncap = 1u << q->common.cap_height;
     if (subtree_begin >= subtree_end || subtree_end > ncap) return fail(QPZK_ERR_BAD_ARG, "bad subtree range");
     if (flags & 1) return fail(QPZK_ERR_UNSUPPORTED, "the parity trace is not kept for sharded proofs");
@@ -1470,6 +1490,7 @@ int qpzk_sprove_begin(qpzk_circuit* q, const uint64_t* wires, size_t wires_words
     s->salt_w = salts_wires;
     s->salt_z = salts_zs;
     s->salt_q = salts_quotient;
+    s->set_seed(salts_wires);
     int rc = s->phase_wires(wires, public_inputs, num_public_inputs);
     if (rc != QPZK_OK) {
       ctx_wait(q->ctx);

@@ -112,6 +112,7 @@ k_transcript_step(TranscriptDev* __restrict__ T, const u64* __restrict__ src, u3
   for (u32 j = 0; j < nsq1 + nsq2; j++) {
     u64 v = sponge_get(sp, lane, xch);  // every lane holds the value
     if (post == 2 && j >= 1) v &= aux;
+    QPZK_CHECK((j < nsq1 ? dst1 + j : dst2 + (j - nsq1)) < sizeof(TranscriptDev) / 8);
     if (lane == 0) words[j < nsq1 ? dst1 + j : dst2 + (j - nsq1)] = v;
     if (post == 1 && j < 2 && lane == 1) T->zeta_next[j] = gl_canon(gl_mul(v, aux));
   }
@@ -127,6 +128,51 @@ __global__ void __launch_bounds__(256) k_alpha_powers(const TranscriptDev* __res
   const u32 c = blockIdx.x;
   const u64 a = T->ch.alpha[c];
   for (u32 t = threadIdx.x; t < stride; t += blockDim.x) apw[c * stride + t] = gl_canon(gl_pow(a, t));
+}
+
+// ---- blinding salts drawn on the device ----
+// plonky2 draws the SALT_SIZE blinding columns of a hiding oracle from the OS RNG (`F::rand()`), which makes
+// reference proofs irreproducible and, for a GPU prover fed from the host, costs 12.6 MB of PCIe traffic per
+// wormhole proof (4 columns x 2^17 x 8 B x 3 oracles). With QPZK_PROVE_SEEDED_SALTS the caller passes a 32-byte
+// seed instead and the salts come from ChaCha8 keyed by it: block b of oracle o is the ChaCha8 block with key =
+// seed, counter = b, nonce = (o, 0); its sixteen 32-bit words are eight salts (little-endian pairs), salt j of
+// an oracle is element (column j / N, natural row j % N), values >= p wrap by p. The generator is a stream
+// cipher, so the seeded mode is as hiding as the seed is secret; the parity tests restate it on the host.
+struct SaltSeed {
+  u32 key[8];
+};
+GL_DEV u32 rotl32(u32 x, int n) { return (x << n) | (x >> (32 - n)); }
+__global__ void __launch_bounds__(128) k_salts_chacha8(SaltSeed seed, u32 oracle, u64 count /* salts, multiple of 8 */,
+                                                       u64* __restrict__ out) {
+  const u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b * 8 >= count) return;
+  u32 s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+#pragma unroll
+  for (int i = 0; i < 8; i++) s[4 + i] = seed.key[i];
+  s[12] = (u32)b;
+  s[13] = (u32)(b >> 32);
+  s[14] = oracle;
+  s[15] = 0;
+  u32 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = s[i];
+#define QPZK_QR(a, b_, c, d)                    \
+  x[a] += x[b_]; x[d] = rotl32(x[d] ^ x[a], 16); \
+  x[c] += x[d]; x[b_] = rotl32(x[b_] ^ x[c], 12); \
+  x[a] += x[b_]; x[d] = rotl32(x[d] ^ x[a], 8);  \
+  x[c] += x[d]; x[b_] = rotl32(x[b_] ^ x[c], 7);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {  // 8 rounds = 4 double rounds
+    QPZK_QR(0, 4, 8, 12) QPZK_QR(1, 5, 9, 13) QPZK_QR(2, 6, 10, 14) QPZK_QR(3, 7, 11, 15)
+    QPZK_QR(0, 5, 10, 15) QPZK_QR(1, 6, 11, 12) QPZK_QR(2, 7, 8, 13) QPZK_QR(3, 4, 9, 14)
+  }
+#undef QPZK_QR
+  u64 v[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) v[e] = gl_canon(((u64)(x[2 * e + 1] + s[2 * e + 1]) << 32) | (u64)(x[2 * e] + s[2 * e]));
+  ulonglong2* o = reinterpret_cast<ulonglong2*>(out + b * 8);
+#pragma unroll
+  for (int e = 0; e < 4; e++) o[e] = make_ulonglong2(v[2 * e], v[2 * e + 1]);
 }
 
 // Small host values into device words without a host-to-device copy (a pageable cudaMemcpyAsync

@@ -575,28 +575,41 @@ class Circuit:
                 salt_words = a.size
         return w.ctypes.data_as(_vp), w.size, pi, sp, salt_words, keep
 
-    def prove(self, wires, public_inputs, salts=None, trace=False):
-        self.prove_begin(wires, public_inputs, salts, trace=trace)
+    def prove(self, wires, public_inputs, salts=None, trace=False, seed=None):
+        """salts: the three [4][N] blinding arrays of a hiding circuit, or None with `seed` = 4 u64 words: the
+        salts are then drawn on the device (QPZK_PROVE_SEEDED_SALTS; qpzk.synth.seeded_salts restates them)."""
+        self.prove_begin(wires, public_inputs, salts, trace=trace, seed=seed)
         return self.prove_end()
 
-    def prove_dev(self, wires_dev, public_inputs, salts_dev=None):
+    def prove_dev(self, wires_dev, public_inputs, salts_dev=None, seed=None):
         """Same as prove() with the witness matrix (and salts) already resident on the device."""
-        self.prove_begin_dev(wires_dev, public_inputs, salts_dev)
+        self.prove_begin_dev(wires_dev, public_inputs, salts_dev, seed=seed)
         return self.prove_end()
 
-    def prove_begin(self, wires, public_inputs, salts=None, trace=False):
+    def prove_begin(self, wires, public_inputs, salts=None, trace=False, seed=None):
         """Enqueue one proof (qpzk_prove_begin); the host arrays must stay alive until prove_end()."""
         wp, wn, pi, sp, sn, keep = self._host_args(wires, public_inputs, salts)
-        _check(load_library().qpzk_prove_begin(self._h, wp, wn, _ptr(pi), pi.size, sp[0], sp[1], sp[2], sn,
-                                               1 if trace else 0))
+        flags = 1 if trace else 0
+        if seed is not None:
+            sd = _arr(seed)
+            if sd.size != 4:
+                raise ValueError("seed must be 4 u64 words")
+            keep.append(sd)
+            sp, sn, flags = [sd.ctypes.data_as(_vp), None, None], 4, flags | 4
+        _check(load_library().qpzk_prove_begin(self._h, wp, wn, _ptr(pi), pi.size, sp[0], sp[1], sp[2], sn, flags))
         self._keep = keep
 
-    def prove_begin_dev(self, wires_dev, public_inputs, salts_dev=None):
+    def prove_begin_dev(self, wires_dev, public_inputs, salts_dev=None, seed=None):
         pi = _arr(public_inputs)
         sp = [None, None, None] if salts_dev is None else [_vp(x) for x in salts_dev]
+        sn, flags, keep = (self.salt_words if salts_dev is not None else 0), 2, [pi]
+        if seed is not None:
+            sd = _arr(seed)
+            keep.append(sd)
+            sp, sn, flags = [sd.ctypes.data_as(_vp), None, None], 4, 6
         _check(load_library().qpzk_prove_begin(self._h, _vp(wires_dev), self.wires_words, _ptr(pi), pi.size, sp[0], sp[1],
-                                               sp[2], self.salt_words if salts_dev is not None else 0, 2))
-        self._keep = [pi]
+                                               sp[2], sn, flags))
+        self._keep = keep
 
     def prove_end(self):
         ln = ctypes.c_size_t(0)

@@ -44,9 +44,10 @@ def allgather_cap_nccl(batch, group=None):
     per = nwords // world
     if (b * 4, e * 4) != (rank * per, (rank + 1) * per):
         raise ValueError("subtree range does not match the rank's slot in the all-gather")
-    batch.ctx.sync()  # the commit ran on the context's stream; NCCL uses torch's
-    dist.all_gather_into_tensor(t, t[rank * per:(rank + 1) * per], group=group)
-    torch.cuda.current_stream().synchronize()
+    # on the context's own stream: ordered after the commit, no host synchronisation in between
+    with torch.cuda.stream(torch.cuda.ExternalStream(batch.ctx.stream, device=torch.device("cuda", batch.ctx.device))):
+        dist.all_gather_into_tensor(t, t[rank * per:(rank + 1) * per], group=group)
+    batch.ctx.sync()
     return t
 
 

@@ -539,3 +539,39 @@ def build_recursion(degree_bits, zk=False, seed=1, provider=None, arities=None,
                 wires=np.ascontiguousarray(wires.astype(np.uint64)),
                 public_inputs=np.array(public_inputs, np.uint64), salts=salts, degree_bits=degree_bits, zk=zk,
                 arities=arities, gate=gate)
+
+
+def seeded_salts(seed, oracle, n_lde, salt_cols=4):
+    """Host restatement of the on-device salt generator (include/qpzk.h QPZK_PROVE_SEEDED_SALTS, csrc/transcript.cuh
+    k_salts_chacha8): the [salt_cols][n_lde] blinding columns of oracle `oracle` (0 wires, 1 Z|partial products,
+    2 quotient) for a 4-word seed: ChaCha8 blocks with key = seed, counter = block index, nonce = (oracle, 0); each
+    block's sixteen words are eight salts; values >= p wrap by p. Vectorised over the blocks."""
+    key = np.ascontiguousarray(np.asarray(seed, np.uint64)).view(np.uint32)
+    count = salt_cols * n_lde
+    nb = (count + 7) // 8
+    b = np.arange(nb, dtype=np.uint64)
+    s = [np.full(nb, v, np.uint32) for v in (0x61707865, 0x3320646E, 0x79622D32, 0x6B206574)]
+    s += [np.full(nb, key[i], np.uint32) for i in range(8)]
+    s += [(b & np.uint64(0xFFFFFFFF)).astype(np.uint32), (b >> np.uint64(32)).astype(np.uint32),
+          np.full(nb, oracle, np.uint32), np.zeros(nb, np.uint32)]
+    x = [v.copy() for v in s]
+
+    def rotl(v, n):
+        return (v << np.uint32(n)) | (v >> np.uint32(32 - n))
+
+    def qr(a, bb, c, d):
+        x[a] += x[bb]; x[d] = rotl(x[d] ^ x[a], 16)
+        x[c] += x[d]; x[bb] = rotl(x[bb] ^ x[c], 12)
+        x[a] += x[bb]; x[d] = rotl(x[d] ^ x[a], 8)
+        x[c] += x[d]; x[bb] = rotl(x[bb] ^ x[c], 7)
+
+    with np.errstate(over="ignore"):
+        for _ in range(4):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        w = [x[i] + s[i] for i in range(16)]
+    out = np.empty((nb, 8), np.uint64)
+    for e in range(8):
+        v = (w[2 * e + 1].astype(np.uint64) << np.uint64(32)) | w[2 * e].astype(np.uint64)
+        out[:, e] = np.where(v >= np.uint64(P), v - np.uint64(P), v)
+    return out.ravel()[:count].reshape(salt_cols, n_lde)

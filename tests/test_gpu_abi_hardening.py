@@ -139,3 +139,26 @@ def test_small_and_ragged_trees_through_the_climb_kernel(ctx):
         assert np.array_equal(t.cap, cap), (log_n, leaf_len, cap_h)
         assert np.array_equal(t.digests, dg), (log_n, leaf_len, cap_h)
         t.free()
+
+
+def test_seeded_salts_match_the_host_restatement(ctx):
+    """QPZK_PROVE_SEEDED_SALTS: the blinding salts are drawn on the device from a 32-byte seed (ChaCha8). The proof
+    must be the one the oracle prover produces when it is handed the same salts, restated on the host."""
+    import qpzk
+    circ = minibuilder.build(8, zk=True, seed=31)
+    seed = np.array([0x0123456789ABCDEF, 0xFEDCBA9876543210, 7, 0xFFFFFFFFFFFFFFFF], np.uint64)
+    N = 1 << (8 + 3)
+    salts = [synth.seeded_salts(seed, o, N) for o in range(3)]
+    assert all((s < np.uint64(0xFFFFFFFF00000001)).all() for s in salts)
+    oc = orc.Circuit(circ["common"], circ["digest"], circ["constants_sigmas"], threads=4)
+    want = oc.prove(circ["wires"], circ["public_inputs"], salts)
+    gc = qpzk.Circuit(ctx, circ["common"], circ["digest"], circ["constants_sigmas"])
+    assert gc.prove(circ["wires"], circ["public_inputs"], seed=seed) == want
+    assert gc.prove(circ["wires"], circ["public_inputs"], salts) == want          # explicit salts: same bytes
+    other = gc.prove(circ["wires"], circ["public_inputs"], seed=seed + np.uint64(1))
+    assert other != want                                                           # another seed, another proof
+    rc, _ = orc.verify(circ["common"], gc.verifier_only_bytes(), other)
+    assert rc == 0
+    with pytest.raises(ValueError):                                                # a seed is 4 words
+        gc.prove(circ["wires"], circ["public_inputs"], seed=seed[:3])
+    gc.free()
