@@ -656,15 +656,20 @@ __global__ void k_ext_powers(const u64* __restrict__ zp /* [2], device */, u64 n
   pw[2 * m] = gl_canon(r.a);
   pw[2 * m + 1] = gl_canon(r.b);
 }
-// One CTA per polynomial: out[p] = sum_m coeffs[p][m] * pw[m].
+// out[p] = sum_m coeffs[p][m] * pw[m]. grid (polynomials, chunks): CTA (p, c) sums coefficients
+// [c * chunk, (c + 1) * chunk) of polynomial p. With one chunk the result goes straight to out; with several
+// (long polynomials: one CTA per polynomial left a 2^18-coefficient opening at 1.7 waves of 8 warps per SM,
+// 2.7 ms for 255 polynomials) the partial sums go to part[p][c] and k_eval_reduce adds them up.
 __global__ void __launch_bounds__(256)
-k_eval_at_ext(const u64* __restrict__ coeffs, u64 n, const u64* __restrict__ pw, u64* __restrict__ out /*[.][2]*/) {
+k_eval_at_ext(const u64* __restrict__ coeffs, u64 n, u64 chunk, const u64* __restrict__ pw, u64* __restrict__ out /*[.][2]*/,
+              u64* __restrict__ part /*[.][chunks][2]*/) {
   __shared__ u64 sa[256], sb[256];
   const u64* c = coeffs + (u64)blockIdx.x * n;
+  const u64 lo = (u64)blockIdx.y * chunk, hi = lo + chunk < n ? lo + chunk : n;
   Acc160 a, b;
   acc_init(a);
   acc_init(b);
-  for (u64 m = threadIdx.x; m < n; m += blockDim.x) {
+  for (u64 m = lo + threadIdx.x; m < hi; m += blockDim.x) {
     u64 v = c[m];
     acc_mac(a, v, pw[2 * m]);
     acc_mac(b, v, pw[2 * m + 1]);
@@ -680,9 +685,21 @@ k_eval_at_ext(const u64* __restrict__ coeffs, u64 n, const u64* __restrict__ pw,
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out[2 * blockIdx.x] = gl_canon(sa[0]);
-    out[2 * blockIdx.x + 1] = gl_canon(sb[0]);
+    u64* o = gridDim.y == 1 ? out + 2 * (u64)blockIdx.x : part + 2 * ((u64)blockIdx.x * gridDim.y + blockIdx.y);
+    o[0] = gl_canon(sa[0]);
+    o[1] = gl_canon(sb[0]);
   }
+}
+__global__ void k_eval_reduce(const u64* __restrict__ part, u32 npolys, u32 chunks, u64* __restrict__ out) {
+  const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npolys) return;
+  u64 a = 0, b = 0;
+  for (u32 c = 0; c < chunks; c++) {
+    a = gl_add(a, part[2 * ((u64)p * chunks + c)]);
+    b = gl_add(b, part[2 * ((u64)p * chunks + c) + 1]);
+  }
+  out[2 * p] = gl_canon(a);
+  out[2 * p + 1] = gl_canon(b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -759,6 +776,87 @@ k_divide_by_linear(const u64* __restrict__ p, u64* __restrict__ q, u64 n, const 
     }
   }
   if (hi == n && lo < hi) {
+    q[n - 1] = 0;
+    q[2 * n - 1] = 0;
+  }
+}
+
+// The same division for long polynomials, spread over the machine (one CTA walked 2^18 coefficients in 1.2 ms):
+// every thread of the grid owns a segment of `per` coefficients.
+//   k_divlin_local : the segment's affine map x -> L + Z x (L = its Horner value, Z = z^per), to maps[t] = (L, Z)
+//   k_divlin_scan  : ONE CTA turns the maps into the carries: carry[t] = value entering segment t from above
+//                    (suffix composition over all T segments: each thread folds a run of them, then the
+//                    1024-wide shared-memory scan above, then the runs are replayed)
+//   k_divlin_apply : the segment replayed from its carry, q written
+struct DivMap {
+  u64 la, lb, za, zb;
+};
+__global__ void __launch_bounds__(256)
+k_divlin_local(const u64* __restrict__ p, u64 n, u64 per, const u64* __restrict__ zp, DivMap* __restrict__ maps) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 lo = t * per;
+  if (lo >= n) return;
+  const u64 hi = lo + per < n ? lo + per : n;
+  const gl2 z = gl2_make(__ldg(zp), __ldg(zp + 1));
+  gl2 acc = gl2_make(0, 0), zl = gl2_make(1, 0);
+  for (u64 m = hi; m-- > lo;) {
+    acc = gl2_add(gl2_make(p[m], p[n + m]), gl2_mul(z, acc));
+    zl = gl2_mul(zl, z);
+  }
+  DivMap o;
+  o.la = acc.a; o.lb = acc.b; o.za = zl.a; o.zb = zl.b;
+  maps[t] = o;
+}
+// maps[T] -> carry[T][2] (carry into segment t = composition of segments t+1 .. T-1 applied to 0)
+__global__ void __launch_bounds__(1024)
+k_divlin_scan(const DivMap* __restrict__ maps, u64 T, u64* __restrict__ carry) {
+  __shared__ u64 la[1024], lb[1024], za[1024], zb[1024];
+  const u32 t = threadIdx.x, NT = blockDim.x;
+  const u64 run = (T + NT - 1) / NT;
+  const u64 lo = (u64)t * run < T ? (u64)t * run : T, hi = lo + run < T ? lo + run : T;
+  // this thread's run as one map: f_lo o f_{lo+1} o ... o f_{hi-1}
+  gl2 L = gl2_make(0, 0), Z = gl2_make(1, 0);
+  for (u64 i = hi; i-- > lo;) {  // prepend f_i: f_i(L + Z x) = L_i + Z_i L + Z_i Z x
+    const gl2 Li = gl2_make(maps[i].la, maps[i].lb), Zi = gl2_make(maps[i].za, maps[i].zb);
+    L = gl2_add(Li, gl2_mul(Zi, L));
+    Z = gl2_mul(Zi, Z);
+  }
+  for (u32 d = 1; d < NT; d <<= 1) {  // inclusive suffix scan over the runs
+    la[t] = L.a; lb[t] = L.b; za[t] = Z.a; zb[t] = Z.b;
+    __syncthreads();
+    if (t + d < NT) {
+      gl2 L2 = gl2_make(la[t + d], lb[t + d]), Z2 = gl2_make(za[t + d], zb[t + d]);
+      L = gl2_add(L, gl2_mul(Z, L2));
+      Z = gl2_mul(Z, Z2);
+    }
+    __syncthreads();
+  }
+  la[t] = L.a; lb[t] = L.b;
+  __syncthreads();
+  gl2 acc = t + 1 < NT ? gl2_make(la[t + 1], lb[t + 1]) : gl2_make(0, 0);  // carry into the last segment of the run
+  for (u64 i = hi; i-- > lo;) {
+    carry[2 * i] = gl_canon(acc.a);
+    carry[2 * i + 1] = gl_canon(acc.b);
+    acc = gl2_add(gl2_make(maps[i].la, maps[i].lb), gl2_mul(gl2_make(maps[i].za, maps[i].zb), acc));
+  }
+}
+__global__ void __launch_bounds__(256)
+k_divlin_apply(const u64* __restrict__ p, u64* __restrict__ q, u64 n, u64 per, const u64* __restrict__ zp,
+               const u64* __restrict__ carry) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 lo = t * per;
+  if (lo >= n) return;
+  const u64 hi = lo + per < n ? lo + per : n;
+  const gl2 z = gl2_make(__ldg(zp), __ldg(zp + 1));
+  gl2 acc = gl2_make(carry[2 * t], carry[2 * t + 1]);
+  for (u64 m = hi; m-- > lo;) {
+    acc = gl2_add(gl2_make(p[m], p[n + m]), gl2_mul(z, acc));
+    if (m > 0) {
+      q[m - 1] = gl_canon(acc.a);
+      q[n + m - 1] = gl_canon(acc.b);
+    }
+  }
+  if (hi == n) {
     q[n - 1] = 0;
     q[2 * n - 1] = 0;
   }

@@ -445,6 +445,45 @@ static int grind_pow(qpzk_ctx* c, const PowState& ps, u32 pos, u32 min_lz, u64* 
   return QPZK_OK;
 }
 
+// OpeningSet::new for `npolys` coefficient columns at the point whose powers are pw: polynomials longer than 2^15
+// coefficients are split over several CTAs (k_eval_at_ext / k_eval_reduce)
+static int launch_eval_at_ext(qpzk_ctx* c, const u64* coeffs, u32 npolys, u64 n, const u64* pw, u64* out) {
+  if (!npolys) return QPZK_OK;
+  const u64 chunk = n > (1ull << 15) ? (1ull << 13) : n;
+  const u32 chunks = (u32)((n + chunk - 1) / chunk);
+  if (chunks == 1) {
+    k_eval_at_ext<<<dim3(npolys, 1), 256, 0, c->stream>>>(coeffs, n, chunk, pw, out, nullptr);
+    c->launches++;
+  } else {
+    DevBuf part(c);
+    QP(part.alloc((size_t)npolys * chunks * 16));
+    k_eval_at_ext<<<dim3(npolys, chunks), 256, 0, c->stream>>>(coeffs, n, chunk, pw, out, part.p);
+    k_eval_reduce<<<(npolys + 127) / 128, 128, 0, c->stream>>>(part.p, npolys, chunks, out);
+    c->launches += 2;
+  }
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+// divide_by_linear: one CTA up to 2^15 coefficients, the three-phase grid-wide form above that
+static int launch_divide_by_linear(qpzk_ctx* c, const u64* p, u64* q, u64 n, const u64* z_dev) {
+  if (n <= (1ull << 15)) {
+    k_divide_by_linear<<<1, 1024, 0, c->stream>>>(p, q, n, z_dev);
+    c->launches++;
+    CU(cudaGetLastError());
+    return QPZK_OK;
+  }
+  const u64 per = 16, T = (n + per - 1) / per;
+  DevBuf maps(c), carry(c);
+  QP(maps.alloc(T * sizeof(DivMap)));
+  QP(carry.alloc(T * 16));
+  k_divlin_local<<<(unsigned)((T + 255) / 256), 256, 0, c->stream>>>(p, n, per, z_dev, reinterpret_cast<DivMap*>(maps.p));
+  k_divlin_scan<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const DivMap*>(maps.p), T, carry.p);
+  k_divlin_apply<<<(unsigned)((T + 255) / 256), 256, 0, c->stream>>>(p, q, n, per, z_dev, carry.p);
+  c->launches += 3;
+  CU(cudaGetLastError());
+  return QPZK_OK;
+}
+
 static u32 pow_grid_blocks(u32 min_lz) {  // candidates per sweep of k_pow_grind_dev ~ the expected witness
   const u32 lg = min_lz < 12 ? 12 : (min_lz > 16 ? 16 : min_lz);
   return (1u << lg) / 128;
@@ -477,9 +516,9 @@ int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point, uint64_t* ou
   w.w[1] = point[1];
   k_set_words<<<1, 32, 0, c->stream>>>(pt.p, w, 2);
   k_ext_powers<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pt.p, n, zpow.p);
-  k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, res.p);
-  c->launches += 3;
+  c->launches += 2;
   CU(cudaGetLastError());
+  QP(launch_eval_at_ext(c, b->coeffs, b->ncols, n, zpow.p, res.p));
   CU(cudaMemcpyAsync(out, res.p, (size_t)b->ncols * 16, cudaMemcpyDeviceToHost, c->stream));
   CU(ctx_wait(c));
   return QPZK_OK;
@@ -705,10 +744,11 @@ static int fri_begin(qpzk_circuit* q, const qpzk_batch* const* oracles, const u6
   k_ext_powers<<<(unsigned)((total_polys + 127) / 128), 128, 0, c->stream>>>(alpha_dev, total_polys, apow.p);  // alpha^j
   k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl0, n, apow.p, comp0.p);
   k_fri_compose<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(pl1, n, apow.p, comp1.p);
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp0.p, q0.p, n, zeta_dev);
-  k_divide_by_linear<<<1, 1024, 0, c->stream>>>(comp1.p, q1.p, n, zeta_next_dev);
+  c->launches += 3;
+  QP(launch_divide_by_linear(c, comp0.p, q0.p, n, zeta_dev));
+  QP(launch_divide_by_linear(c, comp1.p, q1.p, n, zeta_next_dev));
   k_ext_axpy<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(q0.p, q1.p, apow.p + 2ull * nch, n, F->fpoly);
-  c->launches += 6;
+  c->launches++;
   CU(cudaGetLastError());
   F->coeffs_cur = F->fpoly;
   F->cur_n = n;
@@ -1061,13 +1101,10 @@ struct qpzk_sprove {
       c->launches += 2;
       u32 off = 0;
       for (auto* b : oracles) {
-        k_eval_at_ext<<<b->ncols, 256, 0, c->stream>>>(b->coeffs, n, zpow.p, open_dev + 2ull * off);
+        QP(launch_eval_at_ext(c, b->coeffs, b->ncols, n, zpow.p, open_dev + 2ull * off));
         off += b->ncols;
-        c->launches++;
       }
-      k_eval_at_ext<<<nch, 256, 0, c->stream>>>(zs_b->coeffs, n, zpow_next.p, open_dev + 2ull * off);
-      c->launches++;
-      CU(cudaGetLastError());
+      QP(launch_eval_at_ext(c, zs_b->coeffs, nch, n, zpow_next.p, open_dev + 2ull * off));
       tr_step(c, T, open_dev, 2 * (total_polys + nch), 0, 0, nullptr, 2, QPZK_TR_OFF(fri_alpha), 0, 0, 0, 0);
     }
     CU(cudaEventRecord(q->ev[4], c->stream));  // stage 3: openings
