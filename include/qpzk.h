@@ -163,6 +163,14 @@ int qpzk_batch_from_values_shard_dev(qpzk_ctx* ctx, const uint64_t* values_dev, 
                                      uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                      const uint64_t* salts_dev, uint32_t salt_cols,
                                      uint32_t subtree_begin, uint32_t subtree_end, qpzk_batch** out);
+/* The same, ENQUEUED only: the call returns without waiting for the context's stream, the handle is valid for
+ * stream-ordered use on the same context at once (an NCCL all-gather on qpzk_batch_cap_dev issued on
+ * qpzk_ctx_stream follows the commit without a host round trip); synchronise (qpzk_ctx_sync, or any blocking
+ * accessor) before reading results on the host. Per-stage times are not collected. */
+int qpzk_batch_from_values_shard_dev_async(qpzk_ctx* ctx, const uint64_t* values_dev, uint32_t ncols,
+                                           uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
+                                           const uint64_t* salts_dev, uint32_t salt_cols,
+                                           uint32_t subtree_begin, uint32_t subtree_end, qpzk_batch** out);
 int qpzk_batch_from_coeffs_shard_dev(qpzk_ctx* ctx, const uint64_t* coeffs_dev, uint32_t ncols,
                                      uint32_t degree_bits, uint32_t rate_bits, uint32_t cap_height,
                                      const uint64_t* salts_dev, uint32_t salt_cols,

@@ -904,6 +904,16 @@ int qpzk_batch_from_values_shard_dev(qpzk_ctx* c, const uint64_t* values, uint32
                        subtree_begin, subtree_end);
   });
 }
+int qpzk_batch_from_values_shard_dev_async(qpzk_ctx* c, const uint64_t* values, uint32_t ncols, uint32_t degree_bits,
+                                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
+                                           uint32_t salt_cols, uint32_t subtree_begin, uint32_t subtree_end,
+                                           qpzk_batch** out) {
+  if (subtree_end == 0) return fail(QPZK_ERR_BAD_ARG, "empty subtree range");
+  return guarded([&] {
+    return commit_impl(c, values, false, false, ncols, degree_bits, rate_bits, cap_height, salts, false, salt_cols, out,
+                       subtree_begin, subtree_end, false);
+  });
+}
 int qpzk_batch_from_coeffs_shard_dev(qpzk_ctx* c, const uint64_t* coeffs, uint32_t ncols, uint32_t degree_bits,
                                      uint32_t rate_bits, uint32_t cap_height, const uint64_t* salts,
                                      uint32_t salt_cols, uint32_t subtree_begin, uint32_t subtree_end,

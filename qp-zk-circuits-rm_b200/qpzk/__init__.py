@@ -88,6 +88,8 @@ def load_library():
         "qpzk_measure_imad_peak": (i, [_vp, i, ctypes.POINTER(ctypes.c_double)]),
         "qpzk_batch_from_coeffs_shard_dev": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, u32, u32,
                                                  ctypes.POINTER(_vp)]),
+        "qpzk_batch_from_values_shard_dev_async": (i, [_vp, _vp, u32, u32, u32, u32, _vp, u32, u32, u32,
+                                                       ctypes.POINTER(_vp)]),
         "qpzk_circuit_create": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, _vp, ctypes.c_size_t,
                                     ctypes.POINTER(_vp)]),
         "qpzk_circuit_cap": (i, [_vp, _u64p, ctypes.c_size_t]),
@@ -347,15 +349,17 @@ class PolynomialBatch:
 
     @classmethod
     def from_values_shard_dev(cls, ctx, dev_ptr, ncols, n, rate_bits, cap_height, subtree_begin, subtree_end,
-                              salts=None):
-        """One rank's part of a multi-GPU commit: cap subtrees [subtree_begin, subtree_end) only."""
+                              salts=None, enqueue_only=False):
+        """One rank's part of a multi-GPU commit: cap subtrees [subtree_begin, subtree_end) only.
+        enqueue_only: return without waiting for the stream (qpzk_batch_from_values_shard_dev_async)."""
         L = load_library()
         k = n.bit_length() - 1
         sptr = _vp(salts[0]) if salts is not None else None
         salt_cols = salts[1] if salts is not None else 0
         h = _vp()
-        _check(L.qpzk_batch_from_values_shard_dev(ctx._h, _vp(dev_ptr), ncols, k, rate_bits, cap_height, sptr,
-                                                  salt_cols, subtree_begin, subtree_end, ctypes.byref(h)))
+        fn = L.qpzk_batch_from_values_shard_dev_async if enqueue_only else L.qpzk_batch_from_values_shard_dev
+        _check(fn(ctx._h, _vp(dev_ptr), ncols, k, rate_bits, cap_height, sptr, salt_cols, subtree_begin, subtree_end,
+                  ctypes.byref(h)))
         b = PolynomialBatch(ctx, h, ncols, k, rate_bits, cap_height, salt_cols)
         b.subtrees = (subtree_begin, subtree_end)
         return b

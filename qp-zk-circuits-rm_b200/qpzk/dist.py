@@ -30,9 +30,21 @@ class _DevArray:
                                          "version": 3, "strides": None}
 
 
-def allgather_cap_nccl(batch, group=None):
+_EXT_STREAMS = {}
+
+
+def _ext_stream(ctx):
+    """torch view of the qpzk context's CUDA stream (cached per context)."""
+    import torch
+    key = (ctx.device, ctx.stream)
+    if key not in _EXT_STREAMS:
+        _EXT_STREAMS[key] = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device))
+    return _EXT_STREAMS[key]
+
+
+def allgather_cap_nccl(batch, group=None, sync=True):
     """In-place NCCL all-gather of the subtree roots on the device cap of `batch` (every rank ends up
-    with the full cap). Returns the torch view of the cap (int64 words)."""
+    with the full cap), on the context's own stream. Returns the torch view of the cap (int64 words)."""
     import torch
     import torch.distributed as dist
 
@@ -45,9 +57,10 @@ def allgather_cap_nccl(batch, group=None):
     if (b * 4, e * 4) != (rank * per, (rank + 1) * per):
         raise ValueError("subtree range does not match the rank's slot in the all-gather")
     # on the context's own stream: ordered after the commit, no host synchronisation in between
-    with torch.cuda.stream(torch.cuda.ExternalStream(batch.ctx.stream, device=torch.device("cuda", batch.ctx.device))):
+    with torch.cuda.stream(_ext_stream(batch.ctx)):
         dist.all_gather_into_tensor(t, t[rank * per:(rank + 1) * per], group=group)
-    batch.ctx.sync()
+    if sync:
+        batch.ctx.sync()
     return t
 
 
@@ -70,7 +83,7 @@ def _stream_ctx(ctx):
     """torch stream context over the qpzk context's own CUDA stream, so that a collective is ordered after the
     phase just enqueued and before the next one without any host synchronisation."""
     import torch
-    return torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", ctx.device)))
+    return torch.cuda.stream(_ext_stream(ctx))
 
 
 def exchange_nccl(proof, group=None):

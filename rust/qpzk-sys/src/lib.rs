@@ -55,6 +55,7 @@ extern "C" {
     pub fn qpzk_batch_from_values_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_from_coeffs_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_from_values_shard_dev(ctx: *mut qpzk_ctx, values_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_batch) -> c_int;
+    pub fn qpzk_batch_from_values_shard_dev_async(ctx: *mut qpzk_ctx, values_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_from_coeffs_shard_dev(ctx: *mut qpzk_ctx, coeffs_dev: *const u64, ncols: u32, degree_bits: u32, rate_bits: u32, cap_height: u32, salts_dev: *const u64, salt_cols: u32, subtree_begin: u32, subtree_end: u32, out_: *mut *mut qpzk_batch) -> c_int;
     pub fn qpzk_batch_cap(b: *const qpzk_batch, out_: *mut u64) -> c_int;
     pub fn qpzk_batch_cap_dev(b: *mut qpzk_batch) -> *mut u64;
