@@ -193,6 +193,21 @@ int qpzk_batch_open(const qpzk_batch* b, uint64_t leaf_index, uint64_t* leaf_out
 /* Full materialisation (compatibility / debugging): `merkle_tree.leaves` row-major
  * [N][ncols+salt_cols] and `merkle_tree.digests` in plonky2's layout. Either may be NULL. */
 int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests);
+/* PolynomialBatch <-> bytes in the layout of plonky2's `Write::write_polynomial_batch` /
+ * `Read::read_polynomial_batch` (qp-plonky2 util/serialization): polynomials (count, then length + coefficients
+ * each) | merkle_tree (leaf count, then length + elements each; digest count + digests in plonky2's layout; cap
+ * height + cap) | degree_log | rate_bits | blinding (1 byte). This is the `constants_sigmas_commitment` field of
+ * the serialized ProverOnlyCircuitData that `WormholeProver::new_from_files`
+ * (/root/reference/wormhole/prover/src/lib.rs:105-187) reads, so a prover restored from files puts the
+ * commitment on the device WITHOUT recomputing it. from_bytes checks every length against the
+ * others (QPZK_ERR_BAD_ARG on a mismatch or a truncated buffer) and copies; with QPZK_IMPORT_VERIFY it also
+ * recomputes the LDE and the tree on the device and refuses bytes that are not the commitment of the
+ * polynomials they carry. `consumed` (may be NULL) receives the number of bytes read. */
+#define QPZK_IMPORT_VERIFY 1u
+int qpzk_batch_serialized_size(const qpzk_batch* b, uint64_t* nbytes);
+int qpzk_batch_to_bytes(const qpzk_batch* b, uint8_t* out, uint64_t capacity);
+int qpzk_batch_from_bytes(qpzk_ctx* ctx, const uint8_t* bytes, uint64_t nbytes, uint32_t flags, qpzk_batch** out,
+                          uint64_t* consumed);
 /* `OpeningSet::new` for one oracle (qp-plonky2 plonk/proof.rs, reached from prove() at
  * /root/reference/wormhole/prover/src/lib.rs:233-237): every committed polynomial evaluated at an
  * extension-field point; out = [ncols][2]. */
@@ -219,6 +234,18 @@ typedef struct qpzk_circuit qpzk_circuit;
 int qpzk_circuit_create(qpzk_ctx* ctx, const uint8_t* common_bytes, size_t common_len,
                         const uint64_t* circuit_digest /* [4] */, const uint64_t* constants_sigmas,
                         size_t constants_sigmas_words, qpzk_circuit** out);
+/* The same circuit from a prover restored from files (`WormholeProver::new_from_files`,
+ * /root/reference/wormhole/prover/src/lib.rs:105-187): instead of the value columns the call takes
+ * the serialized `constants_sigmas_commitment` (qpzk_batch_from_bytes layout; flags as there) and puts it on the
+ * device as it is - no transform of 84 columns x 8 cosets, no hashing. Only the value columns the permutation
+ * argument reads are rebuilt, by one forward transform of the stored coefficients. The commitment's shape must
+ * be the one the common data states. qpzk_circuit_commitment_size / _to_bytes write that field for a circuit
+ * created either way (what a patched `ProverOnlyCircuitData::to_bytes` stores). */
+int qpzk_circuit_create_from_commitment(qpzk_ctx* ctx, const uint8_t* common_bytes, size_t common_len,
+                                        const uint64_t* circuit_digest /* [4] */, const uint8_t* commitment_bytes,
+                                        uint64_t commitment_len, uint32_t flags, qpzk_circuit** out);
+int qpzk_circuit_commitment_size(const qpzk_circuit* c, uint64_t* nbytes);
+int qpzk_circuit_commitment_to_bytes(const qpzk_circuit* c, uint8_t* out, uint64_t capacity);
 /* `verifier_only.constants_sigmas_cap`: [2^cap_height][4]; cap_words = capacity of `out` in u64. */
 int qpzk_circuit_cap(const qpzk_circuit* c, uint64_t* out, size_t cap_words);
 /* Shape of the circuit as parsed from the common data: out[0..8) = degree_bits, rate_bits, cap_height,

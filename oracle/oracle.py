@@ -200,6 +200,30 @@ def batch_commit(cols, rate_bits, cap_height, is_coeffs=False, salts=None, threa
     return dict(coeffs=coeffs, leaves=leaves, digests=dig, cap=cap)
 
 
+def batch_to_bytes(commit, rate_bits, blinding):
+    """`Write::write_polynomial_batch` of qp-plonky2 1.1.1 (util/serialization, un-vendored; restated - no
+    fixture of a serialized ProverOnlyCircuitData ships with the reference, so this layout is UNPINNED): the
+    `constants_sigmas_commitment` field read back by `WormholeProver::new_from_files`
+    (/root/reference/wormhole/prover/src/lib.rs:105-187). ``commit`` = the dict batch_commit returns.
+    usize = u64 little-endian, bool = 1 byte; vectors of field elements carry a length, the cap does not."""
+    coeffs, leaves, dig, cap = commit["coeffs"], commit["leaves"], commit["digests"], commit["cap"]
+    ncols, n = coeffs.shape
+    u = lambda v: int(v).to_bytes(8, "little")
+    out = [u(ncols)]
+    for c in range(ncols):
+        out += [u(n), coeffs[c].astype("<u8").tobytes()]
+    N, w = leaves.shape
+    rec = np.empty((N, w + 1), "<u8")
+    rec[:, 0] = w
+    rec[:, 1:] = leaves
+    out += [u(N), rec.tobytes(), u(dig.shape[0] if dig is not None and dig.size else 0)]
+    if dig is not None and dig.size:
+        out.append(dig.astype("<u8").tobytes())
+    out += [u(cap.shape[0].bit_length() - 1), cap.astype("<u8").tobytes(), u(n.bit_length() - 1), u(rate_bits),
+            b"\x01" if blinding else b"\x00"]
+    return b"".join(out)
+
+
 class Challenger:
     def __init__(self):
         self._h = lib().orc_challenger_new()

@@ -524,10 +524,27 @@ int qpzk_batch_eval_ext(const qpzk_batch* b, const uint64_t* point, uint64_t* ou
   return QPZK_OK;
 }
 
-int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len, const uint64_t* digest4,
-                        const uint64_t* constants_sigmas, size_t constants_sigmas_words, qpzk_circuit** out) {
+// out[c][i] = n * in[c][(n - i) mod n]: an inverse transform read backwards is the forward transform
+// (values on the subgroup from coefficients, natural order both sides).
+__global__ void k_forward_from_inverse(const u64* __restrict__ in, u64* __restrict__ out, u32 k, u32 ncols, u64 n_mod_p) {
+  const u64 n = (u64)1 << k;
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (u32 c = blockIdx.y; c < ncols; c += gridDim.y)
+    out[(u64)c * n + i] = gl_canon(gl_mul(in[(u64)c * n + ((n - i) & (n - 1))], n_mod_p));
+}
+
+// constants_sigmas != NULL: the value columns, committed here (CircuitBuilder::build).
+// Otherwise commitment_bytes: the serialized constants_sigmas_commitment of a prover restored from files
+// (`read_polynomial_batch`, qpzk_batch_from_bytes) - nothing is recomputed except the value columns the
+// permutation argument reads, one forward transform of the coefficients.
+static int circuit_create_impl(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len, const uint64_t* digest4,
+                               const uint64_t* constants_sigmas, size_t constants_sigmas_words,
+                               const uint8_t* commitment_bytes, uint64_t commitment_len, uint32_t import_flags,
+                               qpzk_circuit** out) {
   return guarded([&]() -> int {
-    if (!c || !common_bytes || !digest4 || !constants_sigmas || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    if (!c || !common_bytes || !digest4 || (!constants_sigmas && !commitment_bytes) || !out)
+      return fail(QPZK_ERR_BAD_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
     std::unique_ptr<qpzk_circuit> q(new qpzk_circuit());
     q->ctx = c;
@@ -539,7 +556,7 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
     while ((1ull << qdb) < cm.qdf) qdb++;
     const u64 n = 1ull << cm.degree_bits;
     const u32 ncs = (u32)(cm.num_constants + cm.num_routed);
-    if (constants_sigmas_words != (size_t)ncs * n)
+    if (constants_sigmas && constants_sigmas_words != (size_t)ncs * n)
       return fail(QPZK_ERR_BAD_ARG, "constants_sigmas must hold (num_constants + num_routed_wires) * 2^degree_bits words");
     CircuitDesc& d = q->desc;
     memset(&d, 0, sizeof d);
@@ -589,10 +606,25 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
     QP(dev_alloc(c, zh.size() * 8, &q->zh_dev));
     CU(cudaMemcpyAsync(q->zh_dev, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
     QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
-    CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
-    // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
-    QP(commit_impl(c, q->cs_values, false, false, ncs, (u32)cm.degree_bits, (u32)cm.rate_bits, (u32)cm.cap_height, nullptr,
-                   false, 0, &q->cs_batch));
+    if (constants_sigmas) {
+      CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
+      // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
+      QP(commit_impl(c, q->cs_values, false, false, ncs, (u32)cm.degree_bits, (u32)cm.rate_bits, (u32)cm.cap_height, nullptr,
+                     false, 0, &q->cs_batch));
+    } else {
+      QP(qpzk_batch_from_bytes(c, commitment_bytes, commitment_len, import_flags, &q->cs_batch, nullptr));
+      const qpzk_batch* b = q->cs_batch;
+      if (b->ncols != ncs || b->salt_cols != 0 || b->degree_bits != cm.degree_bits || b->rate_bits != cm.rate_bits ||
+          b->cap_height != cm.cap_height)
+        return fail(QPZK_ERR_BAD_ARG, "the serialised constants_sigmas_commitment does not have the shape the common data states");
+      DevBuf tmp(c);
+      QP(tmp.alloc((size_t)ncs * n * 8));
+      QP(launch_ifft(c, b->coeffs, n, tmp.p, n, ncs, (int)cm.degree_bits));  // n^-1 * sum_j c_j w^(-ij)
+      k_forward_from_inverse<<<dim3((unsigned)((n + 255) / 256), ncs < 64 ? ncs : 64), 256, 0, c->stream>>>(
+          tmp.p, q->cs_values, (u32)cm.degree_bits, ncs, n);
+      c->launches++;
+      CU(cudaGetLastError());
+    }
     q->cs_cap.resize(4ull << cm.cap_height);
     QP(qpzk_batch_cap(q->cs_batch, q->cs_cap.data()));
     {
@@ -614,6 +646,28 @@ int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_
     *out = q.release();
     return QPZK_OK;
   });
+}
+
+int qpzk_circuit_create(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len, const uint64_t* digest4,
+                        const uint64_t* constants_sigmas, size_t constants_sigmas_words, qpzk_circuit** out) {
+  if (!constants_sigmas) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  return circuit_create_impl(c, common_bytes, common_len, digest4, constants_sigmas, constants_sigmas_words, nullptr, 0, 0, out);
+}
+int qpzk_circuit_create_from_commitment(qpzk_ctx* c, const uint8_t* common_bytes, size_t common_len,
+                                        const uint64_t* digest4, const uint8_t* commitment_bytes, uint64_t commitment_len,
+                                        uint32_t flags, qpzk_circuit** out) {
+  if (!commitment_bytes) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  return circuit_create_impl(c, common_bytes, common_len, digest4, nullptr, 0, commitment_bytes, commitment_len, flags, out);
+}
+/* `constants_sigmas_commitment` of this circuit in the serialized layout (what a patched
+ * ProverOnlyCircuitData::to_bytes writes for that field). */
+int qpzk_circuit_commitment_size(const qpzk_circuit* q, uint64_t* nbytes) {
+  if (!q) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  return qpzk_batch_serialized_size(q->cs_batch, nbytes);
+}
+int qpzk_circuit_commitment_to_bytes(const qpzk_circuit* q, uint8_t* out, uint64_t capacity) {
+  if (!q) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  return qpzk_batch_to_bytes(q->cs_batch, out, capacity);
 }
 
 int qpzk_circuit_cap(const qpzk_circuit* q, uint64_t* out, size_t cap_words) {

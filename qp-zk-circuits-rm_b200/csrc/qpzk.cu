@@ -1018,6 +1018,240 @@ int qpzk_batch_export(const qpzk_batch* b, uint64_t* leaves, uint64_t* digests) 
   if (digests) return export_digests(c, b->levels, b->log_N(), b->cap_height, digests);
   return QPZK_OK;
 }
+// ---- PolynomialBatch <-> bytes ------------------------------------------------------------------------
+// The layout of plonky2's `Write::write_polynomial_batch` / `Read::read_polynomial_batch`
+// (qp-plonky2 util/serialization, un-vendored - restated, no fixture ships one: SURVEY 8(f).4): the
+// `constants_sigmas_commitment` field of the serialized ProverOnlyCircuitData that
+// /root/reference/wormhole/prover/src/lib.rs:105-187 (`new_from_files`) reads back, so that a prover started
+// from files never recomputes the commit. All integers little-endian u64 unless noted:
+//   polynomials.len(), then per polynomial: coeffs.len(), coeffs
+//   merkle_tree: leaves.len(), then per leaf: len, elements | digests.len(), digests (4 words each, plonky2's
+//                interleaved layout) | cap.height(), 2^height cap hashes
+//   degree_log, rate_bits, blinding (1 byte)
+static const u32 kSaltSize = 4;  // SALT_SIZE of a blinded oracle
+static u64 batch_bytes_len(u32 ncols, u32 width, u32 k, u32 r, u32 h) {
+  const u64 n = (u64)1 << k, N = n << r;
+  return 8 + (u64)ncols * (8 + 8 * n) + 8 + N * (8 + 8 * (u64)width) + 8 + 32 * (2 * N - ((u64)2 << h)) + 8 + ((u64)32 << h) + 17;
+}
+// serialized leaves ([N] records of 1 + width words, the first one the length) -> column-major LDE
+__global__ void k_rows_to_columns(const u64* __restrict__ rec, u64* __restrict__ lde, u64 N, u32 width) {
+  __shared__ u64 tile[32][33];
+  const u64 r0 = (u64)blockIdx.x * 32;
+  const u32 c0 = blockIdx.y * 32;
+  for (u32 rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+    const u32 cc = c0 + threadIdx.x;
+    if (cc < width && r0 + rr < N) tile[rr][threadIdx.x] = rec[(r0 + rr) * (width + 1) + 1 + cc];
+  }
+  __syncthreads();
+  for (u32 cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+    const u64 row = r0 + threadIdx.x;
+    if (c0 + cc < width && row < N) lde[(u64)(c0 + cc) * N + row] = tile[threadIdx.x][cc];
+  }
+}
+// plonky2 `digests` -> level-major (the inverse of k_export_digests: same index map, copy the other way)
+__global__ void k_import_digests(const u64* __restrict__ in, u32 log_n, u32 cap_height, u64* __restrict__ levels) {
+  const u32 L = log_n - cap_height;
+  const u64 total = ((u64)2 << log_n) - ((u64)2 << cap_height);
+  const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const u64 twoN = (u64)2 << log_n;
+  u32 i = 0;
+  while (g >= twoN - (twoN >> (i + 1))) i++;
+  const u64 j = g - (twoN - (twoN >> i));
+  const u32 per_sub_bits = L - i;
+  const u64 sub = j >> per_sub_bits, jj = j & (((u64)1 << per_sub_bits) - 1);
+  const u64 idx = 2 * (((jj >> 1) << (i + 1)) + ((u64)1 << i) - 1) + (jj & 1);
+  const u64 sub_len = ((u64)2 << L) - 2;
+  const ulonglong2* s = reinterpret_cast<const ulonglong2*>(in + (sub * sub_len + idx) * 4);
+  ulonglong2* d = reinterpret_cast<ulonglong2*>(levels + g * 4);
+  d[0] = s[0];
+  d[1] = s[1];
+}
+// counts words that differ or are not canonical
+__global__ void k_count_mismatch(const u64* __restrict__ a, const u64* __restrict__ b, u64 n, unsigned long long* out) {
+  u64 bad = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+    bad += (a[i] != b[i]) || a[i] >= GL_P;
+  if (bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+int qpzk_batch_serialized_size(const qpzk_batch* b, uint64_t* nbytes) {
+  if (!b || !nbytes) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+  if (b->sharded()) return fail(QPZK_ERR_UNSUPPORTED, "a shard holds only its own leaves: serialise the unsharded batch");
+  *nbytes = batch_bytes_len(b->ncols, b->width(), b->degree_bits, b->rate_bits, b->cap_height);
+  return QPZK_OK;
+}
+
+int qpzk_batch_to_bytes(const qpzk_batch* b, uint8_t* out, uint64_t capacity) {
+  return guarded([&]() -> int {
+    uint64_t need = 0;
+    QP(qpzk_batch_serialized_size(b, &need));
+    if (!out || capacity < need) return fail(QPZK_ERR_BAD_ARG, "buffer too small for the serialised batch");
+    qpzk_ctx* c = b->ctx;
+    CU(cudaSetDevice(c->device));
+    const u64 n = (u64)1 << b->degree_bits, N = (u64)1 << b->log_N();
+    const u32 w = b->width();
+    const u64 ndig = 2 * N - ((u64)2 << b->cap_height);
+    uint8_t* p = out;
+    auto put = [&](u64 v) { memcpy(p, &v, 8); p += 8; };
+    put(b->ncols);
+    for (u32 i = 0; i < b->ncols; i++) {
+      put(n);
+      CU(cudaMemcpyAsync(p, b->coeffs + (u64)i * n, n * 8, cudaMemcpyDeviceToHost, c->stream));
+      p += n * 8;
+    }
+    put(N);
+    {  // rows, each behind its length
+      std::vector<u64> rows((size_t)N * w);
+      QP(qpzk_batch_export(b, rows.data(), nullptr));
+      for (u64 i = 0; i < N; i++) {
+        put(w);
+        memcpy(p, rows.data() + i * w, (size_t)w * 8);
+        p += (size_t)w * 8;
+      }
+    }
+    put(ndig);
+    QP(export_digests(c, b->levels, b->log_N(), b->cap_height, reinterpret_cast<uint64_t*>(p)));  // waits for the stream
+    p += ndig * 32;
+    put(b->cap_height);
+    CU(cudaMemcpyAsync(p, cap_ptr(b->levels, b->log_N(), b->cap_height), (size_t)32 << b->cap_height, cudaMemcpyDeviceToHost,
+                       c->stream));
+    p += (size_t)32 << b->cap_height;
+    put(b->degree_bits);
+    put(b->rate_bits);
+    *p++ = b->salt_cols ? 1 : 0;
+    CU(ctx_wait(c));
+    if ((uint64_t)(p - out) != need) return fail(QPZK_ERR_CUDA, "internal error: serialised length");
+    return QPZK_OK;
+  });
+}
+
+// Nothing is recomputed: coefficients, leaves and digests go to the device as they are (what plonky2's
+// `read_polynomial_batch` does on the host). The bytes are untrusted as far as SHAPES go - every length is
+// checked against the others before anything is allocated - but, like plonky2, the digests are taken on
+// trust unless QPZK_IMPORT_VERIFY asks for the check: LDE of the coefficients == the leaves' polynomial
+// columns, Merkle tree of the leaves == the digests and the cap, every word canonical.
+int qpzk_batch_from_bytes(qpzk_ctx* c, const uint8_t* bytes, uint64_t nbytes, uint32_t flags, qpzk_batch** out,
+                          uint64_t* consumed) {
+  return guarded([&]() -> int {
+    if (!c || !bytes || !out) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const uint8_t* p = bytes;
+    const uint8_t* const end = bytes + nbytes;
+    bool short_read = false;
+    auto get = [&]() -> u64 {
+      if ((uint64_t)(end - p) < 8) { short_read = true; return 0; }
+      u64 v;
+      memcpy(&v, p, 8);
+      p += 8;
+      return v;
+    };
+    const char* trunc = "serialised PolynomialBatch: truncated";
+    const u64 ncols64 = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (ncols64 == 0 || ncols64 > 4096) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: bad polynomial count");
+    const u32 ncols = (u32)ncols64;
+    const u64 n = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (!is_pow2(n) || n > ((u64)1 << 30)) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: polynomial length must be a power of two");
+    const u32 k = ilog2(n);
+    if ((uint64_t)(end - bytes) < 8 + (u64)ncols * (8 + 8 * n)) return fail(QPZK_ERR_BAD_ARG, trunc);
+    const uint8_t* const coeffs0 = p;  // the first polynomial's coefficients; the others follow, each behind its length
+    p += 8 * n;
+    for (u32 i = 1; i < ncols; i++) {
+      if (get() != n) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: polynomials differ in length");
+      p += 8 * n;
+    }
+    const u64 N = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (!is_pow2(N) || N < n || N > ((u64)1 << 30)) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: bad leaf count");
+    const u32 r = ilog2(N) - k;
+    const u64 w64 = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (w64 != ncols && w64 != ncols + kSaltSize) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: leaf width must be the polynomial count (+ 4 salts)");
+    const u32 w = (u32)w64;
+    p -= 8;
+    const uint8_t* const leaves0 = p;  // N records of (w + 1) words
+    if ((uint64_t)(end - p) < N * 8 * (w + 1)) return fail(QPZK_ERR_BAD_ARG, trunc);
+    for (u64 i = 0; i < N; i++) {
+      u64 len;
+      memcpy(&len, p + i * 8 * (w + 1), 8);
+      if (len != w) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: leaves differ in length");
+    }
+    p += N * 8 * (w + 1);
+    const u64 ndig = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (ndig > 2 * N || (uint64_t)(end - p) < ndig * 32) return fail(QPZK_ERR_BAD_ARG, trunc);
+    const uint8_t* const dig0 = p;
+    p += ndig * 32;
+    const u64 h64 = get();
+    if (short_read) return fail(QPZK_ERR_BAD_ARG, trunc);
+    if (h64 > k + r || ndig != 2 * N - ((u64)2 << h64)) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: digest count does not match the cap height");
+    const u32 h = (u32)h64;
+    if ((uint64_t)(end - p) < ((u64)32 << h) + 17) return fail(QPZK_ERR_BAD_ARG, trunc);
+    const uint8_t* const cap0 = p;
+    p += (u64)32 << h;
+    const u64 degree_log = get(), rate_bits = get();
+    const uint8_t blinding = *p++;
+    if (degree_log != k || rate_bits != r || blinding > 1 || (blinding ? w != ncols + kSaltSize : w != ncols))
+      return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: degree_log / rate_bits / blinding contradict the vectors");
+
+    std::unique_ptr<qpzk_batch> b(new qpzk_batch());
+    b->ctx = c;
+    b->ncols = ncols;
+    b->salt_cols = w - ncols;
+    b->degree_bits = k;
+    b->rate_bits = r;
+    b->cap_height = h;
+    b->leaf0 = 0;
+    b->leaf1 = N;
+    b->lde_stride = N;
+    QP(dev_alloc(c, (size_t)ncols * n * 8, &b->coeffs));
+    QP(dev_alloc(c, (size_t)w * N * 8, &b->lde_alloc));
+    b->lde = b->lde_alloc;
+    QP(dev_alloc(c, (size_t)N * 2 * 32, &b->levels));
+    // one strided copy drops the length word in front of every polynomial
+    CU(cudaMemcpy2DAsync(b->coeffs, n * 8, coeffs0, (n + 1) * 8, n * 8, ncols, cudaMemcpyHostToDevice, c->stream));
+    {
+      DevBuf rec(c), dig(c);
+      QP(rec.alloc((size_t)N * (w + 1) * 8));
+      CU(cudaMemcpyAsync(rec.p, leaves0, (size_t)N * (w + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+      k_rows_to_columns<<<dim3((unsigned)((N + 31) / 32), (w + 31) / 32), dim3(32, 8), 0, c->stream>>>(rec.p, b->lde, N, w);
+      c->launches++;
+      if (ndig) {
+        QP(dig.alloc((size_t)ndig * 32));
+        CU(cudaMemcpyAsync(dig.p, dig0, (size_t)ndig * 32, cudaMemcpyHostToDevice, c->stream));
+        k_import_digests<<<(unsigned)((ndig + 255) / 256), 256, 0, c->stream>>>(dig.p, k + r, h, b->levels);
+        c->launches++;
+      }
+      CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(const_cast<u64*>(cap_ptr(b->levels, k + r, h)), cap0, (size_t)32 << h, cudaMemcpyHostToDevice, c->stream));
+    if (flags & QPZK_IMPORT_VERIFY) {
+      DevBuf lde2(c), lev2(c), cnt(c);
+      QP(lde2.alloc((size_t)ncols * N * 8));
+      QP(lev2.alloc((size_t)N * 2 * 32));
+      QP(cnt.alloc(8));
+      CU(cudaMemsetAsync(cnt.p, 0, 8, c->stream));
+      QP(launch_lde(c, b->coeffs, n, lde2.p, N, ncols, (int)k, (int)r));
+      QP(build_tree(c, b->lde, 1, N, w, k + r, h, lev2.p, nullptr));
+      k_count_mismatch<<<c->sm_count * 4, 256, 0, c->stream>>>(b->lde, lde2.p, (u64)ncols * N, (unsigned long long*)cnt.p);
+      k_count_mismatch<<<c->sm_count * 4, 256, 0, c->stream>>>(b->levels, lev2.p, (2 * N - ((u64)1 << h)) * 4, (unsigned long long*)cnt.p);
+      k_count_mismatch<<<c->sm_count * 4, 256, 0, c->stream>>>(b->coeffs, b->coeffs, (u64)ncols * n, (unsigned long long*)cnt.p);
+      c->launches += 3;
+      CU(cudaGetLastError());
+      unsigned long long bad = 0;
+      CU(cudaMemcpyAsync(&bad, cnt.p, 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(ctx_wait(c));
+      if (bad) return fail(QPZK_ERR_BAD_ARG, "serialised PolynomialBatch: leaves / digests / cap are not the commitment of the polynomials");
+    }
+    CU(ctx_wait(c));  // the host bytes are borrowed for the call only
+    if (consumed) *consumed = (uint64_t)(p - bytes);
+    *out = b.release();
+    return QPZK_OK;
+  });
+}
+
 uint32_t qpzk_batch_ncols(const qpzk_batch* b) { return b ? b->ncols : 0; }
 uint32_t qpzk_batch_width(const qpzk_batch* b) { return b ? b->width() : 0; }
 uint32_t qpzk_batch_degree_bits(const qpzk_batch* b) { return b ? b->degree_bits : 0; }

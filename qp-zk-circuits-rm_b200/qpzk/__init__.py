@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("QPZK_LIB") or os.path.join(_PKG, "libqpzk.so")   # QP
 
 P = 0xFFFFFFFF00000001
 SALT_SIZE = 4
+IMPORT_VERIFY = 1  # QPZK_IMPORT_VERIFY
 STAGES = ("h2d", "ifft", "lde", "leaf_hash", "merkle_levels", "d2h")
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
@@ -92,6 +93,13 @@ def load_library():
                                                        ctypes.POINTER(_vp)]),
         "qpzk_circuit_create": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, _vp, ctypes.c_size_t,
                                     ctypes.POINTER(_vp)]),
+        "qpzk_circuit_create_from_commitment": (i, [_vp, ctypes.c_char_p, ctypes.c_size_t, _u64p, ctypes.c_char_p, u64, u32,
+                                                    ctypes.POINTER(_vp)]),
+        "qpzk_circuit_commitment_size": (i, [_vp, ctypes.POINTER(u64)]),
+        "qpzk_circuit_commitment_to_bytes": (i, [_vp, ctypes.c_char_p, u64]),
+        "qpzk_batch_serialized_size": (i, [_vp, ctypes.POINTER(u64)]),
+        "qpzk_batch_to_bytes": (i, [_vp, ctypes.c_char_p, u64]),
+        "qpzk_batch_from_bytes": (i, [_vp, ctypes.c_char_p, u64, u32, ctypes.POINTER(_vp), ctypes.POINTER(u64)]),
         "qpzk_circuit_cap": (i, [_vp, _u64p, ctypes.c_size_t]),
         "qpzk_circuit_info": (i, [_vp, _u32p]),
         "qpzk_circuit_verifier_only": (ctypes.c_size_t, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
@@ -364,6 +372,36 @@ class PolynomialBatch:
         b.subtrees = (subtree_begin, subtree_end)
         return b
 
+    def to_bytes(self):
+        """`Write::write_polynomial_batch` bytes (polynomials, merkle_tree, degree_log, rate_bits, blinding)."""
+        L = load_library()
+        need = ctypes.c_uint64(0)
+        _check(L.qpzk_batch_serialized_size(self._h, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        _check(L.qpzk_batch_to_bytes(self._h, buf, need.value))
+        return buf.raw
+
+    @classmethod
+    def from_bytes(cls, ctx, data, verify=False):
+        """`Read::read_polynomial_batch`: the commitment goes to the device as stored, nothing is recomputed
+        (verify=True: the LDE and the tree are recomputed on the device and compared). Returns (batch, bytes read)."""
+        L = load_library()
+        data = bytes(data)
+        h, used = _vp(), ctypes.c_uint64(0)
+        _check(L.qpzk_batch_from_bytes(ctx._h, data, len(data), IMPORT_VERIFY if verify else 0, ctypes.byref(h),
+                                       ctypes.byref(used)))
+        b = PolynomialBatch(ctx, h, int(L.qpzk_batch_ncols(h)), int(L.qpzk_batch_degree_bits(h)), 0, 0, 0)
+        b.salt_cols = int(L.qpzk_batch_width(h)) - b.ncols
+        # rate_bits and cap_height sit at fixed places in the layout
+        n, w = 1 << b.degree_bits, b.ncols + b.salt_cols
+        off = 8 + b.ncols * 8 * (n + 1)
+        N = int.from_bytes(data[off:off + 8], "little")
+        b.rate_bits = N.bit_length() - 1 - b.degree_bits
+        off += 8 + N * 8 * (w + 1)
+        nd = int.from_bytes(data[off:off + 8], "little")
+        b.cap_height = int.from_bytes(data[off + 8 + 32 * nd:off + 16 + 32 * nd], "little")
+        return b, used.value
+
     def set_cap(self, cap):
         c = _arr(cap)
         if c.shape != (1 << self.cap_height, 4):
@@ -536,13 +574,20 @@ class Circuit:
     INFO = ("degree_bits", "rate_bits", "cap_height", "num_wires", "num_routed", "num_challenges", "salt_cols",
             "num_public_inputs")
 
-    def __init__(self, ctx, common_bytes, circuit_digest, constants_sigmas):
+    def __init__(self, ctx, common_bytes, circuit_digest, constants_sigmas=None, commitment=None, verify=False):
+        """constants_sigmas: the value columns (committed here, `build()`), or commitment: the serialized
+        `constants_sigmas_commitment` of a prover restored from files (uploaded as stored, `new_from_files`)."""
         L = load_library()
-        cs = _arr(constants_sigmas)
         dg = _arr(circuit_digest)
         h = _vp()
         cb = bytes(common_bytes)
-        _check(L.qpzk_circuit_create(ctx._h, cb, len(cb), _ptr(dg), cs.ctypes.data_as(_vp), cs.size, ctypes.byref(h)))
+        if commitment is not None:
+            cm = bytes(commitment)
+            _check(L.qpzk_circuit_create_from_commitment(ctx._h, cb, len(cb), _ptr(dg), cm, len(cm),
+                                                         IMPORT_VERIFY if verify else 0, ctypes.byref(h)))
+        else:
+            cs = _arr(constants_sigmas)
+            _check(L.qpzk_circuit_create(ctx._h, cb, len(cb), _ptr(dg), cs.ctypes.data_as(_vp), cs.size, ctypes.byref(h)))
         self.ctx, self._h, self.common = ctx, h, cb
         info = (ctypes.c_uint32 * 8)()
         _check(L.qpzk_circuit_info(h, info))
@@ -559,6 +604,15 @@ class Circuit:
         out = np.zeros((ncap, 4), np.uint64)
         _check(load_library().qpzk_circuit_cap(self._h, _ptr(out), out.size))
         return out
+
+    def commitment_bytes(self):
+        """The serialized `constants_sigmas_commitment` (the PolynomialBatch field of `ProverOnlyCircuitData::to_bytes`)."""
+        L = load_library()
+        need = ctypes.c_uint64(0)
+        _check(L.qpzk_circuit_commitment_size(self._h, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        _check(L.qpzk_circuit_commitment_to_bytes(self._h, buf, need.value))
+        return buf.raw
 
     def verifier_only_bytes(self):
         L = load_library()

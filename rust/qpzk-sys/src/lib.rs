@@ -64,12 +64,18 @@ extern "C" {
     pub fn qpzk_batch_get_lde_rows(b: *const qpzk_batch, idx: *const u32, nidx: u32, step: u32, out_: *mut u64) -> c_int;
     pub fn qpzk_batch_open(b: *const qpzk_batch, leaf_index: u64, leaf_out: *mut u64, siblings_out: *mut u64) -> c_int;
     pub fn qpzk_batch_export(b: *const qpzk_batch, leaves: *mut u64, digests: *mut u64) -> c_int;
+    pub fn qpzk_batch_serialized_size(b: *const qpzk_batch, nbytes: *mut u64) -> c_int;
+    pub fn qpzk_batch_to_bytes(b: *const qpzk_batch, out_: *mut u8, capacity: u64) -> c_int;
+    pub fn qpzk_batch_from_bytes(ctx: *mut qpzk_ctx, bytes: *const u8, nbytes: u64, flags: u32, out_: *mut *mut qpzk_batch, consumed: *mut u64) -> c_int;
     pub fn qpzk_batch_eval_ext(b: *const qpzk_batch, point: *const u64, out_: *mut u64) -> c_int;
     pub fn qpzk_batch_ncols(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_width(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_degree_bits(b: *const qpzk_batch) -> u32;
     pub fn qpzk_batch_free(b: *mut qpzk_batch);
     pub fn qpzk_circuit_create(ctx: *mut qpzk_ctx, common_bytes: *const u8, common_len: usize, circuit_digest: *const u64, constants_sigmas: *const u64, constants_sigmas_words: usize, out_: *mut *mut qpzk_circuit) -> c_int;
+    pub fn qpzk_circuit_create_from_commitment(ctx: *mut qpzk_ctx, common_bytes: *const u8, common_len: usize, circuit_digest: *const u64, commitment_bytes: *const u8, commitment_len: u64, flags: u32, out_: *mut *mut qpzk_circuit) -> c_int;
+    pub fn qpzk_circuit_commitment_size(c: *const qpzk_circuit, nbytes: *mut u64) -> c_int;
+    pub fn qpzk_circuit_commitment_to_bytes(c: *const qpzk_circuit, out_: *mut u8, capacity: u64) -> c_int;
     pub fn qpzk_circuit_cap(c: *const qpzk_circuit, out_: *mut u64, cap_words: usize) -> c_int;
     pub fn qpzk_circuit_info(c: *const qpzk_circuit, out_: *mut u32) -> c_int;
     pub fn qpzk_circuit_verifier_only(c: *const qpzk_circuit, out_: *mut u8, cap: usize) -> usize;

@@ -14,6 +14,19 @@ __global__ void k_chain(u64* st, int nperm, int variant) {
   for (int i = 0; i < nperm; i++) s = poseidon_permute_coop(s, lane, xch[g]);
   if (g == 0 && lane < 12) st[lane] = gl_canon(s);
 }
+// Many resident groups (the tree-climb regime: 4096 leaves x 17 permutations): every 16-lane group runs its own
+// chain. half_mask = 1: each half of a warp synchronises with its own 16-bit mask (k_tree_climb), 0: one
+// full-warp mask. Measured on B200: no difference (the halves stay in lockstep either way); what matters is the
+// number of resident warps per scheduler - 10.2 us per step at one warp per scheduler (148 blocks), 21.3 us at
+// 3.5 (512 blocks = 4096 groups), 34.4 us at 7: the 16-lane permutation saturates a scheduler at about two warps.
+__global__ void __launch_bounds__(128) k_chain_many(u64* st, int nperm, int half_mask) {
+  __shared__ u64 xch[8][COOP_XCH_WORDS];
+  const u32 g = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const u32 mask = half_mask ? 0xffffu << (threadIdx.x & 16) : 0xffffffffu;
+  u64 s = lane < 12 ? st[lane] + blockIdx.x * 8 + g : 0;
+  for (int i = 0; i < nperm; i++) s = poseidon_permute_coop(s, lane, xch[g], mask);
+  if (s == 0x123456789ULL) st[lane] = s;
+}
 __global__ void k_chain_thread(u64* st, int nperm) {
   u64 s[12];
   for (int i = 0; i < 12; i++) s[i] = st[i];
@@ -74,5 +87,19 @@ int main(int argc, char** argv) {
     printf("%s %s: %s  %.2f us per dependent permutation\n", argc > 1 ? argv[1] : "variant", mode == 0 ? "coop16" : "thread", bad ? "MISMATCH" : "ok",
            best * 1e3 / nperm);
   }
+  for (int hm = 0; hm < 2; hm++)
+    for (int blocks : {148, 512, 1024}) {
+      float best = 1e30f;
+      for (int it = 0; it < 3; it++) {
+        cudaEventRecord(e0);
+        k_chain_many<<<blocks, 128>>>(d, 17, hm);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+      }
+      printf("%d blocks x 8 groups x 17 dependent permutations, %s mask: %.1f us (%.2f us per step)\n", blocks,
+             hm ? "half-warp" : "full-warp", best * 1e3, best * 1e3 / 17);
+    }
   return 0;
 }
