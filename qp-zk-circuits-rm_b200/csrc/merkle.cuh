@@ -70,7 +70,9 @@ k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, u64 nout) {
 // per-level launches this replaces added a launch gap per level: 16 % of the GPU time of a proof sat in
 // ~1,300 such launches, profiles/r1_bench_launch_list_summary.txt). Counters are reset by the group that
 // consumes them, so one small per-context array serves every tree built on the context's stream.
+#ifndef QPZK_COOP_THREADS
 #define QPZK_COOP_THREADS 128
+#endif
 #define QPZK_COOP_GROUPS (QPZK_COOP_THREADS / 16)
 #define QPZK_CLIMB_MAX_START 8192  // most nodes a climb may start from (sizes the counter array: 2x this)
 
@@ -112,6 +114,13 @@ k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wi
     u64* out = levels + (twoN - (twoN >> l) + t) * 4;
     QPZK_CHECK(l <= log_n && t < (((u64)1 << log_n) >> l));
     if (lane < 4) out[lane] = gl_canon(s);
+#ifdef CLIMB_TL  // scripts/exp/climb_exp.cu: latest completion time per level
+    if (lane == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      atomicMax(&g_tl[l], now);
+    }
+#endif
     if (l >= top) break;
     // publish, then pair up with the sibling subtree
     __threadfence();
@@ -130,7 +139,19 @@ k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wi
     t >>= 1;
     const u64* in = levels + (twoN - (twoN >> (l - 1)) + 2 * t) * 4;
     s = lane < 8 ? __ldcg(in + lane) : 0;                            // L2: the sibling was written by another SM
+#ifdef CLIMB_TL
+    unsigned long long tp0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
+#endif
     s = poseidon_permute_coop(s, lane, xch[g], mask);
+#ifdef CLIMB_TL
+    if (lane == 0) {
+      unsigned long long tp1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
+      atomicMax(&g_pmax[l], tp1 - tp0);
+      atomicAdd(&g_psum[l], tp1 - tp0);
+    }
+#endif
   }
 }
 

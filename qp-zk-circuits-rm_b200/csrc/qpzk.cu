@@ -91,7 +91,7 @@ struct qpzk_ctx {
   std::map<std::tuple<int, int, bool>, u64*> tw_mats;    // (k, a, inverse) -> twiddle matrix [2^a][2^(k-a)]
   u64* scratch_path = nullptr;                           // small device scratch for openings
   u32* climb_counters = nullptr;                         // k_tree_climb arrival counters (all zero between launches)
-  u64 coop_max = 4096;                                   // most permutations per step for the 16-lane kernels
+  u64 coop_max = 1024;                                   // most permutations per step for the 16-lane kernels
   cudaMemPool_t pool = nullptr;                          // the library's own stream-ordered pool on this device
 };
 
@@ -381,16 +381,20 @@ static int launch_ifft(qpzk_ctx* c, const u64* values, u64 src_stride, u64* coef
 // Leaf digests + all levels down to the cap. Element (row, col) at src[row*rs + col*cs].
 // Above `coop_max` independent permutations a step runs one thread per permutation (throughput); at or below
 // it the rest of the tree - leaves included, if there are that few - is ONE k_tree_climb launch on the 16-lane
-// path. The 16-lane kernels spend ~3.8x the lane-instructions per permutation, so the threshold trades
-// single-proof latency against throughput with several proofs in flight. Measured with per-level launches
-// (2^14 ZK proof, 6 streams): 0 -> 171 proofs/s / 9.8 ms latency; 1024 -> 175 / 8.9; 4096 -> 175 / 8.8;
-// 8192 -> 171 / 8.8. QPZK_COOP_MAX (read once per process) overrides.
+// path. The 16-lane kernels spend ~3.8x the lane-instructions per permutation and a scheduler saturates at about
+// two of their warps (scripts/exp/coop_lat.cu: 10.2 us per step at one warp per scheduler, 21.3 us at 3.5), and in
+// a climb the LATER sibling goes on with the parent, so the groups that survive are the ones on the busiest SMs:
+// started from 4096 nodes, levels 2-5 take 27 us each instead of 10.7 (scripts/exp/climb_exp.cu). Starting the
+// climb at 1024 nodes and giving the levels above it to k_merkle_level is both faster and cheaper (2^14 ZK
+// proof, 8 streams; QPZK_COOP_MAX, read once per process, overrides):
+//   4096 -> 206.8 proofs/s, 8.14 ms single proof, 3.08 ms voting-sized proof
+//   2048 -> 211.6 / 7.96 / 3.00      1024 -> 215.3 / 7.94 / 2.97      512 -> 215.5 / 8.01 / 3.08
 // [leaf0, leaf0 + nleaves) restricts the work to a range of whole cap subtrees (multi-GPU shard); the
 // default is the whole tree.
 static u64 coop_max_from_env() {
   static const u64 v = [] {
     const char* e = getenv("QPZK_COOP_MAX");
-    u64 x = e ? strtoull(e, nullptr, 10) : 4096;
+    u64 x = e ? strtoull(e, nullptr, 10) : 1024;
     return x > QPZK_CLIMB_MAX_START ? (u64)QPZK_CLIMB_MAX_START : x;
   }();
   return v;
