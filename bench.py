@@ -612,6 +612,33 @@ def run_gpu(args, rank, local_rank, world):
         ctx0.dev_free(vd)
         vcirc.free()
 
+    # a prover restored from files (`new_from_files`, /root/reference/wormhole/prover/src/lib.rs:105-187)
+    # uploads the serialized constants_sigmas_commitment instead of recomputing it; both ways timed, same proof bytes
+    restored = None
+    if rank == 0:
+        blob = circuits[0].commitment_bytes()
+        t_new, t_restored = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            qa = qpzk.Circuit(ctx0, circ["common"], circ["digest"], circ["constants_sigmas"])
+            t_new.append((time.perf_counter() - t0) * 1e3)
+            qa.free()
+            t0 = time.perf_counter()
+            qb = qpzk.Circuit(ctx0, circ["common"], circ["digest"], commitment=blob)
+            t_restored.append((time.perf_counter() - t0) * 1e3)
+            if _ < 2:
+                qb.free()
+        same = qb.prove_dev(dev_w[0], circ["public_inputs"], dev_s[0]) == circuits[0].prove_dev(dev_w[0], circ["public_inputs"], dev_s[0])
+        qb.free()
+        if not same:
+            raise SystemExit("bench: a circuit restored from its serialized commitment proves different bytes")
+        restored = {"workload": "qpzk_circuit_create (commit 84 columns x 2^%d on the device) against "
+                                "qpzk_circuit_create_from_commitment (upload the serialized PolynomialBatch from pageable "
+                                "host memory, nothing recomputed)" % PROOF_K,
+                    "create_ms_min": float(np.min(t_new)), "from_commitment_ms_min": float(np.min(t_restored)),
+                    "commitment_bytes": len(blob), "same_proof_bytes": True}
+        del blob
+
     # BASELINE configs[4]: one aggregation-tree node - a recursion-shaped circuit (the 14-gate set an
     # in-circuit verifier instantiates, /root/reference/wormhole/aggregator/src/circuits/tree.rs:111-136) of
     # 2^13 rows, the size SURVEY 8(d) estimates for the reference's default binary tree nodes.
@@ -777,6 +804,8 @@ def run_gpu(args, rank, local_rank, world):
         line["commit_microbench"]["ms_at_2^k_rows"] = sweep
         if voting is not None:
             line["voting_single_proof"] = voting
+        if restored is not None:
+            line["circuit_restored_from_files"] = restored
         if aggregator is not None:
             line["aggregator_node_proof"] = aggregator
         if cpu is not None:
