@@ -20,6 +20,10 @@ pub const QPZK_CTX_BLOCKING_SYNC: u32 = 1;
 pub const QPZK_CTX_YIELD_SYNC: u32 = 2;
 pub const QPZK_EXCHANGE_ALLGATHER: u32 = 1;
 pub const QPZK_EXCHANGE_SUM: u32 = 2;
+pub const QPZK_IMPORT_VERIFY: u32 = 1;
+pub const QPZK_PROVE_TRACE: u32 = 1;
+pub const QPZK_PROVE_DEVICE_INPUTS: u32 = 2;
+pub const QPZK_PROVE_SEEDED_SALTS: u32 = 4;
 
 #[repr(C)] pub struct qpzk_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qpzk_batch { _p: [u8; 0] }

@@ -76,3 +76,61 @@ fn commit_matches_qp_plonky2() {
         qpzk_ctx_destroy(ctx);
     }
 }
+
+/// the byte layout of `write_polynomial_batch` is restated in libqpzk without a fixture (the
+/// reference ships no serialized prover data). This is the pin: the bytes real qp-plonky2 writes for a batch must
+/// equal `qpzk_batch_to_bytes` of the same commit, and `qpzk_batch_from_bytes` must accept them (with the
+/// on-device verification) and serve the same cap.
+#[test]
+fn serialized_batch_matches_qp_plonky2() {
+    use plonky2::util::serialization::{Buffer, Read, Write};
+    let (k, ncols, rate_bits, cap_height) = (10usize, 84usize, 3usize, 4usize);
+    let n = 1usize << k;
+    let flat = splitmix_trace(0x5eed_0003, ncols * n);
+    let values: Vec<PolynomialValues<F>> = flat
+        .chunks(n)
+        .map(|c| PolynomialValues::new(c.iter().map(|&v| F::from_canonical_u64(v)).collect()))
+        .collect();
+    let reference = PolynomialBatch::<F, C, 2>::from_values(
+        values, rate_bits, false, cap_height, &mut TimingTree::default(), None);
+    let mut want: Vec<u8> = Vec::new();
+    want.write_polynomial_batch(&reference).unwrap();
+
+    unsafe {
+        let mut ctx = core::ptr::null_mut();
+        assert_eq!(qpzk_ctx_create(0, 0, &mut ctx), QPZK_OK);
+        let mut batch = core::ptr::null_mut();
+        assert_eq!(
+            qpzk_batch_from_values(ctx, flat.as_ptr(), ncols as u32, k as u32, rate_bits as u32,
+                                   cap_height as u32, core::ptr::null(), 0, &mut batch),
+            QPZK_OK
+        );
+        let mut len = 0u64;
+        assert_eq!(qpzk_batch_serialized_size(batch, &mut len), QPZK_OK);
+        assert_eq!(len as usize, want.len());
+        let mut got = vec![0u8; len as usize];
+        assert_eq!(qpzk_batch_to_bytes(batch, got.as_mut_ptr(), len), QPZK_OK);
+        assert!(got == want, "serialized PolynomialBatch differs from qp-plonky2's");
+        // and back: qp-plonky2 reads ours, we read qp-plonky2's
+        let mut buf = Buffer::new(&got);
+        let back: PolynomialBatch<F, C, 2> = buf.read_polynomial_batch().unwrap();
+        assert_eq!(back.merkle_tree.cap, reference.merkle_tree.cap);
+        let mut restored = core::ptr::null_mut();
+        let mut used = 0u64;
+        assert_eq!(
+            qpzk_batch_from_bytes(ctx, want.as_ptr(), want.len() as u64, QPZK_IMPORT_VERIFY, &mut restored, &mut used),
+            QPZK_OK
+        );
+        assert_eq!(used as usize, want.len());
+        let mut cap = vec![0u64; 4 << cap_height];
+        assert_eq!(qpzk_batch_cap(restored, cap.as_mut_ptr()), QPZK_OK);
+        for (i, h) in reference.merkle_tree.cap.0.iter().enumerate() {
+            for j in 0..4 {
+                assert_eq!(h.elements[j].to_canonical_u64(), cap[4 * i + j]);
+            }
+        }
+        qpzk_batch_free(restored);
+        qpzk_batch_free(batch);
+        qpzk_ctx_destroy(ctx);
+    }
+}
