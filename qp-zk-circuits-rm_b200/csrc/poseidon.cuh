@@ -185,11 +185,28 @@ __constant__ double c_mds_half_d[12];  // (c[i] + c[i+6]) / 2 for i < 6, then (c
 // they enter as the accumulators' initial values, which costs nothing, and the 64-bit modular additions at
 // the head of the next round disappear.
 __constant__ double c_mds_next_rc_d[30][2][12];
-GL_DEV double u32_to_f64(u32 v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+// PV_CVT (experiment): 1 = int -> double with the conversion instruction (I2F.F64.U32, its own pipe) instead of
+// the bias trick (a register-pair move plus a DADD); 2 = also double -> int with F2I.U64.F64.
+#ifndef PV_CVT
+#define PV_CVT 0
+#endif
+GL_DEV double u32_to_f64(u32 v) {
+#if PV_CVT >= 1
+  return __uint2double_rn(v);
+#else
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#endif
+}
 GL_DEV void f64_to_u52(double d, u32& lo, u32& hi) {
+#if PV_CVT >= 2
+  const unsigned long long t = __double2ull_rz(d);  // the sums are non-negative integers below 2^42
+  lo = (u32)t;
+  hi = (u32)(t >> 32);
+#else
   const double t = d + 4503599627370496.0;
   lo = (u32)__double2loint(t);
   hi = (u32)__double2hiint(t) & 0xFFFFFu;
+#endif
 }
 // The 12x12 circulant product itself is split once by z^12 - 1 = (z^6 - 1)(z^6 + 1): with s = x_lo + x_hi and
 // d = x_lo - x_hi (x_lo = x[0..5], x_hi = x[6..11]), U = cyclic_6(s, (c_lo + c_hi)/2) and V = negacyclic_6(d,
