@@ -607,7 +607,7 @@ static int circuit_create_impl(qpzk_ctx* c, const uint8_t* common_bytes, size_t 
     CU(cudaMemcpyAsync(q->zh_dev, zh.data(), zh.size() * 8, cudaMemcpyHostToDevice, c->stream));
     QP(dev_alloc(c, (size_t)ncs * n * 8, &q->cs_values));
     if (constants_sigmas) {
-      CU(cudaMemcpyAsync(q->cs_values, constants_sigmas, (size_t)ncs * n * 8, cudaMemcpyHostToDevice, c->stream));
+      QP(h2d_copy(c, q->cs_values, constants_sigmas, (size_t)ncs * n * 8));
       // build(): PolynomialBatch::from_values(constants | sigmas), never blinded
       QP(commit_impl(c, q->cs_values, false, false, ncs, (u32)cm.degree_bits, (u32)cm.rate_bits, (u32)cm.cap_height, nullptr,
                      false, 0, &q->cs_batch));
@@ -1061,7 +1061,7 @@ struct qpzk_sprove {
     wires_dev = wires_in;
     if (!(flags & 2)) {
       QP(wires_up.alloc((size_t)d.num_wires * n * 8));
-      CU(cudaMemcpyAsync(wires_up.p, wires_in, (size_t)d.num_wires * n * 8, cudaMemcpyHostToDevice, c->stream));
+      QP(h2d_copy(c, wires_up.p, wires_in, (size_t)d.num_wires * n * 8));
       wires_dev = wires_up.p;
     }
     QP(commit(wires_dev, false, d.num_wires, salt_w, 0, &wires_b));

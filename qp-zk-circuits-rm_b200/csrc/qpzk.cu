@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,6 +19,7 @@
 #include <tuple>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/qpzk.h"
@@ -93,6 +95,11 @@ struct qpzk_ctx {
   u32* climb_counters = nullptr;                         // k_tree_climb arrival counters (all zero between launches)
   u64 coop_max = 1024;                                   // most permutations per step for the 16-lane kernels
   cudaMemPool_t pool = nullptr;                          // the library's own stream-ordered pool on this device
+  // uploads from pageable host memory (h2d_copy): two pinned staging buffers filled by h2d_threads host threads
+  void* h2d_arena = nullptr;       // [thread][2] chunks of kH2DChunk bytes
+  cudaEvent_t h2d_ev[32] = {};     // one per chunk: the copy engine has read it
+  int h2d_threads = 4;
+  size_t h2d_min = (size_t)32 << 20;
 };
 
 static void dev_free(qpzk_ctx* c, void* p);
@@ -539,6 +546,100 @@ static int device_init_once(int device) {
   return QPZK_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Host -> device on the context's stream. Pinned or registered memory is one asynchronous copy. From PAGEABLE memory
+// - what a Rust Vec<F> or a numpy array is - the driver stages through its own bounce buffer on the calling thread:
+// 11-12 GB/s on the B200 boxes against 55 GB/s from pinned memory, and a 2^18-row witness with its salts is 484 MB
+// (43 ms of a 121 ms proof). Above h2d_min bytes such a buffer therefore goes through pinned chunks of the
+// context's own, filled by h2d_threads host threads while earlier chunks are on the wire: 28-31 GB/s
+// (scripts/exp/h2d_bench.cu; below ~32 MB the driver's path is as fast).
+// The caller's buffer has been read completely when this returns. QPZK_H2D_THREADS (0 or 1 = always the driver's
+// path) and QPZK_H2D_MIN_MB override the defaults.
+static const size_t kH2DChunk = (size_t)2 << 20;  // per thread, two of them
+static const int kH2DMaxThreads = 16;
+static void h2d_config_from_env(qpzk_ctx* c) {
+  static const int threads = [] {
+    const char* e = getenv("QPZK_H2D_THREADS");
+    long v = e ? strtol(e, nullptr, 10) : 4;
+    return (int)(v < 0 ? 0 : v > kH2DMaxThreads ? kH2DMaxThreads : v);
+  }();
+  static const size_t min_bytes = [] {
+    const char* e = getenv("QPZK_H2D_MIN_MB");
+    unsigned long long v = e ? strtoull(e, nullptr, 10) : 32;
+    return (size_t)(v > 65536 ? 65536 : v) << 20;
+  }();
+  c->h2d_threads = threads;
+  c->h2d_min = min_bytes;
+}
+// Every thread owns a contiguous part of the buffer and two staging chunks: fill one, hand it to the copy engine,
+// fill the other. The threads share nothing but the stream (the copies of different threads may interleave in
+// any order; whatever is enqueued after this call comes after all of them), so there is no handshake between
+// them - an earlier version that had all threads fill ONE chunk together and meet per chunk showed
+// 200-500 ms stalls when a spinning thread lost its core.
+static int h2d_staged(qpzk_ctx* c, char* dst, const char* src, size_t bytes) {
+  const int T = c->h2d_threads;
+  if (!c->h2d_arena) CU(cudaHostAlloc(&c->h2d_arena, (size_t)2 * T * kH2DChunk, cudaHostAllocDefault));
+  for (int i = 0; i < 2 * T; i++)
+    if (!c->h2d_ev[i]) CU(cudaEventCreateWithFlags(&c->h2d_ev[i], cudaEventDisableTiming));
+  const size_t per = (((bytes + T - 1) / T) + 4095) & ~(size_t)4095;
+  static const bool trace = getenv("QPZK_H2D_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  std::atomic<int> first_err{(int)cudaSuccess};
+  auto work = [&](int t) {
+    const size_t beg = std::min(bytes, (size_t)t * per), end = std::min(bytes, beg + per);
+    if (t && cudaSetDevice(c->device) != cudaSuccess) {
+      int ok = (int)cudaSuccess;
+      first_err.compare_exchange_strong(ok, (int)cudaGetLastError());
+      return;
+    }
+    int j = 0;
+    for (size_t off = beg; off < end; off += kH2DChunk, j ^= 1) {
+      const size_t len = std::min(kH2DChunk, end - off);
+      char* buf = static_cast<char*>(c->h2d_arena) + (size_t)(2 * t + j) * kH2DChunk;
+      cudaEvent_t ev = c->h2d_ev[2 * t + j];
+      cudaError_t e = cudaEventSynchronize(ev);  // the copy that last read this chunk has left it
+      if (e == cudaSuccess) {
+        memcpy(buf, src + off, len);
+        e = cudaMemcpyAsync(dst + off, buf, len, cudaMemcpyHostToDevice, c->stream);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(ev, c->stream);
+      if (e != cudaSuccess) {
+        int ok = (int)cudaSuccess;
+        first_err.compare_exchange_strong(ok, (int)e);
+        return;
+      }
+    }
+  };
+  {
+    struct Joiner {
+      std::vector<std::thread> th;
+      ~Joiner() {
+        for (auto& t : th)
+          if (t.joinable()) t.join();
+      }
+    } workers;
+    workers.th.reserve(T - 1);
+    for (int t = 1; t < T; t++) workers.th.emplace_back(work, t);
+    work(0);
+  }
+  if (trace)
+    fprintf(stderr, "[qpzk] staged upload: %zu bytes, %d threads, %.2f ms\n", bytes, T,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  CU((cudaError_t)first_err.load());
+  return QPZK_OK;
+}
+static int h2d_copy(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
+  if (c->h2d_threads > 1 && bytes >= c->h2d_min) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, src);
+    if (e != cudaSuccess) cudaGetLastError();  // older drivers report plain host memory as an error: clear it
+    if (e != cudaSuccess || a.type == cudaMemoryTypeUnregistered)
+      return h2d_staged(c, static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+  }
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return QPZK_OK;
+}
+
 static void ctx_release(qpzk_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
@@ -559,6 +660,9 @@ static void ctx_release(qpzk_ctx* c) {
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->sync_ev) cudaEventDestroy(c->sync_ev);
+  for (auto& e : c->h2d_ev)
+    if (e) cudaEventDestroy(e);
+  if (c->h2d_arena) cudaFreeHost(c->h2d_arena);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -575,6 +679,7 @@ int qpzk_ctx_create(int device, uint32_t flags, qpzk_ctx** out) {
     c->device = device;
     for (auto& e : c->ev) e = nullptr;
     c->coop_max = coop_max_from_env();
+    h2d_config_from_env(c.get());
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -642,7 +747,7 @@ void qpzk_dev_free(qpzk_ctx* c, void* p) {
 int qpzk_memcpy_h2d(qpzk_ctx* c, void* dst, const void* src, size_t bytes) {
   if (!c || !dst || !src) return fail(QPZK_ERR_BAD_ARG, "NULL argument");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  QP(h2d_copy(c, dst, src, bytes));
   CU(ctx_wait(c));
   return QPZK_OK;
 }
@@ -841,7 +946,7 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
       QP(staging.alloc((size_t)ncols * n * 8));
       dstp = staging.p;
     }
-    CU(cudaMemcpyAsync(dstp, in, (size_t)ncols * n * 8, cudaMemcpyHostToDevice, c->stream));
+    QP(h2d_copy(c, dstp, in, (size_t)ncols * n * 8));
     src = dstp;
   } else if (is_coeffs) {
     CU(cudaMemcpyAsync(b->coeffs, in, (size_t)ncols * n * 8, cudaMemcpyDeviceToDevice, c->stream));
@@ -850,7 +955,7 @@ static int commit_impl(qpzk_ctx* c, const uint64_t* in, bool in_is_host, bool is
   const u64* salt_src = salts;
   if (salt_cols && salts_host) {
     QP(salt_staging.alloc((size_t)salt_cols * N * 8));
-    CU(cudaMemcpyAsync(salt_staging.p, salts, (size_t)salt_cols * N * 8, cudaMemcpyHostToDevice, c->stream));
+    QP(h2d_copy(c, salt_staging.p, salts, (size_t)salt_cols * N * 8));
     salt_src = salt_staging.p;
   }
   if (sync) CU(cudaEventRecord(ev[1], c->stream));
@@ -1219,7 +1324,7 @@ int qpzk_batch_from_bytes(qpzk_ctx* c, const uint8_t* bytes, uint64_t nbytes, ui
     {
       DevBuf rec(c), dig(c);
       QP(rec.alloc((size_t)N * (w + 1) * 8));
-      CU(cudaMemcpyAsync(rec.p, leaves0, (size_t)N * (w + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+      QP(h2d_copy(c, rec.p, leaves0, (size_t)N * (w + 1) * 8));
       k_rows_to_columns<<<dim3((unsigned)((N + 31) / 32), (w + 31) / 32), dim3(32, 8), 0, c->stream>>>(rec.p, b->lde, N, w);
       c->launches++;
       if (ndig) {
