@@ -792,9 +792,12 @@ def run_gpu(args, rank, local_rank, world):
                              # 32-bit IMAD peak they were counted as in SURVEY 8(d) (they execute as DFMA today)
                              "frac_class_weighted": alg["perms"] * (4308.0 / imad_wide + 2304.0 / imad_lo) / (hash_ms * 1e-3),
                              "frac_wide_multiplies_only": alg["perms"] * 4308.0 / imad_wide / (hash_ms * 1e-3),
-                             "ncu": {"source": "profiles/r1_leaf_hash_v5_twoplane_ncu_full.txt (k_leaf_hash, same kernel)",
-                                     "issue_slots_busy_pct": 60.9, "fmaheavy_pipe_pct": 75.8, "alu_pipe_pct": 49.6,
-                                     "fp64_pipe_pct": 15.7, "warp_instructions_per_permutation": 19800,
+                             "ncu": {"source": "profiles/r2_poseidon_base_ncu_full.txt (the permutation of k_leaf_hash in the "
+                                               "leaf-hash-shaped harness, 8.07 ms for the same 8.9 M permutations); "
+                                               "SASS histogram: profiles/r2_leaf_hash_sass_histogram.txt",
+                                     "issue_slots_busy_pct": 60.3, "fmaheavy_pipe_pct": 77.7, "alu_pipe_pct": 51.4,
+                                     "fp64_pipe_pct": 11.7, "eligible_warps_per_cycle": 2.04,
+                                     "warp_instructions_per_permutation": 19800,
                                      "limiter": "the FMA-heavy (integer multiply) pipe: 25.9 k pipe cycles per warp-permutation "
                                                 "(IMAD.WIDE / IMAD.HI hold it 4 cycles, other IMAD forms 2) of 33.6 k elapsed"},
                              "traffic": LEAF_HASH_DRAM_BYTES_PER_COMMIT,

@@ -90,7 +90,11 @@ int qpzk_ctx_stage_ms(qpzk_ctx* ctx, float* out_ms /* [QPZK_NUM_STAGES] */);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t qpzk_ctx_launch_count(const qpzk_ctx* ctx);
 
-/* Pinned host memory for callers that want full-speed transfers (optional). */
+/* Pinned host memory for callers that want full-speed transfers (optional: 55 GB/s on the B200 boxes).
+ * Host buffers handed to any entry point may also be ordinary pageable memory (a Rust Vec, a numpy array). From
+ * 32 MB up such a buffer is uploaded through pinned chunks owned by the context and filled by four host threads
+ * (28-35 GB/s instead of the driver's 11-12 GB/s; environment: QPZK_H2D_THREADS, 0 or 1 = always the driver's
+ * path; QPZK_H2D_MIN_MB). The buffer has been read completely when the call returns. */
 int qpzk_host_alloc(size_t bytes, void** out);
 void qpzk_host_free(void* p);
 /* Plain device memory helpers (used by the bench harness and tests for the `_dev` entry points). */
