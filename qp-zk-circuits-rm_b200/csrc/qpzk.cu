@@ -420,8 +420,21 @@ static int build_tree(qpzk_ctx* c, const u64* src, u64 rs, u64 cs, u32 width, u3
     if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
     return QPZK_OK;
   }
-  k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
-                                                                       levels + leaf0 * 4);
+  // Leaf rows up to QPZK_COOP_LEAF_MAX (default 4096) take the 16-lane sponge as well - the climb kernel told to stop at
+  // the leaves (cap_height = log_n) - although the levels above them start climbing only at coop_max nodes: 17 dependent
+  // permutations of a 135-column row cost 17 x 25 us on a thread each and 17 x 21 us on 16 lanes at 4096 rows (a
+  // voting-sized proof: 2.84 -> 2.74 ms); at 8192 rows the lanes are slower than the threads.
+  static const u64 coop_leaf_max = [] {
+    const char* e = getenv("QPZK_COOP_LEAF_MAX");
+    u64 x = e ? strtoull(e, nullptr, 10) : 4096;
+    return x > QPZK_CLIMB_MAX_START ? (u64)QPZK_CLIMB_MAX_START : x;
+  }();
+  if (nleaves <= coop_leaf_max && width > 4)
+    k_tree_climb<true><<<groups(nleaves), QPZK_COOP_THREADS, 0, c->stream>>>(src, rs, cs, width, levels, log_n, log_n, 0, leaf0,
+                                                                            nleaves, c->climb_counters);
+  else
+    k_leaf_hash<<<(unsigned)((nleaves + 127) / 128), 128, 0, c->stream>>>(src + leaf0 * rs, rs, cs, width, nleaves,
+                                                                         levels + leaf0 * 4);
   c->launches++;
   CU(cudaGetLastError());
   if (after_leaves) CU(cudaEventRecord(after_leaves, c->stream));
