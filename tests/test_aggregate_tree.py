@@ -18,14 +18,20 @@ def _node(level, index, children):
     return h.digest() * 4          # fixed-length "proof"
 
 
-def _run(rank, world, gather):
+def _run(rank, world, gather, grouped=False):
     order = []
 
     def begin(level, index, children, slot):
         order.append((level, index, slot))
         return (level, index, list(children))
 
-    root, levels = agg.aggregate_tree([bytes([i]) * 128 for i in range(8)], 2, begin, lambda h: _node(*h), rank, world, gather)
+    def prove_group(level, index, children, ranks):
+        # every rank of the group computes the same bytes, as the ranks of a sharded proof do
+        order.append((level, index, tuple(ranks)))
+        return _node(level, index, list(children))
+
+    root, levels = agg.aggregate_tree([bytes([i]) * 128 for i in range(8)], 2, begin, lambda h: _node(*h), rank, world, gather,
+                                      prove_group=prove_group if grouped else None)
     return root, levels, order
 
 
@@ -56,14 +62,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, grouped=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        root, levels, order = _run(rank, world, agg.torch_all_gather(128))
-        q.put((rank, root, [o[:2] for o in order]))
+        if grouped:
+            groups = agg.make_rank_groups(world, rank)
+            assert sorted(groups) == [2] and dist.get_world_size(groups[2]) == 2
+        root, levels, order = _run(rank, world, agg.torch_all_gather(128), grouped)
+        q.put((rank, root, [o if grouped else o[:2] for o in order]))
     finally:
         dist.destroy_process_group()
 
@@ -84,3 +93,37 @@ def test_gloo_world2_tree():
     # nodes are dealt round-robin: rank 0 proves the even nodes of every level (and the root), rank 1 the odd ones
     assert res[0][2] == [(0, 0), (0, 2), (1, 0), (2, 0)]
     assert res[1][2] == [(0, 1), (0, 3), (1, 1)]
+
+
+def test_ranks_per_node():
+    # 8 leaves, branching factor 2 -> levels of 4, 2, 1 nodes: idle ranks join the upper levels
+    assert [agg.ranks_per_node(c, 8) for c in (4, 2, 1)] == [2, 4, 8]
+    assert [agg.ranks_per_node(c, 4) for c in (4, 2, 1)] == [1, 2, 4]
+    assert [agg.ranks_per_node(c, 2) for c in (4, 2, 1)] == [1, 1, 2]
+    assert [agg.ranks_per_node(c, 1) for c in (4, 2, 1)] == [1, 1, 1]
+    assert agg.ranks_per_node(1, 16) == 8            # a proof shards by whole cosets: at most 8 ranks
+    assert agg.ranks_per_node(3, 8) == 2 and list(agg.node_ranks(2, 2)) == [4, 5]
+    assert agg.ranks_per_node(5, 8) == 1
+
+
+def test_single_rank_grouped_is_the_plain_schedule():
+    assert _run(0, 1, None, grouped=True)[0] == _run(0, 1, None)[0]
+
+
+def test_gloo_world2_tree_with_group_proofs():
+    """World 2: the levels of 4 and 2 nodes are dealt round-robin as before, the root is proved by BOTH ranks
+    together (prove_group), and every rank ends with the root of the single-process run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(rk, 2, port, q, True)) for rk in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in ps)
+    for p in ps:
+        p.join(30)
+    want_root, _, _ = _run(0, 1, None)
+    assert res[0][1] == want_root and res[1][1] == want_root
+    assert res[0][2] == [(0, 0, 0), (0, 2, 1), (1, 0, 0), (2, 0, (0, 1))]
+    assert res[1][2] == [(0, 1, 0), (0, 3, 1), (1, 1, 0), (2, 0, (0, 1))]
