@@ -454,41 +454,139 @@ __device__ u64 g_rc[372];  // lane-indexed reads: global/L1, not the constant ba
 // The constants of round r + 1 enter as the initial value of round r's MDS accumulators (their 32-bit halves
 // join the low / high column sums: free), and they are requested one round ahead, so neither the modular
 // addition nor the load sits on the dependent chain.
+#ifndef PV_COOP_LINEAR
+#define PV_COOP_LINEAR 1
+#endif
+// One full round: s-boxes in parallel lanes, exchange, circulant row; `rc` = the NEXT round's constant of this lane.
+GL_DEV u64 coop_round(u64 s, bool sbox_here, u64 rc, u32 lane, u32 li, bool act, u64* buf, u32 mask) {
+  if (sbox_here) s = sbox7(s);
+  if (act) {
+    buf[lane] = s;
+    buf[lane + 12] = s;
+  }
+  __syncwarp(mask);
+  const u64* row = buf + li;
+  u32 al0 = (u32)rc, al1 = 0, ah0 = (u32)(rc >> 32), ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    const u64 v0 = row[i], v1 = row[i + 1];
+    mad_wide(al0, al1, (u32)v0, c_mds_circ[i]);
+    mad_wide(ah0, ah1, (u32)(v0 >> 32), c_mds_circ[i]);
+    mad_wide(bl0, bl1, (u32)v1, c_mds_circ[i + 1]);
+    mad_wide(bh0, bh1, (u32)(v1 >> 32), c_mds_circ[i + 1]);
+  }
+  if (lane == 0) {
+    mad_wide(al0, al1, (u32)s, c_mds_diag0);
+    mad_wide(ah0, ah1, (u32)(s >> 32), c_mds_diag0);
+  }
+  u64 lo = (((u64)al1 << 32) | al0) + (((u64)bl1 << 32) | bl0);   // < 2^43: no overflow
+  u64 hi = (((u64)ah1 << 32) | ah0) + (((u64)bh1 << 32) | bh0);
+  return mds_combine((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+}
+
+#if PV_COOP_LINEAR
+// The 22 partial rounds without an MDS layer (poseidon_tables.hpp, build_linear_tables). In the textbook form a
+// partial round costs one warp as much as a full round - the s-box runs on lane 0 while 15 lanes wait, then the
+// whole exchange + circulant row - and a single warp's time is the number of instructions it issues
+// (profiles/r2_coop16_latency_vs_load.txt). Here the partial rounds are one linear recurrence driven by the s-box
+// outputs y_0..y_21: each lane keeps two unreduced dot-product accumulators (the 20 later s-box INPUTS x_2..x_21
+// and the 12 words of the state after round 25), a round is broadcast x_k -> y_k = x_k^7 in every lane -> two
+// multiply-adds -> fold of the accumulator that holds x_(k+1): ~115 instructions against ~185, plus 22
+// multiply-adds per lane to set the accumulators up from the state after round 3.
+__device__ u64 g_lin_p[2 * 11 * 16];
+__device__ u64 g_lin_c[2 * 16];
+__device__ u64 g_lin_coef[22 * 2 * 16];
+
+GL_DEV void acc_set(Acc160& a, u64 c) {
+  acc_init(a);
+  a.a0 = (u32)c;
+  a.a1 = (u32)(c >> 32);
+}
+GL_DEV u64 shfl16(u32 mask, u64 v, u32 src) {
+  u32 lo = __shfl_sync(mask, (u32)v, src, 16), hi = __shfl_sync(mask, (u32)(v >> 32), src, 16);
+  return ((u64)hi << 32) | lo;
+}
+
+// s = this lane's word of t_0 (state after round 3 with rc[4] added); returns its word of t_22 (rc[26] added).
+GL_DEV u64 coop_partial_rounds(u64 s, u32 lane, bool act, u64* buf, u32 mask) {
+  if (act) buf[lane] = s;
+  u64 c0 = __ldg(&g_lin_coef[lane]), c1 = __ldg(&g_lin_coef[16 + lane]);
+  Acc160 a0, a1;
+  acc_set(a0, __ldg(&g_lin_c[lane]));
+  acc_set(a1, __ldg(&g_lin_c[16 + lane]));
+  const u64 rcx = __ldg(&g_rc[60]);
+  u32 xl0 = (u32)rcx, xl1 = 0, xh0 = (u32)(rcx >> 32), xh1 = 0;  // x_1 = rc[5][0] + row 0 of the MDS matrix
+  __syncwarp(mask);
+#pragma unroll
+  for (int i = 1; i < 12; i++) {
+    const u64 v = buf[i];
+    acc_mac(a0, v, __ldg(&g_lin_p[(i - 1) * 16 + lane]));
+    acc_mac(a1, v, __ldg(&g_lin_p[(11 + i - 1) * 16 + lane]));
+    mad_wide(xl0, xl1, (u32)v, c_mds_circ[i]);
+    mad_wide(xh0, xh1, (u32)(v >> 32), c_mds_circ[i]);
+  }
+  // k = 0: x_0 is lane 0's word. From here on slot 0 is kept reduced (one multiply-add with a single fold per round:
+  // every round hands one of these accumulators on as the next s-box input, and all lanes execute that fold anyway),
+  // slot 1 stays an unreduced column accumulator until its first word is due (k = 17).
+  u64 y = sbox7(buf[0]);
+  u64 e0 = gl_mad(y, c0, acc_reduce(a0));
+  acc_mac(a1, y, c1);
+  c0 = __ldg(&g_lin_coef[32 + lane]);
+  c1 = __ldg(&g_lin_coef[48 + lane]);
+  mad_wide(xl0, xl1, (u32)y, c_mds_circ[0] + c_mds_diag0);
+  mad_wide(xh0, xh1, (u32)(y >> 32), c_mds_circ[0] + c_mds_diag0);
+  u64 x = mds_combine(xl0, xl1, xh0, xh1);
+  // k = 1..16: x_(k+1) is slot 0 of lane k - 1
+#pragma unroll 1
+  for (u32 k = 1; k <= 16; k++) {
+    y = sbox7(x);
+    e0 = gl_mad(y, c0, e0);
+    acc_mac(a1, y, c1);
+    c0 = __ldg(&g_lin_coef[(k + 1) * 32 + lane]);
+    c1 = __ldg(&g_lin_coef[(k + 1) * 32 + 16 + lane]);
+    x = shfl16(mask, e0, k - 1);
+  }
+  // k = 17..20: x_(k+1) is slot 1 of lane k - 5; slot 0 is spent
+  u64 e1 = acc_reduce(a1);
+#pragma unroll 1
+  for (u32 k = 17; k <= 20; k++) {
+    y = sbox7(x);
+    e1 = gl_mad(y, c1, e1);
+    c1 = __ldg(&g_lin_coef[(k + 1) * 32 + 16 + lane]);
+    x = shfl16(mask, e1, k - 5);
+  }
+  return gl_mad(sbox7(x), c1, e1);
+}
+#endif
+
 GL_DEV u64 poseidon_permute_coop(u64 s, u32 lane, u64* xch, u32 mask = 0xffffffffu) {
   const bool act = lane < 12;
   const u32 li = act ? lane : 0;
   s = pv_add_c(s, __ldg(&g_rc[li]));
   u64 rc_next = __ldg(&g_rc[12 + li]);
+#if PV_COOP_LINEAR
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+    const u64 rc = rc_next;
+    rc_next = __ldg(&g_rc[(r < 3 ? r + 2 : 27) * 12 + li]);  // the last trip fetches round 26's successor
+    s = coop_round(s, true, rc, lane, li, act, xch + (r & 1) * 24, mask);
+  }
+  s = coop_partial_rounds(s, lane, act, xch, mask);
+#pragma unroll 1
+  for (int r = 26; r < 30; r++) {
+    const u64 rc = rc_next;
+    rc_next = __ldg(&g_rc[(r < 28 ? r + 2 : 30) * 12 + li]);  // the last two trips read the zero padding
+    s = coop_round(s, true, rc, lane, li, act, xch + (r & 1) * 24, mask);
+  }
+#else
 #pragma unroll 1
   for (int r = 0; r < 30; r++) {
     const u64 rc = rc_next;
     rc_next = __ldg(&g_rc[(r < 28 ? r + 2 : 30) * 12 + li]);  // the last two trips read the zero padding
     const bool full = r < 4 || r >= 26;
-    if (full || lane == 0) s = sbox7(s);
-    u64* buf = xch + (r & 1) * 24;
-    if (act) {
-      buf[lane] = s;
-      buf[lane + 12] = s;
-    }
-    __syncwarp(mask);
-    const u64* row = buf + li;
-    u32 al0 = (u32)rc, al1 = 0, ah0 = (u32)(rc >> 32), ah1 = 0, bl0 = 0, bl1 = 0, bh0 = 0, bh1 = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i += 2) {
-      const u64 v0 = row[i], v1 = row[i + 1];
-      mad_wide(al0, al1, (u32)v0, c_mds_circ[i]);
-      mad_wide(ah0, ah1, (u32)(v0 >> 32), c_mds_circ[i]);
-      mad_wide(bl0, bl1, (u32)v1, c_mds_circ[i + 1]);
-      mad_wide(bh0, bh1, (u32)(v1 >> 32), c_mds_circ[i + 1]);
-    }
-    if (lane == 0) {
-      mad_wide(al0, al1, (u32)s, c_mds_diag0);
-      mad_wide(ah0, ah1, (u32)(s >> 32), c_mds_diag0);
-    }
-    u64 lo = (((u64)al1 << 32) | al0) + (((u64)bl1 << 32) | bl0);   // < 2^43: no overflow
-    u64 hi = (((u64)ah1 << 32) | ah0) + (((u64)bh1 << 32) | bh0);
-    s = mds_combine((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+    s = coop_round(s, full || lane == 0, rc, lane, li, act, xch + (r & 1) * 24, mask);
   }
+#endif
   return s;
 }
 

@@ -25,6 +25,10 @@ struct PoseidonTablesHost {
   // (constants, s-box on lane 0, dense MDS) and only the remaining 22 - dense in the sparse form.
   int dense;
   u64 h_first[12], h_rc[22], h_init[121], h_w_hat[242], h_v[242];
+  // Linearised partial rounds for the 16-lane permutation (build_linear_tables): 32 accumulators, two per lane.
+  u64 lin_p[2][11][16];    // [slot][i - 1][lane]: coefficient of t0[i], i = 1..11
+  u64 lin_c[2][16];        // [slot][lane]: the constant term
+  u64 lin_coef[22][2][16]; // [k][slot][lane]: coefficient of y_k
 };
 
 static const u64 kMdsCirc[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -179,6 +183,52 @@ static inline void build_sparse_tables(const u64* rc, const detail::Mx& Mt, cons
   }
 }
 
+// The 22 partial rounds as ONE linear recurrence driven by the 22 s-box outputs (poseidon_permute_coop).
+// With t_k the state of partial round k after its constants (t_0 = the state entering round 4 plus rc[4]),
+// x_k = t_k[0], y_k = x_k^7, A = the MDS matrix with its first column zeroed and m0 that first column,
+//     t_(k+1) = A t_k + m0 y_k + rc[5 + k]             (k = 0..21; t_22 enters the s-boxes of round 26)
+// so every x_m and every word of t_22 is an affine function of t_0[1..11] and of y_0..y_(m-1):
+//     x_m  = row_0(A^m) t_0 + sum_(j<m) (row_0(A^(m-1-j)) m0) y_j + sum_(j<m) row_0(A^(m-1-j)) rc[5 + j]
+//     t_22 = A^22 t_0       + sum_(j<22) (A^(21-j) m0) y_j      + sum_(j<22) A^(21-j) rc[5 + j]
+// Column 0 of A^m is zero, so t_0[0] enters only through y_0. x_1 has small coefficients (row 0 of the MDS
+// matrix) and is computed by every lane; the other 20 + 12 accumulators sit two per lane:
+//   slot 0, lane L       : x_(L+2)            (x_2 .. x_17)
+//   slot 1, lane L < 12  : t_22[L]
+//   slot 1, lane L >= 12 : x_(L+6)            (x_18 .. x_21)
+// A coefficient of y_k in an x_m with m <= k (already consumed) is zero.
+static inline void build_linear_tables(PoseidonTablesHost* T, const detail::Mx& M) {
+  using namespace detail;
+  const int W = 12;
+  Mx A = M;
+  u64 m0[12];
+  for (int r = 0; r < W; r++) {
+    m0[r] = M[r * W];
+    A[r * W] = 0;
+  }
+  std::vector<Mx> P(23);
+  P[0] = Mx(W * W, 0);
+  for (int i = 0; i < W; i++) P[0][i * W + i] = 1;
+  for (int d = 1; d <= 22; d++) P[d] = mx_mul(A, P[d - 1], W);
+  auto row_dot = [&](const Mx& X, int row, const u64* v) {
+    u64 s = 0;
+    for (int c = 0; c < W; c++) s = glh::add(s, glh::mul(X[row * W + c], v[c]));
+    return s;
+  };
+  // accumulator `slot` of `lane` is row `row` of the state m rounds in (m = 22: the output)
+  for (int slot = 0; slot < 2; slot++)
+    for (int lane = 0; lane < 16; lane++) {
+      int m, row;
+      if (slot == 0) m = lane + 2, row = 0;
+      else if (lane < 12) m = 22, row = lane;
+      else m = lane + 6, row = 0;
+      for (int i = 1; i < W; i++) T->lin_p[slot][i - 1][lane] = P[m][row * W + i];
+      u64 c = 0;
+      for (int j = 0; j < m; j++) c = glh::add(c, row_dot(P[m - 1 - j], row, T->rc + 12 * (5 + j)));
+      T->lin_c[slot][lane] = c;
+      for (int k = 0; k < 22; k++) T->lin_coef[k][slot][lane] = k < m ? row_dot(P[m - 1 - k], row, m0) : 0;
+    }
+}
+
 static inline void build_poseidon_tables(PoseidonTablesHost* T, int dense = 0) {
   using namespace detail;
   typedef unsigned __int128 u128;
@@ -207,6 +257,7 @@ static inline void build_poseidon_tables(PoseidonTablesHost* T, int dense = 0) {
   build_sparse_tables(T->rc, Mt, Minv, 0, T->fast_first, T->fast_rc, T->fast_init, T->fast_w_hat, T->fast_v);
   T->dense = dense;
   build_sparse_tables(T->rc, Mt, Minv, dense, T->h_first, T->h_rc, T->h_init, T->h_w_hat, T->h_v);
+  build_linear_tables(T, M);
 }
 
 // Constants added by FP64 MDS layer L on behalf of the round that follows it, as the 32-bit halves of each word

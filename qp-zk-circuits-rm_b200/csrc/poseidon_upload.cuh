@@ -20,6 +20,11 @@ static inline cudaError_t poseidon_upload_tables(const PoseidonTablesHost& T) {
     for (int i = 0; i < 372; i++) rc_padded[i] = i < 360 ? T.rc[i] : 0;
     QPZK_UP(g_rc, rc_padded, sizeof rc_padded);
   }
+#if PV_COOP_LINEAR
+  QPZK_UP(g_lin_p, T.lin_p, sizeof T.lin_p);
+  QPZK_UP(g_lin_c, T.lin_c, sizeof T.lin_c);
+  QPZK_UP(g_lin_coef, T.lin_coef, sizeof T.lin_coef);
+#endif
   QPZK_UP(c_fast_first, T.fast_first, sizeof T.fast_first);
   QPZK_UP(c_fast_rc, T.fast_rc, sizeof T.fast_rc);
   QPZK_UP(c_fast_init, T.fast_init, sizeof T.fast_init);
