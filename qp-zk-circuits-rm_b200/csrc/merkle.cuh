@@ -100,8 +100,10 @@ k_tree_climb(const u64* __restrict__ src, u64 row_stride, u64 col_stride, u32 wi
     if (width <= 4) {  // hash_or_noop: short rows are copied, zero padded
       if (lane < width) s = p[lane * col_stride];
     } else {
+      u64 nxt = lane < 8 && lane < width ? __ldg(p + (u64)lane * col_stride) : 0;
       for (u32 off = 0; off < width; off += 8) {
-        if (lane < 8 && off + lane < width) s = __ldg(p + (u64)(off + lane) * col_stride);  // overwrite-mode absorb
+        if (lane < 8 && off + lane < width) s = nxt;  // overwrite-mode absorb
+        if (lane < 8 && off + 8 + lane < width) nxt = __ldg(p + (u64)(off + 8 + lane) * col_stride);  // one chunk ahead
         s = poseidon_permute_coop(s, lane, xch[g], mask);
       }
     }

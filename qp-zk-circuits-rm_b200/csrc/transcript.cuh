@@ -72,11 +72,14 @@ GL_DEV void sponge_duplex(CoopSponge& sp, u32 lane, u64* xch) {
 GL_DEV void sponge_observe(CoopSponge& sp, u32 lane, u64* xch, const u64* __restrict__ src, u32 n, u32 src_mode, u64 m,
                            u64* __restrict__ copy) {
   u32 i = 0;
+  u64 pre = 0;         // this lane's element of the chunk that follows a permutation, requested BEFORE the
+  bool have_pre = false;  // permutation so that its global-memory latency hides behind the ~6.5 us of arithmetic
+  auto fetch = [&](u32 e) { return src_mode ? src[(u64)(e & 1) * m + (e >> 1)] : src[e]; };
   while (i < n) {
     const u32 room = 8 - sp.in_len, take = n - i < room ? n - i : room;
     if (lane >= sp.in_len && lane < sp.in_len + take) {
       const u32 e = i + lane - sp.in_len;
-      u64 v = src_mode ? src[(u64)(e & 1) * m + (e >> 1)] : src[e];
+      u64 v = have_pre ? pre : fetch(e);
       v = gl_canon(v);
       sp.s = v;
       if (copy) copy[e] = v;
@@ -84,7 +87,14 @@ GL_DEV void sponge_observe(CoopSponge& sp, u32 lane, u64* xch, const u64* __rest
     sp.in_len += take;
     sp.out_len = 0;
     i += take;
-    if (sp.in_len == 8) sponge_duplex(sp, lane, xch);
+    have_pre = false;
+    if (sp.in_len == 8) {
+      if (i < n) {  // after the permutation in_len is 0: lane l takes element i + l
+        if (lane < 8 && i + lane < n) pre = fetch(i + lane);
+        have_pre = true;
+      }
+      sponge_duplex(sp, lane, xch);
+    }
   }
 }
 GL_DEV u64 sponge_get(CoopSponge& sp, u32 lane, u64* xch) {
