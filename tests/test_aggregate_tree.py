@@ -70,7 +70,8 @@ def _worker(rank, world, port, q, grouped=False):
     try:
         if grouped:
             groups = agg.make_rank_groups(world, rank)
-            assert sorted(groups) == [2] and dist.get_world_size(groups[2]) == 2
+            assert sorted(groups) == [g for g in (2, 4, 8) if g <= world]
+            assert all(dist.get_world_size(groups[g]) == g for g in groups)
         root, levels, order = _run(rank, world, agg.torch_all_gather(128), grouped)
         q.put((rank, root, [o if grouped else o[:2] for o in order]))
     finally:
@@ -127,3 +128,23 @@ def test_gloo_world2_tree_with_group_proofs():
     assert res[0][1] == want_root and res[1][1] == want_root
     assert res[0][2] == [(0, 0, 0), (0, 2, 1), (1, 0, 0), (2, 0, (0, 1))]
     assert res[1][2] == [(0, 1, 0), (0, 3, 1), (1, 1, 0), (2, 0, (0, 1))]
+
+
+def test_gloo_world4_tree_with_group_proofs():
+    """World 4 (the shape of the 4- and 8-GPU runs: sub-groups of different sizes on different levels): the level
+    of 4 nodes is one node per rank, the level of 2 nodes is proved by the rank pairs (0, 1) and (2, 3), the root by
+    all four ranks, and every rank ends with the root of the single-process run."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(rk, 4, port, q, True)) for rk in range(4)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(30)
+    want_root, _, _ = _run(0, 1, None)
+    assert all(r[1] == want_root for r in res)
+    for rk in range(4):
+        assert res[rk][2] == [(0, rk, 0), (1, rk // 2, (2 * (rk // 2), 2 * (rk // 2) + 1)), (2, 0, (0, 1, 2, 3))]
