@@ -669,7 +669,25 @@ k_eval_at_ext(const u64* __restrict__ coeffs, u64 n, u64 chunk, const u64* __res
   Acc160 a, b;
   acc_init(a);
   acc_init(b);
-  for (u64 m = lo + threadIdx.x; m < hi; m += blockDim.x) {
+  // four coefficients (and their powers) requested before the first multiply-add: with one CTA per polynomial the
+  // loop was a chain of dependent-latency loads (37 us per launch at 2^14 coefficients, 5 launches per proof)
+  u64 m = lo + threadIdx.x;
+  const u64 st = blockDim.x;
+  for (; m + 3 * st < hi; m += 4 * st) {
+    u64 v[4], p0[4], p1[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      v[j] = c[m + j * st];
+      p0[j] = pw[2 * (m + j * st)];
+      p1[j] = pw[2 * (m + j * st) + 1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      acc_mac(a, v[j], p0[j]);
+      acc_mac(b, v[j], p1[j]);
+    }
+  }
+  for (; m < hi; m += st) {
     u64 v = c[m];
     acc_mac(a, v, pw[2 * m]);
     acc_mac(b, v, pw[2 * m + 1]);
@@ -719,12 +737,27 @@ k_fri_compose(PolyList pl, u64 n, const u64* __restrict__ apow, u64* __restrict_
   acc_init(a);
   acc_init(b);
   u32 j = 0;
-  for (u32 o = 0; o < pl.noracles; o++)
-    for (u32 p = 0; p < pl.count[o]; p++, j++) {
-      u64 v = pl.base[o][(u64)p * n + m];
+  for (u32 o = 0; o < pl.noracles; o++) {
+    // four columns requested ahead of their multiply-adds (the loop was one dependent-latency load per polynomial:
+    // 115 us for the 257 polynomials of a wormhole proof)
+    const u64* col = pl.base[o] + m;
+    u32 p = 0;
+    for (; p + 3 < pl.count[o]; p += 4, j += 4) {
+      u64 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) v[i] = col[(u64)(p + i) * n];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        acc_mac(a, v[i], apow[2 * (j + i)]);
+        acc_mac(b, v[i], apow[2 * (j + i) + 1]);
+      }
+    }
+    for (; p < pl.count[o]; p++, j++) {
+      u64 v = col[(u64)p * n];
       acc_mac(a, v, apow[2 * j]);
       acc_mac(b, v, apow[2 * j + 1]);
     }
+  }
   comp[m] = acc_reduce(a);
   comp[n + m] = acc_reduce(b);
 }

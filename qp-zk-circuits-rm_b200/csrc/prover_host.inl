@@ -445,11 +445,12 @@ static int grind_pow(qpzk_ctx* c, const PowState& ps, u32 pos, u32 min_lz, u64* 
   return QPZK_OK;
 }
 
-// OpeningSet::new for `npolys` coefficient columns at the point whose powers are pw: polynomials longer than 2^15
-// coefficients are split over several CTAs (k_eval_at_ext / k_eval_reduce)
+// OpeningSet::new for `npolys` coefficient columns at the point whose powers are pw: polynomials longer than 2^12
+// coefficients are split over several CTAs (k_eval_at_ext / k_eval_reduce): a batch of 2 to 135 polynomials leaves most
+// SMs idle, and what one CTA takes is the latency of its chain of loads
 static int launch_eval_at_ext(qpzk_ctx* c, const u64* coeffs, u32 npolys, u64 n, const u64* pw, u64* out) {
   if (!npolys) return QPZK_OK;
-  const u64 chunk = n > (1ull << 15) ? (1ull << 13) : n;
+  const u64 chunk = n > (1ull << 15) ? (1ull << 13) : (n > (1ull << 12) ? (1ull << 12) : n);
   const u32 chunks = (u32)((n + chunk - 1) / chunk);
   if (chunks == 1) {
     k_eval_at_ext<<<dim3(npolys, 1), 256, 0, c->stream>>>(coeffs, n, chunk, pw, out, nullptr);
