@@ -145,3 +145,73 @@ def proof_digest(proof):
     """Short stand-in for "the parent's witness depends on this child" in tests of the schedule."""
     a = np.frombuffer(proof, dtype=np.uint8).astype(np.uint64)
     return int((a * (np.arange(a.size, dtype=np.uint64) + np.uint64(1))).sum() & np.uint64(0xFFFFFFFFFFFF))
+
+
+# ---- the aggregator's operator interface (host side of the aggregation path) ----
+DEFAULT_TREE_BRANCHING_FACTOR = 2   # tree.rs:17
+DEFAULT_TREE_DEPTH = 3              # tree.rs:20
+
+
+class AggregatorError(Exception):
+    """What the reference reports with `anyhow::bail!` (aggregator.rs:53-55, 76-78; util.rs:18-20)."""
+
+
+class TreeAggregationConfig:
+    """`TreeAggregationConfig::new` (/root/reference/wormhole/aggregator/src/circuits/tree.rs:31-52):
+    num_leaf_proofs = tree_branching_factor ^ tree_depth; the default is 2 ^ 3 = 8 leaves."""
+
+    def __init__(self, tree_branching_factor=DEFAULT_TREE_BRANCHING_FACTOR, tree_depth=DEFAULT_TREE_DEPTH):
+        if tree_branching_factor < 2 or tree_depth < 1:
+            raise ValueError("need a branching factor of at least 2 and a depth of at least 1")
+        self.tree_branching_factor = int(tree_branching_factor)
+        self.tree_depth = int(tree_depth)
+        self.num_leaf_proofs = self.tree_branching_factor ** self.tree_depth
+
+
+def pad_with_dummy_proofs(proofs, proof_len, dummy_proof):
+    """`pad_with_dummy_proofs` (/root/reference/wormhole/aggregator/src/util.rs:11-30): the buffer is filled up to
+    `proof_len` proofs with copies of the dummy proof the reference ships (aggregator/data/dummy_proof[_zk].bin,
+    passed in by the caller as bytes); more than `proof_len` proofs is an error."""
+    proofs = list(proofs)
+    if len(proofs) > proof_len:
+        raise AggregatorError("proofs to aggregate was more than the maximum allowed")
+    if len(proofs) < proof_len and dummy_proof is None:
+        raise AggregatorError("failed to deserialize dummy proof")
+    return proofs + [dummy_proof] * (proof_len - len(proofs))
+
+
+class WormholeProofAggregator:
+    """Host-side mirror of `WormholeProofAggregator` (/root/reference/wormhole/aggregator/src/aggregator.rs:13-93):
+    the same buffer semantics and error behaviour, with `aggregate` running the tree schedule of this module over
+    the ranks and contexts of the caller instead of `aggregate_to_tree`'s rayon fan-out. Proofs are serialized
+    `ProofWithPublicInputs` bytes. Building a node circuit and its witness from the children stays with the caller
+    (`begin_node` / `end_node` / `prove_group`, see `aggregate_tree`)."""
+
+    def __init__(self, config=None, dummy_proof=None):
+        self.config = config if config is not None else TreeAggregationConfig()
+        self.dummy_proof = dummy_proof
+        self.proofs_buffer = []          # Some(Vec::with_capacity(num_leaf_proofs)), aggregator.rs:30
+
+    def with_config(self, config):
+        self.config = config
+        return self
+
+    def push_proof(self, proof):
+        """aggregator.rs:51-63: an error once the buffer holds num_leaf_proofs; after `aggregate` took the buffer a
+        push starts a new one."""
+        if self.proofs_buffer is not None:
+            if len(self.proofs_buffer) >= self.config.num_leaf_proofs:
+                raise AggregatorError("tried to add proof when proof buffer is full")
+            self.proofs_buffer.append(proof)
+        else:
+            self.proofs_buffer = [proof]
+
+    def aggregate(self, begin_node, end_node, rank=0, world=1, all_gather=None, prove_group=None, max_ranks=8):
+        """aggregator.rs:74-92: takes the buffer, pads it with dummy proofs and reduces it to the root proof.
+        Returns (root proof, [proof lists per level])."""
+        if self.proofs_buffer is None:
+            raise AggregatorError("there are no proofs to aggregate")
+        proofs, self.proofs_buffer = self.proofs_buffer, None
+        padded = pad_with_dummy_proofs(proofs, self.config.num_leaf_proofs, self.dummy_proof)
+        return aggregate_tree(padded, self.config.tree_branching_factor, begin_node, end_node, rank, world, all_gather,
+                              prove_group=prove_group, max_ranks=max_ranks)

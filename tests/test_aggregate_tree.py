@@ -148,3 +148,70 @@ def test_gloo_world4_tree_with_group_proofs():
     assert all(r[1] == want_root for r in res)
     for rk in range(4):
         assert res[rk][2] == [(0, rk, 0), (1, rk // 2, (2 * (rk // 2), 2 * (rk // 2) + 1)), (2, 0, (0, 1, 2, 3))]
+
+
+# ---- the operator interface: buffer semantics of /root/reference/wormhole/tests/src/aggregator/aggregator_tests.rs ----
+def _aggregator(**kw):
+    return agg.WormholeProofAggregator(dummy_proof=b"\xdd" * 128, **kw)
+
+
+def _aggregate(a):
+    def begin(level, index, children, slot):
+        return (level, index, list(children))
+
+    return a.aggregate(begin, lambda h: _node(*h))
+
+
+def test_tree_aggregation_config_defaults():
+    c = agg.TreeAggregationConfig()                      # tree.rs:17-20, 31-52
+    assert (c.tree_branching_factor, c.tree_depth, c.num_leaf_proofs) == (2, 3, 8)
+    assert agg.TreeAggregationConfig(8, 1).num_leaf_proofs == 8 and agg.TreeAggregationConfig(4, 2).num_leaf_proofs == 16
+
+
+def test_push_proof_to_buffer():                         # aggregator_tests.rs:10-22
+    a = _aggregator()
+    a.push_proof(b"\x01" * 128)
+    assert len(a.proofs_buffer) == 1
+
+
+def test_push_proof_to_full_buffer():                    # aggregator_tests.rs:24-43
+    a = _aggregator()
+    for _ in range(a.config.num_leaf_proofs):
+        a.push_proof(b"\x01" * 128)
+    with pytest.raises(agg.AggregatorError, match="proof buffer is full"):
+        a.push_proof(b"\x01" * 128)
+    assert len(a.proofs_buffer) == a.config.num_leaf_proofs
+
+
+def test_aggregate_pads_with_dummy_proofs_and_takes_the_buffer():
+    """aggregate_single_proof / aggregate_proofs_into_tree (aggregator_tests.rs:45-100): one pushed proof is padded
+    to 8 leaves with the dummy proof and reduced by 4 + 2 + 1 node proofs; the buffer is gone afterwards."""
+    a = _aggregator()
+    a.push_proof(b"\x01" * 128)
+    root, levels = _aggregate(a)
+    assert [len(l) for l in levels] == [4, 2, 1]
+    want = agg.aggregate_tree([b"\x01" * 128] + [b"\xdd" * 128] * 7, 2, lambda l, i, c, s: (l, i, list(c)),
+                              lambda h: _node(*h))[0]
+    assert root == want
+    assert a.proofs_buffer is None
+    with pytest.raises(agg.AggregatorError, match="no proofs to aggregate"):
+        _aggregate(a)
+    a.push_proof(b"\x02" * 128)                          # aggregator.rs:58-60: a push after `take` starts a new buffer
+    assert a.proofs_buffer == [b"\x02" * 128]
+
+
+def test_aggregate_full_buffer_needs_no_dummy_and_flat_config():
+    a = agg.WormholeProofAggregator().with_config(agg.TreeAggregationConfig(8, 1))   # tree.rs:39-46: one flat 8-ary node
+    for i in range(8):
+        a.push_proof(bytes([i]) * 128)
+    root, levels = _aggregate(a)
+    assert [len(l) for l in levels] == [1] and root == _node(0, 0, [bytes([i]) * 128 for i in range(8)])
+    b = agg.WormholeProofAggregator()                    # no dummy proof supplied and a short buffer
+    b.push_proof(b"\x01" * 128)
+    with pytest.raises(agg.AggregatorError, match="dummy proof"):
+        _aggregate(b)
+
+
+def test_pad_rejects_too_many_proofs():                  # util.rs:18-20
+    with pytest.raises(agg.AggregatorError, match="more than the maximum"):
+        agg.pad_with_dummy_proofs([b"x"] * 9, 8, b"d")
