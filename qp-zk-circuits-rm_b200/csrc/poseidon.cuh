@@ -438,9 +438,11 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
 // dependent-ish instructions = ~50 us. Small Merkle levels, FRI trees and voting-sized commits have too
 // few permutations to fill the machine, so their time is that latency times the number of dependent
 // steps. Here the 12 s-boxes of a full round run in parallel lanes and the MDS row of each lane reads
-// the other 11 words from a shared-memory exchange: ~4.8k serial instructions per permutation. Every
-// round is executed in the textbook form (constants, s-box on all lanes or on lane 0, MDS) - the same
-// permutation as the sparse partial-round form, so results are bit-identical.
+// the other 11 words from a shared-memory exchange. The eight full rounds are executed in the textbook
+// form (constants, s-boxes, MDS); the 22 partial rounds as one linear recurrence driven by the s-box
+// outputs (coop_partial_rounds below; PV_COOP_LINEAR=0 restores the textbook partial rounds): ~4.2k serial
+// instructions per permutation, 6.5 us. The same permutation as the sparse partial-round form of the
+// throughput kernel, so results are bit-identical.
 __device__ u64 g_rc[372];  // lane-indexed reads: global/L1, not the constant bank (divergent index); 12 zeros appended
 #define COOP_XCH_WORDS 48
 
